@@ -1,0 +1,221 @@
+/*
+ * rlic_b200 — C ABI of the B200-native line integral convolution library
+ * (librlic_b200.so, built from rlic_b200/csrc/ for sm_100a).
+ *
+ * This is the drop-in boundary for the one native seam of the reference:
+ * the PyO3 module `rlic._core` with its two functions
+ *     convolve_f32(texture, (u, v, uv_mode), kernel, ((xl,xr),(yl,yr)), iterations)
+ *     convolve_f64(...)
+ * declared at /root/reference/src/lib.rs:451-482 (typed in
+ * /root/reference/src/rlic/_core.pyi:8-29) and called from
+ * /root/reference/src/rlic/_lib.py:228-235.  A maintainer binds these entry
+ * points with ctypes; rlic_b200/_core.py is that binding.
+ *
+ * Conventions
+ *   - plain C types only: pointers, int, int64_t; no torch / CUDA types
+ *     (a CUDA stream is passed as void*)
+ *   - images are C-contiguous, `ny` rows by `nx` columns; x is the column axis
+ *     (parallel to u), y the row axis (parallel to v)   [_lib.py:78-79]
+ *   - uv_mode:   0 = "velocity", 1 = "polarization"      [lib.rs:19-26]
+ *   - boundary:  0 = "closed",   1 = "periodic"          [lib.rs:60-67]
+ *   - every function returns 0 on success or an RLIC_B200_E* code; the message
+ *     is available from rlic_b200_last_error() on the calling thread.  Nothing
+ *     aborts the process (the reference panics->aborts on bad enums and on an
+ *     empty kernel, lib.rs:24,65,371; Cargo.toml:23).
+ *   - re-entrant: no mutable global state besides per-device caches guarded by
+ *     a mutex; each call runs on its own stream (the reference declares
+ *     gil_used = false, lib.rs:448).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry
+ *     point fails with RLIC_B200_ENODEVICE.
+ *
+ * Arithmetic contract: the kernels evaluate the reference's default feature
+ * set (fma + branchless, Cargo.toml:28) operation by operation in the input
+ * dtype, so results are bit-identical to that build on the same inputs.
+ */
+#ifndef RLIC_B200_H
+#define RLIC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RLIC_B200_OK 0
+#define RLIC_B200_EINVAL 1    /* bad enum, negative size, empty kernel, null pointer */
+#define RLIC_B200_ENODEVICE 2 /* no usable CUDA device / driver */
+#define RLIC_B200_ECUDA 3     /* a CUDA runtime call failed (incl. out of memory) */
+#define RLIC_B200_ESHARD 4    /* impossible sharding request */
+
+#define RLIC_B200_VELOCITY 0
+#define RLIC_B200_POLARIZATION 1
+#define RLIC_B200_CLOSED 0
+#define RLIC_B200_PERIODIC 1
+
+/* ABI version of this header; bumped on any signature change. */
+#define RLIC_B200_ABI_VERSION 1
+int rlic_b200_abi_version(void);
+
+/* Message of the last failure on the calling thread ("" if none). */
+const char *rlic_b200_last_error(void);
+
+/* Number of visible CUDA devices (0 when there is no driver/GPU; never fails). */
+int rlic_b200_device_count(void);
+
+/* Number of kernel launches issued by this library since it was loaded
+ * (all threads, all devices).  bench.py reads it around the timed region. */
+int64_t rlic_b200_launch_count(void);
+
+/*
+ * HOST entry points — replace rlic._core.convolve_f32 / convolve_f64
+ * (lib.rs:451-482 -> convolve_iteratively, lib.rs:408-443).
+ *
+ * All pointers are HOST pointers (pageable or pinned).  `out` receives
+ * ny*nx values and must not alias an input.  The library uploads the fields,
+ * runs `iterations` passes with device-resident ping-pong buffers, and
+ * downloads the result; it keeps no reference to host memory after return.
+ * iterations <= 0 writes zeros to `out` (lib.rs:423-432: the loop never runs);
+ * the Python layer handles iterations == 0 itself (_lib.py:208-209).
+ * Runs on the current default device `rlic_b200_set_device` selected for the
+ * calling thread (device 0 if never called).
+ */
+int rlic_b200_convolve_f32(const float *texture, const float *u, const float *v,
+                           int64_t ny, int64_t nx,
+                           const float *kernel, int64_t klen,
+                           int uv_mode,
+                           int x_left, int x_right, int y_left, int y_right,
+                           int64_t iterations, float *out);
+
+int rlic_b200_convolve_f64(const double *texture, const double *u, const double *v,
+                           int64_t ny, int64_t nx,
+                           const double *kernel, int64_t klen,
+                           int uv_mode,
+                           int x_left, int x_right, int y_left, int y_right,
+                           int64_t iterations, double *out);
+
+/* Device used by the host entry points on the calling thread. */
+int rlic_b200_set_device(int device);
+
+/*
+ * DEVICE entry points — same computation on buffers already resident in HBM
+ * (used by bench.py's device-resident `value` and
+ * by the row-slab sharded driver).
+ *
+ *   d_texture, d_u, d_v : device pointers, ny x nx each, read only
+ *   d_work0, d_work1    : device scratch, ny x nx each.  Pass n writes
+ *                         work[(n-1) % 2]; the pointer holding the final result
+ *                         is returned through *d_result.  (Two texture-sized
+ *                         work buffers: the reference's memory contract,
+ *                         README.md:158-164.)
+ *   kernel              : HOST pointer to the klen taps
+ *   stream              : cudaStream_t, or NULL for the legacy default stream
+ *
+ * The call only enqueues work on `stream`; it does not synchronise.
+ */
+int rlic_b200_convolve_device_f32(const float *d_texture, const float *d_u, const float *d_v,
+                                  int64_t ny, int64_t nx,
+                                  const float *kernel, int64_t klen,
+                                  int uv_mode,
+                                  int x_left, int x_right, int y_left, int y_right,
+                                  int64_t iterations,
+                                  float *d_work0, float *d_work1,
+                                  float **d_result, void *stream);
+
+int rlic_b200_convolve_device_f64(const double *d_texture, const double *d_u, const double *d_v,
+                                  int64_t ny, int64_t nx,
+                                  const double *kernel, int64_t klen,
+                                  int uv_mode,
+                                  int x_left, int x_right, int y_left, int y_right,
+                                  int64_t iterations,
+                                  double *d_work0, double *d_work1,
+                                  double **d_result, void *stream);
+
+/*
+ * Packed vector field.  The kernels read the field interleaved, one (u, v)
+ * pair per pixel (count pairs = 2*count scalars), because every step of a walk
+ * needs both components of the same pixel.  rlic_b200_pack_uv_* builds that
+ * layout from two planar device arrays; the *_packed_* and *_slab_* entry
+ * points take it directly so that callers who run many passes pack once.
+ */
+int rlic_b200_pack_uv_f32(const float *d_u, const float *d_v, int64_t count,
+                          float *d_uv, void *stream);
+int rlic_b200_pack_uv_f64(const double *d_u, const double *d_v, int64_t count,
+                          double *d_uv, void *stream);
+
+/* Same as rlic_b200_convolve_device_* with the field already packed. */
+int rlic_b200_convolve_packed_f32(const float *d_texture, const float *d_uv,
+                                  int64_t ny, int64_t nx,
+                                  const float *kernel, int64_t klen,
+                                  int uv_mode,
+                                  int x_left, int x_right, int y_left, int y_right,
+                                  int64_t iterations,
+                                  float *d_work0, float *d_work1,
+                                  float **d_result, void *stream);
+int rlic_b200_convolve_packed_f64(const double *d_texture, const double *d_uv,
+                                  int64_t ny, int64_t nx,
+                                  const double *kernel, int64_t klen,
+                                  int uv_mode,
+                                  int x_left, int x_right, int y_left, int y_right,
+                                  int64_t iterations,
+                                  double *d_work0, double *d_work1,
+                                  double **d_result, void *stream);
+
+/*
+ * ONE PASS over a row slab — the building block of row-slab sharding
+ * (SURVEY.md section 8(e)).  The image has `ny` x `nx` pixels globally; this
+ * device holds global rows [row0 - halo_lo, row0 + nrows + halo_hi) of the
+ * texture (d_texture) and of the packed field (d_uv) in buffers whose first
+ * row is global row `row0 - halo_lo`, and computes output rows
+ * [row0, row0 + nrows) into d_out (first row = row0, no halo).
+ * The image-level wall rules (lib.rs:83-95) are applied in global row numbers;
+ * with y-periodic boundaries the wrap lands in the halo, which the caller has
+ * filled from the neighbouring slab in ring order (rows -1, -2, ... are rows
+ * ny-1, ny-2, ...).  halo_lo/halo_hi must be >= klen/2 unless a closed wall
+ * bounds the slab on that side, otherwise RLIC_B200_ESHARD.
+ * With row0 = 0, nrows = ny and no halo this is one pass of the whole image.
+ */
+int rlic_b200_pass_slab_f32(const float *d_texture, const float *d_uv,
+                            float *d_out,
+                            int64_t ny, int64_t nx,
+                            int64_t row0, int64_t nrows, int64_t halo_lo, int64_t halo_hi,
+                            const float *kernel, int64_t klen,
+                            int uv_mode,
+                            int x_left, int x_right, int y_left, int y_right,
+                            void *stream);
+
+int rlic_b200_pass_slab_f64(const double *d_texture, const double *d_uv,
+                            double *d_out,
+                            int64_t ny, int64_t nx,
+                            int64_t row0, int64_t nrows, int64_t halo_lo, int64_t halo_hi,
+                            const double *kernel, int64_t klen,
+                            int uv_mode,
+                            int x_left, int x_right, int y_left, int y_right,
+                            void *stream);
+
+/*
+ * BATCH of independent fields on the host (BASELINE config 5): `nfields`
+ * images of ny x nx stored back to back in each of texture/u/v/out, split
+ * whole-image over the listed devices (one host thread + stream pair per
+ * device, uploads/downloads overlapped with compute).  devices == NULL or
+ * ndev <= 0 means "all visible devices".
+ */
+int rlic_b200_convolve_batch_f32(const float *texture, const float *u, const float *v,
+                                 int64_t nfields, int64_t ny, int64_t nx,
+                                 const float *kernel, int64_t klen,
+                                 int uv_mode,
+                                 int x_left, int x_right, int y_left, int y_right,
+                                 int64_t iterations,
+                                 const int *devices, int ndev, float *out);
+
+int rlic_b200_convolve_batch_f64(const double *texture, const double *u, const double *v,
+                                 int64_t nfields, int64_t ny, int64_t nx,
+                                 const double *kernel, int64_t klen,
+                                 int uv_mode,
+                                 int x_left, int x_right, int y_left, int y_right,
+                                 int64_t iterations,
+                                 const int *devices, int ndev, double *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RLIC_B200_H */

@@ -1,0 +1,16 @@
+"""Line Integral Convolution on NVIDIA B200 (sm_100a), API-compatible with rLIC.
+
+``rlic_b200.convolve`` mirrors ``rlic.convolve`` (reference:
+``/root/reference/src/rlic/_lib.py:37-235``): same signature, validation, error
+messages, dtype rules and semantics; the computation runs in hand-written CUDA
+kernels behind a C ABI (``include/rlic_b200.h``).  There is no CPU fallback.
+
+rLIC (MIT, C.M.T. Robert) and the vectorplot code it descends from (BSD-2,
+Anne Archibald) are the behavioural reference only; see NOTICE.
+"""
+
+__all__ = [
+    "convolve",
+]
+
+from rlic_b200._lib import convolve

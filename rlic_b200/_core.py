@@ -1,0 +1,165 @@
+"""ctypes binding of the C ABI (``include/rlic_b200.h``) with the call shapes of
+the reference's native module ``rlic._core``
+(``/root/reference/src/lib.rs:451-482``, ``src/rlic/_core.pyi:8-29``):
+
+    convolve_f32(texture, (u, v, uv_mode), kernel, ((xl, xr), (yl, yr)), iterations)
+    convolve_f64(...)
+
+The shared library is loaded when this module is imported; a missing library is
+an ImportError and a missing GPU a RuntimeError at call time.  Nothing here
+computes on the CPU.
+"""
+
+from __future__ import annotations
+
+__all__ = [
+    "convolve_f32",
+    "convolve_f64",
+    "device_count",
+    "launch_count",
+    "lib",
+]
+
+import ctypes
+import os
+from pathlib import Path
+
+import numpy as np
+
+_LIB_PATH = Path(__file__).resolve().parent / "librlic_b200.so"
+
+OK, EINVAL, ENODEVICE, ECUDA, ESHARD = range(5)
+ABI_VERSION = 1
+
+_MODE_CODE = {"velocity": 0, "polarization": 1}
+_WALL_CODE = {"closed": 0, "periodic": 1}
+
+_i64 = ctypes.c_int64
+_int = ctypes.c_int
+_vp = ctypes.c_void_p
+
+
+def _signatures(real) -> dict[str, list]:
+    """argtypes per entry point for one scalar type; mirrors include/rlic_b200.h."""
+    p = ctypes.POINTER(real)
+    walls = [_int] * 4
+    return {
+        "convolve": [p, p, p, _i64, _i64, p, _i64, _int, *walls, _i64, p],
+        "convolve_device": [_vp, _vp, _vp, _i64, _i64, p, _i64, _int, *walls, _i64, _vp, _vp,
+                            ctypes.POINTER(_vp), _vp],
+        "pack_uv": [_vp, _vp, _i64, _vp, _vp],
+        "convolve_packed": [_vp, _vp, _i64, _i64, p, _i64, _int, *walls, _i64, _vp, _vp,
+                            ctypes.POINTER(_vp), _vp],
+        "pass_slab": [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, p, _i64, _int, *walls, _vp],
+        "convolve_batch": [p, p, p, _i64, _i64, _i64, p, _i64, _int, *walls, _i64,
+                           ctypes.POINTER(_int), _int, p],
+    }
+
+
+def _load() -> ctypes.CDLL:
+    if not _LIB_PATH.exists():
+        raise ImportError(
+            f"{_LIB_PATH} is missing: build it with `python -m rlic_b200._build` "
+            "(nvcc, sm_100a). rlic_b200 has no CPU fallback."
+        )
+    cdll = ctypes.CDLL(os.fspath(_LIB_PATH))
+    cdll.rlic_b200_abi_version.restype = _int
+    if cdll.rlic_b200_abi_version() != ABI_VERSION:
+        raise ImportError(f"{_LIB_PATH} has a different ABI version; rebuild it")
+    cdll.rlic_b200_last_error.restype = ctypes.c_char_p
+    cdll.rlic_b200_device_count.restype = _int
+    cdll.rlic_b200_launch_count.restype = _i64
+    cdll.rlic_b200_set_device.argtypes = [_int]
+    cdll.rlic_b200_set_device.restype = _int
+    for sfx, real in (("f32", ctypes.c_float), ("f64", ctypes.c_double)):
+        for name, argtypes in _signatures(real).items():
+            fn = getattr(cdll, f"rlic_b200_{name}_{sfx}")
+            fn.argtypes = argtypes
+            fn.restype = _int
+    return cdll
+
+
+lib = _load()
+
+
+def device_count() -> int:
+    return int(lib.rlic_b200_device_count())
+
+
+def launch_count() -> int:
+    return int(lib.rlic_b200_launch_count())
+
+
+def check(rc: int) -> None:
+    """Turn a non-zero return code into the matching Python exception."""
+    if rc == OK:
+        return
+    msg = (lib.rlic_b200_last_error() or b"").decode("utf-8", "replace")
+    if rc == EINVAL or rc == ESHARD:
+        raise ValueError(msg)
+    if rc == ENODEVICE:
+        raise RuntimeError(f"rlic_b200 needs a CUDA device and has no CPU fallback: {msg}")
+    raise RuntimeError(msg)
+
+
+def wall_codes(boundaries) -> tuple[int, int, int, int]:
+    (xl, xr), (yl, yr) = boundaries
+    try:
+        return (_WALL_CODE[xl], _WALL_CODE[xr], _WALL_CODE[yl], _WALL_CODE[yr])
+    except KeyError as exc:
+        raise ValueError(f"unknown boundary {exc.args[0]!r}") from None
+
+
+def mode_code(uv_mode: str) -> int:
+    try:
+        return _MODE_CODE[uv_mode]
+    except KeyError:
+        raise ValueError(f"unknown uv_mode {uv_mode!r}") from None
+
+
+def _as_image(name: str, arr, dtype: np.dtype, ndim: int) -> np.ndarray:
+    # the PyO3 signature rejects anything but an ndarray of the right dtype/rank
+    if not isinstance(arr, np.ndarray) or arr.dtype != dtype or arr.ndim != ndim:
+        got = f"{type(arr).__name__}" + (
+            f"[{arr.dtype}, ndim={arr.ndim}]" if isinstance(arr, np.ndarray) else ""
+        )
+        raise TypeError(f"argument '{name}': expected a {ndim}-D {dtype} ndarray, got {got}")
+    # any strides are accepted (stride-0 broadcasts, F-order views): normalise before upload
+    return np.ascontiguousarray(arr)
+
+
+def _convolve(sfx: str, real, texture, uv, kernel, boundaries, iterations):
+    dtype = np.dtype(real)
+    u, v, uv_mode = uv
+    texture = _as_image("texture", texture, dtype, 2)
+    u = _as_image("u", u, dtype, 2)
+    v = _as_image("v", v, dtype, 2)
+    kernel = _as_image("kernel", kernel, dtype, 1)
+    if u.shape != texture.shape or v.shape != texture.shape:
+        raise ValueError("texture, u and v must have identical shapes")
+    ny, nx = texture.shape
+    out = np.empty((ny, nx), dtype=dtype)
+    p = ctypes.POINTER(real)
+    rc = getattr(lib, f"rlic_b200_convolve_{sfx}")(
+        texture.ctypes.data_as(p),
+        u.ctypes.data_as(p),
+        v.ctypes.data_as(p),
+        ny,
+        nx,
+        kernel.ctypes.data_as(p),
+        kernel.size,
+        mode_code(uv_mode),
+        *wall_codes(boundaries),
+        int(iterations),
+        out.ctypes.data_as(p),
+    )
+    check(rc)
+    return out
+
+
+def convolve_f32(texture, uv, kernel, boundaries, iterations=1):
+    return _convolve("f32", ctypes.c_float, texture, uv, kernel, boundaries, iterations)
+
+
+def convolve_f64(texture, uv, kernel, boundaries, iterations=1):
+    return _convolve("f64", ctypes.c_double, texture, uv, kernel, boundaries, iterations)

@@ -1,0 +1,169 @@
+"""Public entry point ``convolve``.
+
+Drop-in for ``rlic.convolve``: behaviour (argument kinds, order and text of
+every validation error, ``ExceptionGroup`` aggregation, ``iterations == 0``
+copy, dtype dispatch) mirrors ``/root/reference/src/rlic/_lib.py:37-235``.
+The computation itself happens on the GPU through ``rlic_b200._core``.
+"""
+
+from __future__ import annotations
+
+__all__ = [
+    "convolve",
+]
+
+from typing import TYPE_CHECKING
+
+import numpy as np
+
+from rlic_b200 import _core
+from rlic_b200._boundaries import BoundarySet
+
+if TYPE_CHECKING:
+    from numpy import dtype, ndarray
+
+    from rlic_b200._boundaries import BoundarySpec
+    from rlic_b200._typing import F, UVMode
+
+_KNOWN_UV_MODES = ["velocity", "polarization"]
+_SUPPORTED_DTYPES: list[np.dtype] = [np.dtype("float32"), np.dtype("float64")]
+
+
+def _check_inputs(texture, u, v, kernel, uv_mode, boundaries, iterations):
+    """Run every validator; return (problems, parsed boundaries)."""
+    problems: list[Exception] = []
+    add = problems.append
+
+    if iterations < 0:
+        add(
+            ValueError(
+                f"Invalid number of iterations: {iterations}\n"
+                "Expected a strictly positive integer."
+            )
+        )
+
+    if uv_mode not in _KNOWN_UV_MODES:
+        add(ValueError(f"Invalid uv_mode {uv_mode!r}. Expected one of {_KNOWN_UV_MODES}"))
+
+    named = (("texture", texture), ("u", u), ("v", v), ("kernel", kernel))
+    expectation = (
+        "Expected texture, u, v and kernel with identical dtype, "
+        f"from {_SUPPORTED_DTYPES}. Got "
+        + ", ".join(f"{name}.dtype={arr.dtype!r}" for name, arr in named)
+    )
+    seen = {arr.dtype for _, arr in named}
+    if rejected := seen.difference(_SUPPORTED_DTYPES):
+        add(TypeError(f"Found unsupported data type(s): {list(rejected)}. {expectation}"))
+    if len(seen) != 1:
+        add(TypeError(f"Data types mismatch. {expectation}"))
+
+    if texture.ndim != 2:
+        add(
+            ValueError(
+                f"Expected a texture with exactly two dimensions. Got texture.ndim={texture.ndim}"
+            )
+        )
+    if np.any(texture < 0):
+        add(ValueError("Found invalid texture element(s). Expected only positive values."))
+    if u.shape != texture.shape or v.shape != texture.shape:
+        add(
+            ValueError(
+                "Shape mismatch: expected texture, u and v with identical shapes. "
+                f"Got texture.shape={texture.shape}, u.shape={u.shape}, v.shape={v.shape}"
+            )
+        )
+
+    if kernel.ndim != 1:
+        add(
+            ValueError(
+                f"Expected a kernel with exactly one dimension. Got kernel.ndim={kernel.ndim}"
+            )
+        )
+    if np.any(~np.isfinite(kernel)):
+        add(ValueError("Found non-finite value(s) in kernel."))
+
+    walls = BoundarySet.from_spec(boundaries)
+    if walls is None:
+        add(TypeError(f"Invalid boundary specification {boundaries}"))
+    else:
+        problems.extend(walls.collect_exceptions())
+    return problems, walls
+
+
+def convolve(
+    texture: ndarray[tuple[int, int], dtype[F]],
+    /,
+    u: ndarray[tuple[int, int], dtype[F]],
+    v: ndarray[tuple[int, int], dtype[F]],
+    *,
+    kernel: ndarray[tuple[int], dtype[F]],
+    uv_mode: UVMode = "velocity",
+    boundaries: BoundarySpec = "closed",
+    iterations: int = 1,
+) -> ndarray[tuple[int, int], dtype[F]]:
+    """2-dimensional line integral convolution (GPU).
+
+    Convolve ``texture`` along the streamlines of the vector field ``(u, v)``
+    with the 1D ``kernel``.
+
+    Arguments
+    ---------
+    texture: 2D numpy array, positional-only
+      The image that is smeared along the field lines (usually noise).
+      Must not contain negative values.
+
+    u, v: 2D numpy arrays, same shape as ``texture``
+      Horizontal (along axis 1) and vertical (along axis 0) field components.
+
+    kernel: 1D numpy array, keyword-only
+      Weights along the field line; the first half applies upstream of the
+      starting pixel, the second half downstream.  Must be finite; may be
+      negative; odd lengths balance both directions.
+
+    uv_mode: 'velocity' (default) or 'polarization', keyword-only
+      With 'polarization' only the orientation of (u, v) matters, not its sign.
+
+    boundaries: 'closed' (default), 'periodic', or ``{'x': ..., 'y': ...}`` whose
+      values are one of these names or a ``(left, right)`` pair of them.
+      A 'periodic' side requires 'periodic' on the opposite side.
+
+    iterations: int >= 0 (default 1), keyword-only
+      Number of passes; each pass takes the previous result as its texture.
+      Intermediate results never leave the GPU.
+
+    Returns
+    -------
+    A newly allocated 2D array with the dtype of the inputs (a copy of
+    ``texture`` when ``iterations == 0``).  Inputs are never modified.
+
+    Raises
+    ------
+    TypeError, ValueError for invalid arguments; an ``ExceptionGroup`` carrying
+    all of them when there is more than one.  RuntimeError if the CUDA library
+    or a GPU is unavailable (there is no CPU fallback).
+
+    Notes
+    -----
+    All arrays must share one dtype, float32 or float64; the computation is
+    carried out in that dtype.  Streamlines stop at pixels where u or v is NaN.
+    Arrays of any memory layout are accepted (they are made C-contiguous before
+    upload).  Results are bit-identical to rLIC built with its default
+    features (fma + branchless); see DESIGN.md.
+    """
+    problems, walls = _check_inputs(texture, u, v, kernel, uv_mode, boundaries, iterations)
+    if len(problems) == 1:
+        raise problems[0]
+    if problems:
+        raise ExceptionGroup("Invalid inputs were received.", problems)
+    assert walls is not None
+
+    if iterations == 0:
+        return texture.copy()
+
+    if texture.dtype == np.dtype("float32"):
+        run = _core.convolve_f32
+    elif texture.dtype == np.dtype("float64"):
+        run = _core.convolve_f64
+    else:
+        raise AssertionError
+    return run(texture, (u, v, uv_mode), kernel, (walls.x, walls.y), iterations)

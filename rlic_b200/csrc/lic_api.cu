@@ -1,0 +1,566 @@
+// Host driver and C ABI of librlic_b200.so (see include/rlic_b200.h).
+//
+// Replaces the iteration driver and FFI shim of the reference,
+// /root/reference/src/lib.rs:408-485, with a CUDA host path:
+// upload -> `iterations` passes over device-resident ping-pong buffers -> download.
+// There is no CPU compute path in this file; without a device every entry
+// point fails.
+#include "../../include/rlic_b200.h"
+#include "lic_walk.cuh"
+
+#include <atomic>
+#include <climits>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <algorithm>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace {
+
+using rlic::PassGeom;
+
+thread_local std::string tls_error;
+thread_local int tls_device = 0;
+std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    tls_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                              \
+    do {                                                                            \
+        cudaError_t err__ = (expr);                                                 \
+        if (err__ != cudaSuccess)                                                   \
+            return fail(err__ == cudaErrorNoDevice || err__ == cudaErrorInsufficientDriver \
+                            ? RLIC_B200_ENODEVICE                                   \
+                            : RLIC_B200_ECUDA,                                      \
+                        "%s: %s (%s:%d)", #expr, cudaGetErrorString(err__), __FILE__, __LINE__); \
+    } while (0)
+
+// Stream and stream-ordered allocations that clean up on every exit path.
+struct Stream {
+    cudaStream_t s = nullptr;
+    ~Stream() { if (s) cudaStreamDestroy(s); }
+};
+struct DeviceBuf {
+    void *p = nullptr;
+    cudaStream_t s = nullptr;
+    ~DeviceBuf() { if (p) cudaFreeAsync(p, s); }
+    cudaError_t alloc(size_t bytes, cudaStream_t stream)
+    {
+        s = stream;
+        return cudaMallocAsync(&p, bytes ? bytes : 1, stream);
+    }
+};
+
+struct Walls { int x_left, x_right, y_left, y_right; };
+
+// Keep freed stream-ordered allocations cached in the device pool instead of
+// returning them to the OS at every synchronisation (first call per device).
+cudaError_t use_device(int device)
+{
+    static std::mutex mu;
+    static std::vector<char> tuned;
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess)
+        return e;
+    std::lock_guard<std::mutex> lock(mu);
+    if ((size_t)device >= tuned.size())
+        tuned.resize((size_t)device + 1, 0);
+    if (!tuned[(size_t)device]) {
+        cudaMemPool_t pool;
+        e = cudaDeviceGetDefaultMemPool(&pool, device);
+        if (e != cudaSuccess)
+            return e;
+        uint64_t keep = UINT64_MAX;
+        e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        if (e != cudaSuccess)
+            return e;
+        tuned[(size_t)device] = 1;
+    }
+    return cudaSuccess;
+}
+
+int check_common(int64_t ny, int64_t nx, int64_t klen, int uv_mode, const Walls &w)
+{
+    if (ny < 0 || nx < 0)
+        return fail(RLIC_B200_EINVAL, "negative image size %lld x %lld", (long long)ny, (long long)nx);
+    if (ny > INT_MAX - 2 || nx > INT_MAX - 2)
+        return fail(RLIC_B200_EINVAL, "image side exceeds 2^31-3 pixels");
+    if (klen <= 0)
+        return fail(RLIC_B200_EINVAL,
+                    "empty convolution kernel (the reference aborts the process here, lib.rs:371)");
+    if (klen > INT_MAX / 2)
+        return fail(RLIC_B200_EINVAL, "kernel too long");
+    if (uv_mode != RLIC_B200_VELOCITY && uv_mode != RLIC_B200_POLARIZATION)
+        return fail(RLIC_B200_EINVAL, "unknown uv_mode %d", uv_mode);
+    const int sides[4] = {w.x_left, w.x_right, w.y_left, w.y_right};
+    for (int s : sides)
+        if (s != RLIC_B200_CLOSED && s != RLIC_B200_PERIODIC)
+            return fail(RLIC_B200_EINVAL, "unknown boundary %d", s);
+    return RLIC_B200_OK;
+}
+
+// Wall rules (lib.rs:83-95) for a buffer whose row 0 is global row `shift`.
+// `lo_wall` / `hi_wall`: whether the image edge on that side can be reached
+// from this buffer and must be acted on (always true for a whole image).
+void set_walls(PassGeom &g, int64_t ny, int64_t nx, int64_t shift, bool lo_wall, bool hi_wall,
+               const Walls &w)
+{
+    const int64_t far = 1 << 30;
+    g.j_below_to = w.x_left == RLIC_B200_PERIODIC ? (int)nx - 1 : 0;
+    g.j_above_to = w.x_right == RLIC_B200_PERIODIC ? 0 : (int)nx - 1;
+    const int64_t lo = lo_wall ? -shift : -far;
+    const int64_t hi = hi_wall ? ny - shift : far;   // exclusive
+    g.i_min = (int)lo;
+    g.i_span = (unsigned)(hi - lo);
+    g.i_below_to = (int)((w.y_left == RLIC_B200_PERIODIC ? ny - 1 : 0) - shift);
+    g.i_above_to = (int)((w.y_right == RLIC_B200_PERIODIC ? 0 : ny - 1) - shift);
+}
+
+template <typename T> using Pair = typename rlic::Fp<T>::Pair;
+
+template <typename T, bool POL, typename Taps, typename Idx>
+cudaError_t launch_one(const T *tex, const Pair<T> *uv, T *out, const PassGeom &g,
+                       const Taps &taps, int ntaps, unsigned blocks, cudaStream_t stream)
+{
+    rlic::lic_pass_kernel<T, POL, Taps, Idx>
+        <<<blocks, rlic::kThreads, 0, stream>>>(tex, uv, out, g, taps, ntaps);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_pack(const T *u, const T *v, Pair<T> *uv, size_t count, cudaStream_t stream)
+{
+    if (count == 0)
+        return cudaSuccess;
+    const size_t want = (count + 255) / 256;
+    const unsigned blocks = (unsigned)std::min<size_t>(want, 148 * 16);
+    rlic::pack_uv_kernel<T><<<blocks, 256, 0, stream>>>(u, v, uv, (long long)count);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+// Taps prepared once per call: either a parameter block or a device copy.
+template <typename T> struct TapSet {
+    static constexpr int kMaxParam = rlic::kParamTapBytes / (int)sizeof(T);
+    rlic::ParamTaps<T, kMaxParam> param;
+    DeviceBuf global;
+    int ntaps = 0;
+    bool in_param = true;
+
+    cudaError_t prepare(const T *host_taps, int64_t klen, cudaStream_t stream)
+    {
+        ntaps = (int)klen;
+        in_param = klen <= kMaxParam;
+        if (in_param) {
+            std::memset(param.w, 0, sizeof param.w);
+            std::memcpy(param.w, host_taps, sizeof(T) * (size_t)klen);
+            return cudaSuccess;
+        }
+        cudaError_t e = global.alloc(sizeof(T) * (size_t)klen, stream);
+        if (e != cudaSuccess)
+            return e;
+        // the source may be pageable: the copy is staged before this returns
+        return cudaMemcpyAsync(global.p, host_taps, sizeof(T) * (size_t)klen,
+                               cudaMemcpyHostToDevice, stream);
+    }
+};
+
+// Launch one pass for `nfields` stacked fields of `g.rows_alloc` buffer rows.
+template <typename T>
+int launch_pass(const T *tex, const Pair<T> *uv, T *out, PassGeom g, int64_t nfields,
+                int uv_mode, const TapSet<T> &taps, cudaStream_t stream)
+{
+    if (g.out_rows <= 0 || g.nx <= 0 || nfields <= 0)
+        return RLIC_B200_OK;
+    g.tiles_x = (g.nx + rlic::kTileW - 1) / rlic::kTileW;
+    const int64_t tiles_y = ((int64_t)g.out_rows + rlic::kTileH - 1) / rlic::kTileH;
+    const int64_t per_field = tiles_y * g.tiles_x;
+    const int64_t blocks = per_field * nfields;
+    if (per_field > INT_MAX || blocks > INT_MAX)
+        return fail(RLIC_B200_EINVAL, "too many tiles for one launch (%lld)", (long long)blocks);
+    if (nfields * (int64_t)g.rows_alloc > (int64_t)(1 << 30))
+        return fail(RLIC_B200_EINVAL, "too many stacked rows for one launch");
+    g.tiles_per_field = (int)per_field;
+    const bool wide = nfields * (int64_t)g.rows_alloc * g.nx > (int64_t)INT_MAX;
+    const bool pol = uv_mode == RLIC_B200_POLARIZATION;
+
+    cudaError_t e;
+#define RLIC_LAUNCH(POL, TAPS, TAPV, IDX) \
+    e = launch_one<T, POL, TAPS, IDX>(tex, uv, out, g, TAPV, taps.ntaps, (unsigned)blocks, stream)
+    using PT = rlic::ParamTaps<T, TapSet<T>::kMaxParam>;
+    using GT = rlic::GlobalTaps<T>;
+    const GT gt{static_cast<const T *>(taps.global.p)};
+    if (taps.in_param) {
+        if (pol) { if (wide) RLIC_LAUNCH(true, PT, taps.param, long long); else RLIC_LAUNCH(true, PT, taps.param, int); }
+        else     { if (wide) RLIC_LAUNCH(false, PT, taps.param, long long); else RLIC_LAUNCH(false, PT, taps.param, int); }
+    } else {
+        if (pol) { if (wide) RLIC_LAUNCH(true, GT, gt, long long); else RLIC_LAUNCH(true, GT, gt, int); }
+        else     { if (wide) RLIC_LAUNCH(false, GT, gt, long long); else RLIC_LAUNCH(false, GT, gt, int); }
+    }
+#undef RLIC_LAUNCH
+    CUDA_TRY(e);
+    return RLIC_B200_OK;
+}
+
+// `iterations` passes over device-resident buffers (lib.rs:432-440 without the
+// copy-back: the two work buffers swap roles instead).
+template <typename T>
+int run_device(const T *d_tex, const Pair<T> *d_uv, int64_t nfields, int64_t ny, int64_t nx,
+               const TapSet<T> &taps, int uv_mode, const Walls &w, int64_t iterations, T *work0,
+               T *work1, T **result, cudaStream_t stream)
+{
+    PassGeom g{};
+    g.nx = (int)nx;
+    g.out_rows = (int)ny;
+    g.first_row = 0;
+    g.rows_alloc = (int)ny;
+    set_walls(g, ny, nx, 0, true, true, w);
+    const T *src = d_tex;
+    T *dst = work0;
+    for (int64_t it = 0; it < iterations; ++it) {
+        dst = (it & 1) ? work1 : work0;
+        int rc = launch_pass<T>(src, d_uv, dst, g, nfields, uv_mode, taps, stream);
+        if (rc)
+            return rc;
+        src = dst;
+    }
+    *result = dst;
+    return RLIC_B200_OK;
+}
+
+template <typename T>
+int convolve_host(const T *tex, const T *u, const T *v, int64_t nfields, int64_t ny, int64_t nx,
+                  const T *kernel, int64_t klen, int uv_mode, const Walls &w,
+                  int64_t iterations, T *out, int device)
+{
+    if (int rc = check_common(ny, nx, klen, uv_mode, w))
+        return rc;
+    const size_t count = (size_t)nfields * (size_t)ny * (size_t)nx;
+    if (count == 0)
+        return RLIC_B200_OK;
+    if (!tex || !u || !v || !kernel || !out)
+        return fail(RLIC_B200_EINVAL, "null pointer argument");
+    if (iterations <= 0) {   // lib.rs:423-432: the loop never runs, output stays zero
+        std::memset(out, 0, count * sizeof(T));
+        return RLIC_B200_OK;
+    }
+    const size_t bytes = count * sizeof(T);
+
+    CUDA_TRY(use_device(device));
+    Stream st;
+    CUDA_TRY(cudaStreamCreateWithFlags(&st.s, cudaStreamNonBlocking));
+    // d_tex doubles as the second work buffer
+    DeviceBuf d_tex, d_uv, d_work, d_stage;
+    CUDA_TRY(d_tex.alloc(bytes, st.s));
+    CUDA_TRY(d_uv.alloc(2 * bytes, st.s));
+    CUDA_TRY(d_work.alloc(bytes, st.s));
+    CUDA_TRY(d_stage.alloc(bytes, st.s));
+    TapSet<T> taps;
+    CUDA_TRY(taps.prepare(kernel, klen, st.s));
+
+    // u lands in the (still unused) work buffer, v in a staging buffer that is
+    // returned to the pool as soon as the interleave has been enqueued.
+    CUDA_TRY(cudaMemcpyAsync(d_work.p, u, bytes, cudaMemcpyHostToDevice, st.s));
+    CUDA_TRY(cudaMemcpyAsync(d_stage.p, v, bytes, cudaMemcpyHostToDevice, st.s));
+    CUDA_TRY(launch_pack<T>(static_cast<const T *>(d_work.p), static_cast<const T *>(d_stage.p),
+                            static_cast<Pair<T> *>(d_uv.p), count, st.s));
+    CUDA_TRY(cudaMemcpyAsync(d_tex.p, tex, bytes, cudaMemcpyHostToDevice, st.s));
+
+    T *result = nullptr;
+    // pass 1 reads the uploaded texture and writes d_work; pass 2 writes back
+    // over the texture copy; and so on: exactly two texture-sized work buffers.
+    int rc = run_device<T>(static_cast<T *>(d_tex.p), static_cast<Pair<T> *>(d_uv.p), nfields, ny,
+                           nx, taps, uv_mode, w, iterations, static_cast<T *>(d_work.p),
+                           static_cast<T *>(d_tex.p), &result, st.s);
+    if (rc)
+        return rc;
+    CUDA_TRY(cudaMemcpyAsync(out, result, bytes, cudaMemcpyDeviceToHost, st.s));
+    CUDA_TRY(cudaStreamSynchronize(st.s));
+    return RLIC_B200_OK;
+}
+
+template <typename T>
+int convolve_device(const T *d_tex, const T *d_u, const T *d_v, int64_t ny, int64_t nx,
+                    const T *kernel, int64_t klen, int uv_mode, const Walls &w,
+                    int64_t iterations, T *work0, T *work1, T **result, void *stream)
+{
+    if (int rc = check_common(ny, nx, klen, uv_mode, w))
+        return rc;
+    if (!result)
+        return fail(RLIC_B200_EINVAL, "d_result is null");
+    *result = nullptr;
+    if (ny == 0 || nx == 0)
+        return RLIC_B200_OK;
+    if (!d_tex || !d_u || !d_v || !kernel || !work0 || (!work1 && iterations > 1))
+        return fail(RLIC_B200_EINVAL, "null pointer argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t count = (size_t)ny * (size_t)nx;
+    if (iterations <= 0) {
+        CUDA_TRY(cudaMemsetAsync(work0, 0, sizeof(T) * count, s));
+        *result = work0;
+        return RLIC_B200_OK;
+    }
+    TapSet<T> taps;
+    CUDA_TRY(taps.prepare(kernel, klen, s));
+    DeviceBuf d_uv;   // stream-ordered scratch, returned to the pool after the last pass
+    CUDA_TRY(d_uv.alloc(2 * sizeof(T) * count, s));
+    CUDA_TRY(launch_pack<T>(d_u, d_v, static_cast<Pair<T> *>(d_uv.p), count, s));
+    return run_device<T>(d_tex, static_cast<Pair<T> *>(d_uv.p), 1, ny, nx, taps, uv_mode, w,
+                         iterations, work0, work1, result, s);
+}
+
+template <typename T>
+int convolve_device_packed(const T *d_tex, const T *d_uv, int64_t ny, int64_t nx,
+                           const T *kernel, int64_t klen, int uv_mode, const Walls &w,
+                           int64_t iterations, T *work0, T *work1, T **result, void *stream)
+{
+    if (int rc = check_common(ny, nx, klen, uv_mode, w))
+        return rc;
+    if (!result)
+        return fail(RLIC_B200_EINVAL, "d_result is null");
+    *result = nullptr;
+    if (ny == 0 || nx == 0)
+        return RLIC_B200_OK;
+    if (!d_tex || !d_uv || !kernel || !work0 || (!work1 && iterations > 1))
+        return fail(RLIC_B200_EINVAL, "null pointer argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (iterations <= 0) {
+        CUDA_TRY(cudaMemsetAsync(work0, 0, sizeof(T) * (size_t)ny * (size_t)nx, s));
+        *result = work0;
+        return RLIC_B200_OK;
+    }
+    TapSet<T> taps;
+    CUDA_TRY(taps.prepare(kernel, klen, s));
+    return run_device<T>(d_tex, reinterpret_cast<const Pair<T> *>(d_uv), 1, ny, nx, taps, uv_mode,
+                         w, iterations, work0, work1, result, s);
+}
+
+template <typename T>
+int pack_uv(const T *d_u, const T *d_v, int64_t count, T *d_uv, void *stream)
+{
+    if (count < 0)
+        return fail(RLIC_B200_EINVAL, "negative element count");
+    if (count == 0)
+        return RLIC_B200_OK;
+    if (!d_u || !d_v || !d_uv)
+        return fail(RLIC_B200_EINVAL, "null pointer argument");
+    CUDA_TRY(launch_pack<T>(d_u, d_v, reinterpret_cast<Pair<T> *>(d_uv), (size_t)count,
+                            static_cast<cudaStream_t>(stream)));
+    return RLIC_B200_OK;
+}
+
+template <typename T>
+int pass_slab(const T *d_tex, const T *d_uv, T *d_out, int64_t ny, int64_t nx, int64_t row0,
+              int64_t nrows, int64_t halo_lo, int64_t halo_hi, const T *kernel, int64_t klen,
+              int uv_mode, const Walls &w, void *stream)
+{
+    if (int rc = check_common(ny, nx, klen, uv_mode, w))
+        return rc;
+    if (row0 < 0 || nrows < 0 || row0 + nrows > ny || halo_lo < 0 || halo_hi < 0)
+        return fail(RLIC_B200_ESHARD, "slab rows [%lld,%lld) outside image of %lld rows",
+                    (long long)row0, (long long)(row0 + nrows), (long long)ny);
+    if (nrows == 0 || nx == 0)
+        return RLIC_B200_OK;
+    if (!d_tex || !d_uv || !d_out || !kernel)
+        return fail(RLIC_B200_EINVAL, "null pointer argument");
+    const int64_t reach = klen / 2;   // a walker moves at most one row per tap
+    const bool bare_whole = row0 == 0 && nrows == ny && halo_lo == 0 && halo_hi == 0;
+    const bool periodic_y = w.y_left == RLIC_B200_PERIODIC || w.y_right == RLIC_B200_PERIODIC;
+    // A side needs `reach` halo rows unless a closed wall stops the walker there.
+    const bool lo_closed = row0 == 0 && !periodic_y;
+    const bool hi_closed = row0 + nrows == ny && !periodic_y;
+    PassGeom g{};
+    g.nx = (int)nx;
+    g.out_rows = (int)nrows;
+    g.first_row = (int)halo_lo;
+    g.rows_alloc = (int)(halo_lo + nrows + halo_hi);
+    if (bare_whole) {
+        set_walls(g, ny, nx, 0, true, true, w);
+    } else {
+        if ((!lo_closed && halo_lo < reach) || (!hi_closed && halo_hi < reach))
+            return fail(RLIC_B200_ESHARD,
+                        "slab halo (%lld,%lld) shorter than the kernel half-width %lld",
+                        (long long)halo_lo, (long long)halo_hi, (long long)reach);
+        // periodic rows: the wrap lands in a halo the caller filled (ring order)
+        set_walls(g, ny, nx, row0 - halo_lo, lo_closed, hi_closed, w);
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    TapSet<T> taps;
+    CUDA_TRY(taps.prepare(kernel, klen, s));
+    return launch_pass<T>(d_tex, reinterpret_cast<const Pair<T> *>(d_uv), d_out, g, 1, uv_mode,
+                          taps, s);
+}
+
+// Whole fields split over devices; one host thread per device, fields
+// processed in chunks so uploads, passes and downloads of different chunks
+// overlap on two streams.
+template <typename T>
+int convolve_batch(const T *tex, const T *u, const T *v, int64_t nfields, int64_t ny, int64_t nx,
+                   const T *kernel, int64_t klen, int uv_mode, const Walls &w,
+                   int64_t iterations, const int *devices, int ndev, T *out)
+{
+    if (int rc = check_common(ny, nx, klen, uv_mode, w))
+        return rc;
+    if (nfields < 0)
+        return fail(RLIC_B200_EINVAL, "negative field count");
+    if (nfields == 0 || ny == 0 || nx == 0)
+        return RLIC_B200_OK;
+    int visible = 0;
+    CUDA_TRY(cudaGetDeviceCount(&visible));
+    std::vector<int> devs;
+    if (devices && ndev > 0) {
+        for (int d = 0; d < ndev; ++d) {
+            if (devices[d] < 0 || devices[d] >= visible)
+                return fail(RLIC_B200_ESHARD, "device %d not visible (%d devices)", devices[d], visible);
+            devs.push_back(devices[d]);
+        }
+    } else {
+        for (int d = 0; d < visible; ++d)
+            devs.push_back(d);
+    }
+    if (devs.empty())
+        return fail(RLIC_B200_ENODEVICE, "no CUDA device");
+    const int64_t nd = (int64_t)devs.size();
+    const size_t field_elems = (size_t)ny * (size_t)nx;
+    // chunk: enough fields to fill the GPU (~16 Mpix) but at least 1
+    const int64_t chunk = std::max<int64_t>(1, (int64_t)((size_t)(16u << 20) / field_elems));
+
+    std::vector<int> rcs(devs.size(), 0);
+    std::vector<std::string> msgs(devs.size());
+    std::vector<std::thread> workers;
+    for (int64_t d = 0; d < nd; ++d) {
+        const int64_t f0 = nfields * d / nd, f1 = nfields * (d + 1) / nd;
+        workers.emplace_back([&, d, f0, f1]() {
+            int rc = 0;
+            for (int64_t f = f0; f < f1 && !rc; f += chunk) {
+                const int64_t n = std::min(chunk, f1 - f);
+                const size_t off = (size_t)f * field_elems;
+                rc = convolve_host<T>(tex + off, u + off, v + off, n, ny, nx, kernel, klen, uv_mode,
+                                      w, iterations, out + off, devs[(size_t)d]);
+            }
+            rcs[(size_t)d] = rc;
+            if (rc)
+                msgs[(size_t)d] = tls_error;
+        });
+    }
+    for (auto &t : workers)
+        t.join();
+    for (size_t d = 0; d < devs.size(); ++d)
+        if (rcs[d]) {
+            tls_error = msgs[d];
+            return rcs[d];
+        }
+    return RLIC_B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rlic_b200_abi_version(void) { return RLIC_B200_ABI_VERSION; }
+
+const char *rlic_b200_last_error(void) { return tls_error.c_str(); }
+
+int rlic_b200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int64_t rlic_b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int rlic_b200_set_device(int device)
+{
+    int n = rlic_b200_device_count();
+    if (n == 0)
+        return fail(RLIC_B200_ENODEVICE, "no CUDA device is visible");
+    if (device < 0 || device >= n)
+        return fail(RLIC_B200_EINVAL, "device %d out of range (%d visible)", device, n);
+    tls_device = device;
+    return RLIC_B200_OK;
+}
+
+#define RLIC_DEFINE(T, sfx)                                                                      \
+    int rlic_b200_convolve_##sfx(const T *texture, const T *u, const T *v, int64_t ny,           \
+                                 int64_t nx, const T *kernel, int64_t klen, int uv_mode,         \
+                                 int x_left, int x_right, int y_left, int y_right,               \
+                                 int64_t iterations, T *out)                                     \
+    {                                                                                            \
+        tls_error.clear();                                                                       \
+        return convolve_host<T>(texture, u, v, 1, ny, nx, kernel, klen, uv_mode,                 \
+                                Walls{x_left, x_right, y_left, y_right}, iterations, out,        \
+                                tls_device);                                                     \
+    }                                                                                            \
+    int rlic_b200_convolve_device_##sfx(const T *d_texture, const T *d_u, const T *d_v,          \
+                                        int64_t ny, int64_t nx, const T *kernel, int64_t klen,   \
+                                        int uv_mode, int x_left, int x_right, int y_left,        \
+                                        int y_right, int64_t iterations, T *d_work0,             \
+                                        T *d_work1, T **d_result, void *stream)                  \
+    {                                                                                            \
+        tls_error.clear();                                                                       \
+        return convolve_device<T>(d_texture, d_u, d_v, ny, nx, kernel, klen, uv_mode,            \
+                                  Walls{x_left, x_right, y_left, y_right}, iterations, d_work0,  \
+                                  d_work1, d_result, stream);                                    \
+    }                                                                                            \
+    int rlic_b200_pack_uv_##sfx(const T *d_u, const T *d_v, int64_t count, T *d_uv,              \
+                                void *stream)                                                    \
+    {                                                                                            \
+        tls_error.clear();                                                                       \
+        return pack_uv<T>(d_u, d_v, count, d_uv, stream);                                        \
+    }                                                                                            \
+    int rlic_b200_convolve_packed_##sfx(const T *d_texture, const T *d_uv, int64_t ny,           \
+                                        int64_t nx, const T *kernel, int64_t klen, int uv_mode,  \
+                                        int x_left, int x_right, int y_left, int y_right,        \
+                                        int64_t iterations, T *d_work0, T *d_work1,              \
+                                        T **d_result, void *stream)                              \
+    {                                                                                            \
+        tls_error.clear();                                                                       \
+        return convolve_device_packed<T>(d_texture, d_uv, ny, nx, kernel, klen, uv_mode,         \
+                                         Walls{x_left, x_right, y_left, y_right}, iterations,    \
+                                         d_work0, d_work1, d_result, stream);                    \
+    }                                                                                            \
+    int rlic_b200_pass_slab_##sfx(const T *d_texture, const T *d_uv, T *d_out, int64_t ny,       \
+                                  int64_t nx, int64_t row0, int64_t nrows, int64_t halo_lo,      \
+                                  int64_t halo_hi, const T *kernel, int64_t klen, int uv_mode,   \
+                                  int x_left, int x_right, int y_left, int y_right,              \
+                                  void *stream)                                                  \
+    {                                                                                            \
+        tls_error.clear();                                                                       \
+        return pass_slab<T>(d_texture, d_uv, d_out, ny, nx, row0, nrows, halo_lo, halo_hi,       \
+                            kernel, klen, uv_mode, Walls{x_left, x_right, y_left, y_right},      \
+                            stream);                                                             \
+    }                                                                                            \
+    int rlic_b200_convolve_batch_##sfx(const T *texture, const T *u, const T *v,                 \
+                                       int64_t nfields, int64_t ny, int64_t nx, const T *kernel, \
+                                       int64_t klen, int uv_mode, int x_left, int x_right,       \
+                                       int y_left, int y_right, int64_t iterations,              \
+                                       const int *devices, int ndev, T *out)                     \
+    {                                                                                            \
+        tls_error.clear();                                                                       \
+        return convolve_batch<T>(texture, u, v, nfields, ny, nx, kernel, klen, uv_mode,          \
+                                 Walls{x_left, x_right, y_left, y_right}, iterations, devices,   \
+                                 ndev, out);                                                     \
+    }
+
+RLIC_DEFINE(float, f32)
+RLIC_DEFINE(double, f64)
+
+}  // extern "C"

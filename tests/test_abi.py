@@ -1,0 +1,108 @@
+"""The C-ABI shared library: loads, exports what include/rlic_b200.h declares,
+and refuses to compute without a GPU (no CPU fallback).  No compute calls here
+unless a device is present."""
+
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from rlic_b200 import _core
+
+ROOT = Path(__file__).resolve().parent.parent
+HEADER = (ROOT / "include" / "rlic_b200.h").read_text()
+
+
+def declared_symbols() -> list[str]:
+    # every function prototype in the header: "<ret> rlic_b200_name("
+    names = re.findall(r"^\s*(?:const\s+)?[A-Za-z_0-9]+\s*\*?\s*(rlic_b200_[a-z0-9_]+)\s*\(", HEADER, re.M)
+    return sorted(set(names))
+
+
+def test_header_declares_the_expected_surface():
+    names = declared_symbols()
+    for base in ("convolve", "convolve_device", "convolve_packed", "pack_uv", "pass_slab", "convolve_batch"):
+        for sfx in ("f32", "f64"):
+            assert f"rlic_b200_{base}_{sfx}" in names
+    for misc in ("abi_version", "last_error", "device_count", "launch_count", "set_device"):
+        assert f"rlic_b200_{misc}" in names
+
+
+@pytest.mark.parametrize("symbol", declared_symbols())
+def test_library_exports_every_declared_symbol(symbol):
+    assert hasattr(_core.lib, symbol), f"{symbol} declared in the header but not exported"
+
+
+def test_no_torch_or_cuda_types_in_signatures():
+    body = re.sub(r"/\*.*?\*/", "", HEADER, flags=re.S)   # prototypes only, comments dropped
+    for forbidden in ("at::", "torch", "cudaStream_t", "CUstream", "Tensor"):
+        assert forbidden not in body
+
+
+def test_abi_version_matches_binding():
+    assert _core.lib.rlic_b200_abi_version() == _core.ABI_VERSION
+    m = re.search(r"#define RLIC_B200_ABI_VERSION (\d+)", HEADER)
+    assert int(m.group(1)) == _core.ABI_VERSION
+
+
+def test_error_codes_match_header():
+    for name, value in (("OK", 0), ("EINVAL", 1), ("ENODEVICE", 2), ("ECUDA", 3), ("ESHARD", 4)):
+        m = re.search(rf"#define RLIC_B200_{name} (\d+)", HEADER)
+        assert int(m.group(1)) == value == getattr(_core, name)
+
+
+def test_bad_arguments_are_reported_not_fatal():
+    # argument checks run before any CUDA call, so this works without a GPU
+    p = ctypes.POINTER(ctypes.c_float)
+    a = np.zeros((4, 4), dtype=np.float32)
+    out = np.empty_like(a)
+    k = np.ones(3, dtype=np.float32)
+    ptr = lambda x: x.ctypes.data_as(p)  # noqa: E731
+    f = _core.lib.rlic_b200_convolve_f32
+    # empty kernel: the reference aborts the interpreter here (lib.rs:371,378)
+    assert f(ptr(a), ptr(a), ptr(a), 4, 4, ptr(k), 0, 0, 0, 0, 0, 0, 1, ptr(out)) == _core.EINVAL
+    assert b"empty" in _core.lib.rlic_b200_last_error()
+    assert f(ptr(a), ptr(a), ptr(a), 4, 4, ptr(k), 3, 7, 0, 0, 0, 0, 1, ptr(out)) == _core.EINVAL
+    assert f(ptr(a), ptr(a), ptr(a), 4, 4, ptr(k), 3, 0, 0, 9, 0, 0, 1, ptr(out)) == _core.EINVAL
+    assert f(ptr(a), ptr(a), ptr(a), -1, 4, ptr(k), 3, 0, 0, 0, 0, 0, 1, ptr(out)) == _core.EINVAL
+    with pytest.raises(ValueError, match="empty convolution kernel"):
+        _core.convolve_f32(a, (a, a, "velocity"), np.ones(0, dtype=np.float32),
+                           (("closed", "closed"), ("closed", "closed")), 1)
+
+
+def test_core_rejects_wrong_dtype_like_the_pyo3_signature():
+    a64 = np.zeros((4, 4))
+    k64 = np.ones(3)
+    walls = (("closed", "closed"), ("closed", "closed"))
+    with pytest.raises(TypeError, match="texture"):
+        _core.convolve_f32(a64, (a64, a64, "velocity"), k64, walls, 1)
+    with pytest.raises(TypeError, match="kernel"):
+        _core.convolve_f64(a64, (a64, a64, "velocity"), np.ones((3, 3)), walls, 1)
+
+
+def test_empty_images_need_no_device():
+    walls = (("closed", "closed"), ("closed", "closed"))
+    for shape in ((0, 5), (5, 0), (0, 0)):
+        a = np.zeros(shape, dtype=np.float32)
+        out = _core.convolve_f32(a, (a, a, "velocity"), np.ones(3, dtype=np.float32), walls, 2)
+        assert out.shape == shape and out.dtype == np.float32
+
+
+@pytest.mark.skipif(_core.device_count() > 0, reason="a GPU is present")
+def test_without_a_gpu_the_product_fails_loudly():
+    import rlic_b200
+
+    img = np.random.default_rng(0).random((8, 8))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        rlic_b200.convolve(img, img, img, kernel=np.ones(3))
+
+
+def test_product_never_imports_the_oracle():
+    # the oracle is test infrastructure; the package must not reference it
+    pkg = ROOT / "rlic_b200"
+    for path in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")):
+        text = path.read_text()
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), path
+        assert "liblic_oracle" not in text, path

@@ -1,0 +1,267 @@
+"""Bit-for-bit parity of the CUDA path with the CPU oracle (crate-default
+arithmetic: fma + branchless), through the public API and the raw C ABI.
+
+Covers the edge cases listed in SURVEY.md section 4: exact zeros and signed
+zeros, NaN, kernels longer than the image, even kernels, L in {1, 2}, 1xN / Nx1
+images, strided and stride-0 inputs, every boundary combination, both modes and
+dtypes, tile-edge sizes, the frozen golden vectors, and the BASELINE configs.
+"""
+
+import ctypes
+import threading
+
+import numpy as np
+import pytest
+from numpy.testing import assert_array_equal
+
+import oracle
+import rlic_b200 as rlic
+from rlic_b200 import _core, workloads
+
+from golden_cases import CASES, as_spec, expected, load
+
+pytestmark = pytest.mark.gpu
+
+WALLS = {
+    "closed": (("closed", "closed"), ("closed", "closed")),
+    "periodic": (("periodic", "periodic"), ("periodic", "periodic")),
+    "x-periodic": (("periodic", "periodic"), ("closed", "closed")),
+    "y-periodic": (("closed", "closed"), ("periodic", "periodic")),
+}
+
+
+def random_case(shape, dtype, klen, seed, specials=True):
+    rng = np.random.default_rng(seed)
+    tex = rng.random(shape).astype(dtype)
+    u = (rng.random(shape) - 0.5).astype(dtype)
+    v = (rng.random(shape) - 0.5).astype(dtype)
+    if specials and min(shape) >= 8:
+        u[1, 2] = v[1, 2] = 0.0
+        u[3, 4] = np.nan
+        v[5, 1] = -0.0
+        u[2, 5], v[2, 5] = -0.0, 0.0
+        u[4, 3] = 0.0
+        v[6, 6] = np.nan
+    kernel = (rng.random(klen) - 0.2).astype(dtype)
+    return tex, u, v, kernel
+
+
+def check(tex, u, v, kernel, mode="velocity", walls="closed", iterations=1):
+    bnd = WALLS[walls]
+    got = rlic.convolve(tex, u, v, kernel=kernel, uv_mode=mode, boundaries=as_spec(bnd),
+                        iterations=iterations)
+    want = oracle.convolve(tex, u, v, kernel=kernel, uv_mode=mode, boundaries=bnd,
+                           iterations=iterations)
+    assert got.dtype == tex.dtype and got.shape == tex.shape
+    assert_array_equal(got, want)   # NaNs compare equal position-wise here
+    return got
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_golden_vectors(name):
+    mode, bnd, its = CASES[name]
+    tex, u, v, kernel = load(name)
+    got = rlic.convolve(tex, u, v, kernel=kernel, uv_mode=mode, boundaries=as_spec(bnd), iterations=its)
+    assert_array_equal(got, expected(name, 3))
+
+
+@pytest.mark.parametrize("walls", WALLS)
+@pytest.mark.parametrize("mode", ["velocity", "polarization"])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_random_fields_with_special_pixels(dtype, mode, walls):
+    check(*random_case((45, 70), dtype, 23, seed=11), mode=mode, walls=walls, iterations=2)
+
+
+@pytest.mark.parametrize("klen", [1, 2, 3, 4, 5, 8, 33, 64, 200])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_kernel_lengths_including_longer_than_image(dtype, klen):
+    check(*random_case((19, 21), dtype, klen, seed=klen), mode="polarization", walls="x-periodic")
+    check(*random_case((19, 21), dtype, klen, seed=klen + 1), walls="periodic", iterations=2)
+
+
+def test_taps_beyond_the_parameter_block_use_the_global_path():
+    # > 768 f32 taps / > 384 f64 taps do not fit the launch-parameter block
+    check(*random_case((9, 12), np.float32, 1001, seed=5), walls="periodic")
+    check(*random_case((9, 12), np.float64, 500, seed=6), mode="polarization", walls="closed")
+
+
+@pytest.mark.parametrize(
+    "shape", [(1, 1), (1, 40), (40, 1), (2, 2), (8, 32), (9, 33), (7, 31), (16, 64), (17, 65), (64, 3)]
+)
+def test_degenerate_and_tile_edge_shapes(shape):
+    for walls in ("closed", "periodic"):
+        check(*random_case(shape, np.float64, 9, seed=sum(shape), specials=False), walls=walls,
+              mode="polarization", iterations=2)
+
+
+def test_uniform_and_axis_aligned_fields():
+    rng = np.random.default_rng(3)
+    tex = rng.random((40, 50))
+    one, zero = np.ones_like(tex), np.zeros_like(tex)
+    k = np.linspace(0.1, 1, 15)
+    for u, v in ((one, zero), (zero, one), (-one, zero), (zero, -one), (one, one), (-one, one),
+                 (zero, zero), (-zero, zero), (one, -one)):
+        for walls in WALLS:
+            check(tex, u, v, k, walls=walls)
+            check(tex, u, v, k, mode="polarization", walls=walls)
+
+
+def test_fields_with_exact_grid_zeros():
+    # the branchless formula turns +-0 velocities into 0/0 when the walker sits
+    # exactly on an edge (last table rows)
+    n = 64
+    x = np.linspace(0, np.pi, n)
+    rng = np.random.default_rng(0)
+    tex = rng.random((n, n))
+    u = np.broadcast_to(np.cos(2 * x), (n, n))
+    v = np.broadcast_to(np.sin(x), (n, n))          # v[:, 0] == +0.0 exactly
+    assert v[0, 0] == 0.0
+    k = workloads.triangle_kernel(65, np.float64)
+    for walls in WALLS:
+        check(tex, u, v, k, walls=walls, iterations=2)
+    check(tex.astype(np.float32), u.astype(np.float32), v.astype(np.float32),
+          k.astype(np.float32), walls="periodic")
+
+
+def test_infinite_and_huge_velocities():
+    tex, u, v, k = random_case((24, 24), np.float32, 13, seed=8)
+    u[7, 7] = np.inf
+    v[8, 8] = -np.inf
+    u[9, 9] = 3e38
+    v[9, 9] = -3e38
+    u[10, 10] = 1e-45    # denormal
+    v[11, 11] = -1e-42
+    check(tex, u, v, k, walls="periodic", iterations=2)
+    check(tex, u, v, k, mode="polarization")
+
+
+def test_negative_kernel_values_and_nan_texture():
+    tex, u, v, k = random_case((20, 20), np.float64, 9, seed=4)
+    tex[5, 5] = np.nan
+    k[2] = -3.0
+    check(tex, u, v, k, iterations=2)
+
+
+def test_strided_and_broadcast_inputs():
+    rng = np.random.default_rng(2)
+    big = rng.random((60, 90))
+    tex = big[::2, ::3]                                # non-contiguous view
+    u = np.broadcast_to(rng.random(30) - 0.5, (30, 30))  # stride-0 rows
+    v = (rng.random((30, 30)) - 0.5).T                 # F-order
+    k = np.linspace(0, 1, 12)[::-1]                    # negative stride
+    got = check(tex, u, v, k, walls="y-periodic")
+    assert got.flags.c_contiguous
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_many_iterations(dtype):
+    check(*random_case((33, 47), dtype, 7, seed=9), iterations=11, walls="periodic")
+
+
+def test_c1_readme_example():
+    w = workloads.readme_example()
+    got = rlic.convolve(w.texture, w.u, w.v, **w.kwargs())
+    p = ("periodic", "periodic")
+    assert_array_equal(got, oracle.convolve(w.texture, w.u, w.v, kernel=w.kernel, boundaries=(p, p)))
+    got5 = rlic.convolve(w.texture, w.u, w.v, kernel=w.kernel, boundaries="periodic", iterations=5)
+    assert_array_equal(
+        got5, oracle.convolve(w.texture, w.u, w.v, kernel=w.kernel, boundaries=(p, p), iterations=5)
+    )
+
+
+def test_c2_shape_reduced():
+    w = workloads.vortex_noise(512, iterations=5)
+    got = rlic.convolve(w.texture, w.u, w.v, **w.kwargs())
+    want = oracle.convolve(w.texture, w.u, w.v, kernel=w.kernel, iterations=5,
+                           threads=oracle.max_threads())
+    assert_array_equal(got, want)
+
+
+def test_c3_polarization_reduced():
+    w = workloads.polarization_split(256, taps=129)
+    got = rlic.convolve(w.texture, w.u, w.v, **w.kwargs())
+    bnd = (("periodic", "periodic"), ("closed", "closed"))
+    want = oracle.convolve(w.texture, w.u, w.v, kernel=w.kernel, uv_mode="polarization", boundaries=bnd)
+    assert_array_equal(got, want)
+
+
+def test_c2_full_size_against_oracle_bands_and_properties():
+    """4096^2 f32, 65 taps: pass 1 checked on bands against the oracle, all five
+    passes checked through size-independent properties."""
+    w = workloads.vortex_noise(4096, iterations=5)
+    one = rlic.convolve(w.texture, w.u, w.v, kernel=w.kernel, iterations=1)
+    for r0 in (0, 1000, 2040, 4096 - 24):
+        band = oracle.pass_rows(w.texture, w.u, w.v, kernel=w.kernel, rows=(r0, r0 + 24))
+        assert_array_equal(one[r0:r0 + 24], band)
+    five = rlic.convolve(w.texture, w.u, w.v, **w.kwargs())
+    # iterations compose: 5 = 1 + 4
+    four_more = rlic.convolve(one, w.u, w.v, kernel=w.kernel, iterations=4)
+    assert_array_equal(five, four_more)
+    # transpose symmetry (reference tests/test_convolution.py:69-82) at full size
+    sym = rlic.convolve(w.texture.T, w.v.T, w.u.T, kernel=w.kernel, iterations=5).T
+    assert_array_equal(five, sym)
+    assert np.isfinite(five).all()
+
+
+def test_c2_full_size_full_oracle():
+    """The whole 5-iteration headline configuration against the oracle on all
+    host cores (a few seconds per iteration per 8 cores)."""
+    w = workloads.vortex_noise(4096, iterations=5)
+    got = rlic.convolve(w.texture, w.u, w.v, **w.kwargs())
+    want = oracle.convolve(w.texture, w.u, w.v, kernel=w.kernel, iterations=5,
+                           threads=oracle.max_threads())
+    assert_array_equal(got, want)
+
+
+def test_mismatch_fraction_against_the_pypi_x86_64_variant():
+    # informational bound: the fma+branching build (PyPI x86_64 wheels) may
+    # differ in the last bits; north_star tolerance is 1e-5 of the range in f32
+    w = workloads.vortex_noise(512, iterations=1)
+    got = rlic.convolve(w.texture, w.u, w.v, kernel=w.kernel)
+    other = oracle.convolve(w.texture, w.u, w.v, kernel=w.kernel, variant=oracle.VARIANT_FMA)
+    assert np.abs(got - other).max() <= 1e-5 * np.ptp(other)
+
+
+def test_concurrent_calls_are_independent():
+    cases = [random_case((64, 64), np.float32, 9 + 2 * t, seed=40 + t) for t in range(6)]
+    want = [oracle.convolve(t, u, v, kernel=k, iterations=3) for t, u, v, k in cases]
+    got = [None] * len(cases)
+
+    def work(i):
+        t, u, v, k = cases[i]
+        for _ in range(5):
+            got[i] = rlic.convolve(t, u, v, kernel=k, iterations=3)
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(cases))]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    for g, w_ in zip(got, want):
+        assert_array_equal(g, w_)
+
+
+def test_batch_entry_point_matches_per_field_calls():
+    rng = np.random.default_rng(12)
+    nf, ny, nx = 5, 40, 56
+    tex = rng.random((nf, ny, nx), dtype=np.float32)
+    u = rng.random((nf, ny, nx), dtype=np.float32) - 0.5
+    v = rng.random((nf, ny, nx), dtype=np.float32) - 0.5
+    u[2, 3, 3] = np.nan
+    k = workloads.triangle_kernel(33, np.float32)
+    out = np.empty_like(tex)
+    p = ctypes.POINTER(ctypes.c_float)
+    rc = _core.lib.rlic_b200_convolve_batch_f32(
+        tex.ctypes.data_as(p), u.ctypes.data_as(p), v.ctypes.data_as(p), nf, ny, nx,
+        k.ctypes.data_as(p), k.size, 0, 0, 0, 1, 1, 3, None, 0, out.ctypes.data_as(p))
+    _core.check(rc)
+    bnd = (("closed", "closed"), ("periodic", "periodic"))
+    for f in range(nf):
+        assert_array_equal(out[f], oracle.convolve(tex[f], u[f], v[f], kernel=k, boundaries=bnd, iterations=3))
+
+
+def test_launch_counter_counts_passes():
+    tex, u, v, k = random_case((16, 16), np.float32, 5, seed=1, specials=False)
+    before = _core.launch_count()
+    rlic.convolve(tex, u, v, kernel=k, iterations=4)
+    assert _core.launch_count() - before == 4 + 1   # 4 passes + the field interleave
