@@ -1,0 +1,408 @@
+#!/usr/bin/env python
+"""Benchmark of the rlic.convolve hot path on B200 (contract: see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one full `convolve` call on the headline configuration
+(BASELINE.json configs[1]: 4096x4096 f32 noise, analytic vortex, 65-tap triangle
+kernel, closed boundaries, iterations=5).  With N > 1 ranks the image is N times
+taller ((N*4096) x 4096), split into row slabs with a per-iteration halo
+exchange: per-GPU work is fixed, i.e. weak scaling.
+
+Prints ONE JSON line on rank 0.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+N_SIDE = 4096
+TAPS = 65
+ITERATIONS = 5
+METRIC = "Mpix/s"
+
+
+# ----------------------------------------------------------------------------
+def measured_peak_gbs() -> tuple[float, str]:
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        try:
+            return float(json.loads(f.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines: list[str] = []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self) -> dict:
+        sm, smax, power, reasons = [], [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+                power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, parts[4:8]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax),
+                "power_w_max": max(power), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_slab(rank: int, world: int):
+    """This rank's rows of the (world*4096) x 4096 weak-scaling image."""
+    from rlic_b200 import workloads
+
+    ny = N_SIDE * world
+    rng = np.random.default_rng(rank)
+    texture = rng.random((N_SIDE, N_SIDE), dtype=np.float32)
+    y = np.linspace(-1, 1, ny, dtype=np.float64)[rank * N_SIDE:(rank + 1) * N_SIDE]
+    x = np.linspace(-1, 1, N_SIDE, dtype=np.float64)
+    u = np.broadcast_to((-y)[:, None], (N_SIDE, N_SIDE)).astype(np.float32)
+    v = np.broadcast_to(x[None, :], (N_SIDE, N_SIDE)).astype(np.float32)
+    return texture, u, v, workloads.triangle_kernel(TAPS, np.float32)
+
+
+def gather_bytes_per_pixel() -> int:
+    # u, v once per step, texture once per step + centre, one store
+    return (3 * (TAPS - 1) + 2) * 4
+
+
+# ----------------------------------------------------------------------------
+def cpu_baseline(threads: int | None, budget_s: float, rank: int = 0) -> dict:
+    """Times the CPU oracle (restatement of the reference's Rust core) on a
+    band of rows of pass 1 of the same workload, sized for ~budget_s seconds."""
+    import oracle
+
+    texture, u, v, kernel = make_slab(0, 1)
+    threads = threads or oracle.max_threads()
+    # calibrate on a thin band (also warms the caches), then size the sample
+    t0 = time.perf_counter()
+    oracle.convolve(texture[:64], u[:64], v[:64], kernel=kernel, threads=threads)
+    calib = time.perf_counter() - t0
+    rows = int(min(N_SIDE, max(64, 64 * budget_s / max(calib, 1e-6))))
+    rows -= rows % 8
+    r0 = (N_SIDE - rows) // 2
+    import ctypes
+
+    out = np.zeros_like(texture)
+    # the band walks inside the full image (true halo context), row-parallel over threads
+    t0 = time.perf_counter()
+    if threads == 1:
+        oracle.pass_rows(texture, u, v, kernel=kernel, rows=(r0, r0 + rows))
+    else:
+        # oracle.convolve on the band plus TAPS//2 rows of context each side
+        h = TAPS // 2
+        a, b = max(0, r0 - h), min(N_SIDE, r0 + rows + h)
+        oracle.convolve(texture[a:b], u[a:b], v[a:b], kernel=kernel, threads=threads)
+        rows = b - a
+    dt = time.perf_counter() - t0
+    del out, ctypes
+    mpix = rows * N_SIDE / dt / 1e6
+    return {
+        "value": mpix, "unit": METRIC, "cores": threads, "kind": "port",
+        "sample": (f"one pass over a {rows}-row band of the 4096x4096 f32 65-tap vortex workload "
+                   f"({rows * N_SIDE * (TAPS - 1) / 1e6:.0f} M pixel-steps) in {dt:.2f} s on {threads} "
+                   "thread(s); C restatement of the reference's Rust core (oracle/lic_oracle.c, "
+                   "fma+branchless), the reference itself is single-threaded"),
+        "ns_per_pixel_step": dt / (rows * N_SIDE * (TAPS - 1)) * 1e9 * threads,
+        "seconds": dt,
+    }
+
+
+def run_reference(args) -> dict:
+    """--impl reference: the CPU implementation of the path on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return {}
+    vals = []
+    info = None
+    per_step = max(2.0, min(20.0, 90.0 / max(1, args.steps + args.warmup)))
+    for i in range(args.warmup + args.steps):
+        info = cpu_baseline(None, per_step)
+        if i >= args.warmup:
+            vals.append(info)
+    mpix = statistics.mean(x["value"] for x in vals)
+    ms = statistics.mean(x["seconds"] for x in vals) * 1e3
+    single = cpu_baseline(1, 4.0)
+    info = dict(info)
+    info["value"] = mpix
+    info["single_thread_value"] = single["value"]
+    info["single_thread_ns_per_pixel_step"] = single["ns_per_pixel_step"]
+    return {
+        "impl": "reference", "metric": METRIC, "value": mpix, "unit": METRIC, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(1),
+        "pixel_steps_per_s": mpix * 1e6 * (TAPS - 1),
+        "cpu_baseline": info,
+        "e2e": {"value": mpix, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+
+
+def workload_config(world: int) -> dict:
+    return {
+        "workload": (f"BASELINE configs[1] per GPU: {N_SIDE * world}x{N_SIDE} f32 noise, analytic vortex, "
+                     f"{TAPS}-tap triangle kernel, closed boundaries, iterations={ITERATIONS}"
+                     + (f", row slabs over {world} GPUs with a {TAPS // 2}-row halo exchange per iteration"
+                        if world > 1 else "")),
+        "image": [N_SIDE * world, N_SIDE], "taps": TAPS, "iterations": ITERATIONS,
+        "boundaries": "closed", "uv_mode": "velocity",
+        "l2": "inputs larger than L2 (texture 64 MiB + packed field 128 MiB + output 64 MiB per GPU vs 126 MB)",
+        "step": "pack (u,v) + 5 passes" if world == 1 else "5 x (edge strips, halo exchange, interior)",
+    }
+
+
+# ----------------------------------------------------------------------------
+def run_ours(args) -> dict:
+    import torch
+
+    import rlic_b200
+    from rlic_b200 import _core
+    from rlic_b200.device import convolve_device, pack_field
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run for --gpus > 1")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (rlic_b200 has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    _core.check(_core.lib.rlic_b200_set_device(local))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+
+    texture, u, v, kernel = make_slab(rank, world)
+    pixels_local = texture.size
+    h2d = texture.nbytes + u.nbytes + v.nbytes + kernel.nbytes
+    d2h = texture.nbytes
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident: `value` and the kernel roofline -------
+    d_tex = torch.from_numpy(texture).to(dev)
+    d_u = torch.from_numpy(np.ascontiguousarray(u)).to(dev)
+    d_v = torch.from_numpy(np.ascontiguousarray(v)).to(dev)
+    work = (torch.empty_like(d_tex), torch.empty_like(d_tex))
+    uv_buf = torch.empty((*d_tex.shape, 2), dtype=d_tex.dtype, device=dev)
+
+    if world == 1:
+        def step(events=None):
+            field = pack_field(d_u, d_v, out=uv_buf)
+            if events is not None:
+                events[0].record()
+            out = convolve_device(d_tex, field=field, kernel=kernel, boundaries="closed",
+                                  iterations=ITERATIONS, work=work)
+            if events is not None:
+                events[1].record()
+            return out
+    else:
+        from rlic_b200.sharded import ShardedConvolver
+
+        sc = ShardedConvolver(N_SIDE * world, N_SIDE, kernel=kernel, boundaries="closed")
+        sc.set_field(d_u, d_v)
+
+        def step(events=None):
+            if events is not None:
+                events[0].record()
+            out = sc.convolve(d_tex, iterations=ITERATIONS)
+            if events is not None:
+                events[1].record()
+            return out
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(args.steps)]
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = _core.launch_count()
+    with ClockSampler(local) as clocks:
+        barrier()
+        t_begin.record()
+        for k in range(args.steps):
+            result = step(ev[k])
+        t_end.record()
+        barrier()
+    launches = _core.launch_count() - launches0
+    total_ms = t_begin.elapsed_time(t_end)
+    pass_ms = sum(a.elapsed_time(b) for a, b in ev)   # the 5 passes of every step
+    if dist is not None:
+        t = torch.tensor([total_ms, pass_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, pass_ms = t.tolist()
+        n_l = torch.tensor([launches], device=dev, dtype=torch.int64)
+        dist.all_reduce(n_l)
+        launches = int(n_l.item())
+    ms_per_step = total_ms / args.steps
+    pixels_all = pixels_local * world
+    value = pixels_all * ITERATIONS / (ms_per_step * 1e-3) / 1e6
+
+    passes = args.steps * ITERATIONS
+    pass_avg_ms = pass_ms / passes
+    peak, peak_src = measured_peak_gbs()
+    achieved = gather_bytes_per_pixel() * pixels_local / (pass_avg_ms * 1e-3) / 1e9
+    traffic = None
+    tf = ROOT / "profiles" / "traffic.json"
+    if tf.exists() and world == 1:
+        try:
+            traffic = json.loads(tf.read_text()).get("lic_pass_kernel_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {
+        "bound": "hbm", "kernel": "lic_pass_kernel<float,...> (one pass over this GPU's pixels)",
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "peak_source": peak_src, "traffic": traffic,
+        "algorithmic_bytes_per_launch": gather_bytes_per_pixel() * pixels_local,
+        "launch_ms": pass_avg_ms,
+        "note": "achieved = (3*(L-1)+2)*4 gather bytes per pixel x pixels per launch / mean launch time",
+    }
+
+    # ---------------- end to end through the public API, host buffers ---------
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()  # noqa: E731
+    h_tex, h_u, h_v = pin(texture), pin(u), pin(v)
+    e2e = None
+    if world == 1:
+        for _ in range(2):
+            rlic_b200.convolve(h_tex, h_u, h_v, kernel=kernel, boundaries="closed", iterations=ITERATIONS)
+        torch.cuda.synchronize()
+        n_e2e = max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            out = rlic_b200.convolve(h_tex, h_u, h_v, kernel=kernel, boundaries="closed",
+                                     iterations=ITERATIONS)
+        dt = (time.perf_counter() - t0) / n_e2e
+        e2e_val = pixels_all * ITERATIONS / dt / 1e6
+        e2e_ms = dt * 1e3
+        assert np.array_equal(out, result.cpu().numpy()), "host and device paths disagree"
+    else:
+        # each rank moves its slab host -> device, runs the sharded passes, reads its slab back
+        pinned_out = torch.empty(texture.shape, dtype=torch.float32).pin_memory()
+        t_u, t_v, t_t = (torch.from_numpy(a) for a in (h_u, h_v, h_tex))
+
+        def e2e_step():
+            a_u, a_v, a_t = (t.to(dev, non_blocking=True) for t in (t_u, t_v, t_tex_ref[0]))
+            sc.set_field(a_u, a_v)
+            res = sc.convolve(a_t, iterations=ITERATIONS)
+            pinned_out.copy_(res, non_blocking=True)
+
+        t_tex_ref = [t_t]
+        e2e_step()
+        barrier()
+        n_e2e = max(3, min(args.steps, 10))
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n_e2e):
+            e2e_step()
+        b.record()
+        barrier()
+        t = torch.tensor([a.elapsed_time(b)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = t.item() / n_e2e
+        e2e_val = pixels_all * ITERATIONS / (e2e_ms * 1e-3) / 1e6
+    e2e = {"value": e2e_val, "unit": METRIC, "h2d_bytes_per_step": h2d * world,
+           "d2h_bytes_per_step": d2h * world, "ms_per_step": e2e_ms,
+           "api": "rlic_b200.convolve(numpy arrays in pinned host memory)" if world == 1
+                  else "per rank: pinned host slab -> ShardedConvolver -> pinned host slab"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(world),
+        "pixel_steps_per_s": value * 1e6 * (TAPS - 1),
+        "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(None, 12.0)
+        line["cpu_baseline"]["single_thread"] = cpu_baseline(1, 4.0)
+    elif rank == 0:
+        line["cpu_baseline"] = None
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return line if rank == 0 else {}
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    line = run_reference(args) if args.impl == "reference" else run_ours(args)
+    if line:
+        print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

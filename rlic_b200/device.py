@@ -1,0 +1,133 @@
+"""Device-resident entry points.
+
+``convolve`` in ``rlic_b200._lib`` mirrors the reference's NumPy contract and
+therefore pays two PCIe trips per call.  Callers whose data already lives on
+the GPU use these functions instead: same arithmetic, same C ABI underneath
+(``rlic_b200_pack_uv_*`` / ``rlic_b200_convolve_packed_*`` /
+``rlic_b200_pass_slab_*``), torch tensors in and out.  torch is used for device
+memory and streams only.
+"""
+
+from __future__ import annotations
+
+__all__ = ["PackedField", "convolve_device", "pack_field"]
+
+import ctypes
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from rlic_b200 import _core
+from rlic_b200._boundaries import BoundarySet
+
+_SFX = {torch.float32: ("f32", ctypes.c_float, np.float32), torch.float64: ("f64", ctypes.c_double, np.float64)}
+
+
+def _kind(t: torch.Tensor):
+    try:
+        return _SFX[t.dtype]
+    except KeyError:
+        raise TypeError(f"expected float32 or float64 tensors, got {t.dtype}") from None
+
+
+def _stream_handle(stream) -> int:
+    s = torch.cuda.current_stream() if stream is None else stream
+    return int(s.cuda_stream)
+
+
+def _walls(boundaries) -> tuple[int, int, int, int]:
+    bs = BoundarySet.from_spec(boundaries)
+    if bs is None:
+        raise TypeError(f"Invalid boundary specification {boundaries}")
+    bs.validate()
+    return _core.wall_codes((bs.x, bs.y))
+
+
+def _host_taps(kernel, np_dtype) -> np.ndarray:
+    if isinstance(kernel, torch.Tensor):
+        kernel = kernel.detach().cpu().numpy()
+    kernel = np.ascontiguousarray(kernel, dtype=np_dtype)
+    if kernel.ndim != 1:
+        raise ValueError(f"Expected a kernel with exactly one dimension. Got kernel.ndim={kernel.ndim}")
+    if not np.isfinite(kernel).all():
+        raise ValueError("Found non-finite value(s) in kernel.")
+    return kernel
+
+
+def _check_image(name: str, t: torch.Tensor, like: torch.Tensor | None = None) -> None:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError(f"{name} must be a CUDA tensor")
+    if t.dim() != 2 or not t.is_contiguous():
+        raise ValueError(f"{name} must be a contiguous 2-D tensor")
+    if like is not None and (t.shape != like.shape or t.dtype != like.dtype or t.device != like.device):
+        raise ValueError(f"{name} must match the texture's shape, dtype and device")
+
+
+@dataclass
+class PackedField:
+    """A vector field in the kernels' native layout: ``uv[i, j] = (u, v)``."""
+
+    uv: torch.Tensor   # (ny, nx, 2), contiguous
+
+    @property
+    def shape(self) -> tuple[int, int]:
+        return tuple(self.uv.shape[:2])
+
+
+def pack_field(u: torch.Tensor, v: torch.Tensor, *, out: torch.Tensor | None = None,
+               stream=None) -> PackedField:
+    """Interleave two planar components on the device (one streaming kernel)."""
+    _check_image("u", u)
+    _check_image("v", v, u)
+    sfx, _, _ = _kind(u)
+    uv = torch.empty((*u.shape, 2), dtype=u.dtype, device=u.device) if out is None else out
+    with torch.cuda.device(u.device):
+        rc = getattr(_core.lib, f"rlic_b200_pack_uv_{sfx}")(
+            u.data_ptr(), v.data_ptr(), u.numel(), uv.data_ptr(), _stream_handle(stream))
+    _core.check(rc)
+    return PackedField(uv)
+
+
+def convolve_device(texture: torch.Tensor, u: torch.Tensor | None = None, v: torch.Tensor | None = None,
+                    *, kernel, field: PackedField | None = None, uv_mode: str = "velocity",
+                    boundaries="closed", iterations: int = 1,
+                    work: tuple[torch.Tensor, torch.Tensor] | None = None, stream=None) -> torch.Tensor:
+    """``rlic_b200.convolve`` for CUDA tensors; returns a new CUDA tensor.
+
+    Pass either planar ``u, v`` or a pre-packed ``field`` (saves the interleave
+    when the same field is reused).  ``work`` optionally supplies the two
+    texture-sized scratch tensors; the result is one of them.  Work is enqueued
+    on ``stream`` (default: torch's current stream) without synchronising.
+    """
+    _check_image("texture", texture)
+    sfx, real, np_dtype = _kind(texture)
+    if iterations < 0:
+        raise ValueError(
+            f"Invalid number of iterations: {iterations}\nExpected a strictly positive integer.")
+    taps = _host_taps(kernel, np_dtype)
+    walls = _walls(boundaries)
+    mode = _core.mode_code(uv_mode)
+    if iterations == 0:
+        return texture.clone()
+    with torch.cuda.device(texture.device):
+        if field is None:
+            if u is None or v is None:
+                raise TypeError("pass u and v, or field=")
+            _check_image("u", u, texture)
+            _check_image("v", v, texture)
+            field = pack_field(u, v, stream=stream)
+        elif field.shape != tuple(texture.shape) or field.uv.dtype != texture.dtype:
+            raise ValueError("field must match the texture's shape and dtype")
+        if work is None:
+            work = (torch.empty_like(texture), torch.empty_like(texture) if iterations > 1 else None)
+        w0, w1 = work
+        result = ctypes.c_void_p()
+        ny, nx = texture.shape
+        rc = getattr(_core.lib, f"rlic_b200_convolve_packed_{sfx}")(
+            texture.data_ptr(), field.uv.data_ptr(), ny, nx,
+            taps.ctypes.data_as(ctypes.POINTER(real)), taps.size, mode, *walls, int(iterations),
+            w0.data_ptr(), w1.data_ptr() if w1 is not None else None,
+            ctypes.byref(result), _stream_handle(stream))
+    _core.check(rc)
+    return w0 if result.value == w0.data_ptr() else w1

@@ -197,10 +197,22 @@ def test_c2_full_size_against_oracle_bands_and_properties():
     # iterations compose: 5 = 1 + 4
     four_more = rlic.convolve(one, w.u, w.v, kernel=w.kernel, iterations=4)
     assert_array_equal(five, four_more)
-    # transpose symmetry (reference tests/test_convolution.py:69-82) at full size
-    sym = rlic.convolve(w.texture.T, w.v.T, w.u.T, kernel=w.kernel, iterations=5).T
-    assert_array_equal(five, sym)
+    # (transpose symmetry is NOT asserted here: the reference breaks ties towards y,
+    # and this analytic field produces exact ties on its diagonals)
     assert np.isfinite(five).all()
+
+
+def test_transpose_symmetry_at_scale():
+    # reference tests/test_convolution.py:69-82, on a tie-free random field, 2048^2 f32
+    rng = np.random.default_rng(21)
+    n = 2048
+    tex = rng.random((n, n), dtype=np.float32)
+    u = rng.random((n, n), dtype=np.float32) - np.float32(0.5)
+    v = rng.random((n, n), dtype=np.float32) - np.float32(0.5)
+    k = workloads.triangle_kernel(65, np.float32)
+    a = rlic.convolve(tex, u, v, kernel=k, iterations=3, boundaries="periodic")
+    b = rlic.convolve(tex.T, v.T, u.T, kernel=k, iterations=3, boundaries="periodic").T
+    assert_array_equal(a, b)
 
 
 def test_c2_full_size_full_oracle():
