@@ -206,7 +206,7 @@ def workload_config(world: int) -> dict:
                         if world > 1 else "")),
         "image": [N_SIDE * world, N_SIDE], "taps": TAPS, "iterations": ITERATIONS,
         "boundaries": "closed", "uv_mode": "velocity",
-        "l2": "inputs larger than L2 (texture 64 MiB + packed field 128 MiB + output 64 MiB per GPU vs 126 MB)",
+        "l2": "inputs larger than L2 (texture 64 MiB + packed field 256 MiB + output 64 MiB per GPU vs 126 MB)",
         "step": "pack (u,v) + 5 passes" if world == 1 else "5 x (edge strips, halo exchange, interior)",
     }
 
@@ -251,7 +251,7 @@ def run_ours(args) -> dict:
     d_u = torch.from_numpy(np.ascontiguousarray(u)).to(dev)
     d_v = torch.from_numpy(np.ascontiguousarray(v)).to(dev)
     work = (torch.empty_like(d_tex), torch.empty_like(d_tex))
-    uv_buf = torch.empty((*d_tex.shape, 2), dtype=d_tex.dtype, device=dev)
+    uv_buf = torch.empty((*d_tex.shape, 4), dtype=d_tex.dtype, device=dev)
 
     if world == 1:
         def step(events=None):

@@ -131,19 +131,26 @@ int rlic_b200_convolve_device_f64(const double *d_texture, const double *d_u, co
                                   double **d_result, void *stream);
 
 /*
- * Packed vector field.  The kernels read the field interleaved, one (u, v)
- * pair per pixel (count pairs = 2*count scalars), because every step of a walk
- * needs both components of the same pixel.  rlic_b200_pack_uv_* builds that
- * layout from two planar device arrays; the *_packed_* and *_slab_* entry
- * points take it directly so that callers who run many passes pack once.
+ * Packed vector field.  The kernels read the field as one record per pixel,
+ *     { u, v, ru, rv }        (4 scalars: 16 bytes for f32, 32 bytes for f64)
+ * where ru, rv are the refined reciprocals that an IEEE division by u, v
+ * computes as its first stage; they are walker- and iteration-invariant, so they
+ * are computed once per pixel here instead of twice per step in the walk.
+ * Pixels with a zero, non-finite or extreme (outside [2^-40, 2^40]) component
+ * carry ru = NaN and take the kernels' generic step.  The layout is private to
+ * the library version that produced it: always build it with
+ * rlic_b200_pack_field_*, from two planar device arrays of `count` scalars into
+ * a device buffer of 4*count scalars, aligned to 4 scalars.  The *_packed_* and
+ * *_slab_* entry points take that buffer, so callers running many passes over
+ * one field pack once.
  */
-int rlic_b200_pack_uv_f32(const float *d_u, const float *d_v, int64_t count,
-                          float *d_uv, void *stream);
-int rlic_b200_pack_uv_f64(const double *d_u, const double *d_v, int64_t count,
-                          double *d_uv, void *stream);
+int rlic_b200_pack_field_f32(const float *d_u, const float *d_v, int64_t count,
+                             float *d_field, void *stream);
+int rlic_b200_pack_field_f64(const double *d_u, const double *d_v, int64_t count,
+                             double *d_field, void *stream);
 
 /* Same as rlic_b200_convolve_device_* with the field already packed. */
-int rlic_b200_convolve_packed_f32(const float *d_texture, const float *d_uv,
+int rlic_b200_convolve_packed_f32(const float *d_texture, const float *d_field,
                                   int64_t ny, int64_t nx,
                                   const float *kernel, int64_t klen,
                                   int uv_mode,
@@ -151,7 +158,7 @@ int rlic_b200_convolve_packed_f32(const float *d_texture, const float *d_uv,
                                   int64_t iterations,
                                   float *d_work0, float *d_work1,
                                   float **d_result, void *stream);
-int rlic_b200_convolve_packed_f64(const double *d_texture, const double *d_uv,
+int rlic_b200_convolve_packed_f64(const double *d_texture, const double *d_field,
                                   int64_t ny, int64_t nx,
                                   const double *kernel, int64_t klen,
                                   int uv_mode,
@@ -164,7 +171,7 @@ int rlic_b200_convolve_packed_f64(const double *d_texture, const double *d_uv,
  * ONE PASS over a row slab — the building block of row-slab sharding
  * (SURVEY.md section 8(e)).  The image has `ny` x `nx` pixels globally; this
  * device holds global rows [row0 - halo_lo, row0 + nrows + halo_hi) of the
- * texture (d_texture) and of the packed field (d_uv) in buffers whose first
+ * texture (d_texture) and of the packed field (d_field) in buffers whose first
  * row is global row `row0 - halo_lo`, and computes output rows
  * [row0, row0 + nrows) into d_out (first row = row0, no halo).
  * The image-level wall rules (lib.rs:83-95) are applied in global row numbers;
@@ -174,7 +181,7 @@ int rlic_b200_convolve_packed_f64(const double *d_texture, const double *d_uv,
  * bounds the slab on that side, otherwise RLIC_B200_ESHARD.
  * With row0 = 0, nrows = ny and no halo this is one pass of the whole image.
  */
-int rlic_b200_pass_slab_f32(const float *d_texture, const float *d_uv,
+int rlic_b200_pass_slab_f32(const float *d_texture, const float *d_field,
                             float *d_out,
                             int64_t ny, int64_t nx,
                             int64_t row0, int64_t nrows, int64_t halo_lo, int64_t halo_hi,
@@ -183,7 +190,7 @@ int rlic_b200_pass_slab_f32(const float *d_texture, const float *d_uv,
                             int x_left, int x_right, int y_left, int y_right,
                             void *stream);
 
-int rlic_b200_pass_slab_f64(const double *d_texture, const double *d_uv,
+int rlic_b200_pass_slab_f64(const double *d_texture, const double *d_field,
                             double *d_out,
                             int64_t ny, int64_t nx,
                             int64_t row0, int64_t nrows, int64_t halo_lo, int64_t halo_hi,

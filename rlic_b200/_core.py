@@ -5,9 +5,9 @@ the reference's native module ``rlic._core``
     convolve_f32(texture, (u, v, uv_mode), kernel, ((xl, xr), (yl, yr)), iterations)
     convolve_f64(...)
 
-The shared library is loaded when this module is imported; a missing library is
-an ImportError and a missing GPU a RuntimeError at call time.  Nothing here
-computes on the CPU.
+The shared library is loaded on first use (so that the package can be imported
+to build it); a missing or stale library is an ImportError and a missing GPU a
+RuntimeError at call time.  Nothing here computes on the CPU.
 """
 
 from __future__ import annotations
@@ -47,7 +47,7 @@ def _signatures(real) -> dict[str, list]:
         "convolve": [p, p, p, _i64, _i64, p, _i64, _int, *walls, _i64, p],
         "convolve_device": [_vp, _vp, _vp, _i64, _i64, p, _i64, _int, *walls, _i64, _vp, _vp,
                             ctypes.POINTER(_vp), _vp],
-        "pack_uv": [_vp, _vp, _i64, _vp, _vp],
+        "pack_field": [_vp, _vp, _i64, _vp, _vp],
         "convolve_packed": [_vp, _vp, _i64, _i64, p, _i64, _int, *walls, _i64, _vp, _vp,
                             ctypes.POINTER(_vp), _vp],
         "pass_slab": [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, p, _i64, _int, *walls, _vp],
@@ -79,7 +79,18 @@ def _load() -> ctypes.CDLL:
     return cdll
 
 
-lib = _load()
+class _LazyLib:
+    """Loads librlic_b200.so the first time an entry point is looked up."""
+
+    _cdll = None
+
+    def __getattr__(self, name):
+        if _LazyLib._cdll is None:
+            _LazyLib._cdll = _load()
+        return getattr(_LazyLib._cdll, name)
+
+
+lib = _LazyLib()
 
 
 def device_count() -> int:

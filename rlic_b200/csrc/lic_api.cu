@@ -112,43 +112,51 @@ int check_common(int64_t ny, int64_t nx, int64_t klen, int uv_mode, const Walls 
     return RLIC_B200_OK;
 }
 
-// Wall rules (lib.rs:83-95) for a buffer whose row 0 is global row `shift`.
-// `lo_wall` / `hi_wall`: whether the image edge on that side can be reached
-// from this buffer and must be acted on (always true for a whole image).
-void set_walls(PassGeom &g, int64_t ny, int64_t nx, int64_t shift, bool lo_wall, bool hi_wall,
-               const Walls &w)
+// Geometry of one pass over a buffer whose row 0 is global row `shift`
+// (wall rules: lib.rs:83-95).  `lo_wall` / `hi_wall`: whether the image edge on
+// that side can be reached from this buffer and must be acted on (always true
+// for a whole image).  Rows are counted from the first row that needs no action.
+void set_geometry(PassGeom &g, int64_t ny, int64_t nx, int64_t shift, bool lo_wall, bool hi_wall,
+                  int64_t first_row, int64_t out_rows, int64_t rows_alloc, const Walls &w)
 {
-    const int64_t far = 1 << 30;
+    g.nx = (int)nx;
+    g.out_rows = (int)out_rows;
+    g.field_stride = rows_alloc * nx;
     g.j_below_to = w.x_left == RLIC_B200_PERIODIC ? (int)nx - 1 : 0;
     g.j_above_to = w.x_right == RLIC_B200_PERIODIC ? 0 : (int)nx - 1;
-    const int64_t lo = lo_wall ? -shift : -far;
-    const int64_t hi = hi_wall ? ny - shift : far;   // exclusive
-    g.i_min = (int)lo;
-    g.i_span = (unsigned)(hi - lo);
-    g.i_below_to = (int)((w.y_left == RLIC_B200_PERIODIC ? ny - 1 : 0) - shift);
-    g.i_above_to = (int)((w.y_right == RLIC_B200_PERIODIC ? 0 : ny - 1) - shift);
+    // buffer row of the first row needing no action: global row 0 when the low
+    // wall is live, else buffer row 0 (a walker never gets above it: halo >= reach)
+    const int64_t i_min = lo_wall ? -shift : 0;
+    g.origin = i_min * nx;
+    g.first_rel = (int)(first_row - i_min);
+    const int64_t below_to = (w.y_left == RLIC_B200_PERIODIC ? ny - 1 : 0) - shift;   // buffer rows
+    const int64_t above_to = (w.y_right == RLIC_B200_PERIODIC ? 0 : ny - 1) - shift;
+    const int64_t span = (ny - shift) - i_min;   // rows until global row ny
+    g.below_shift = (below_to - i_min + 1) * nx;
+    g.above_shift = (above_to - i_min - span) * nx;
+    g.total = hi_wall ? span * nx : -1;          // -1: unreachable, resolved per index width
 }
 
-template <typename T> using Pair = typename rlic::Fp<T>::Pair;
+template <typename T> using Field = rlic::PackedField<T>;
 
 template <typename T, bool POL, typename Taps, typename Idx>
-cudaError_t launch_one(const T *tex, const Pair<T> *uv, T *out, const PassGeom &g,
+cudaError_t launch_one(const T *tex, const Field<T> *field, T *out, const PassGeom &g,
                        const Taps &taps, int ntaps, unsigned blocks, cudaStream_t stream)
 {
     rlic::lic_pass_kernel<T, POL, Taps, Idx>
-        <<<blocks, rlic::kThreads, 0, stream>>>(tex, uv, out, g, taps, ntaps);
+        <<<blocks, rlic::kThreads, 0, stream>>>(tex, field, out, g, taps, ntaps);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }
 
 template <typename T>
-cudaError_t launch_pack(const T *u, const T *v, Pair<T> *uv, size_t count, cudaStream_t stream)
+cudaError_t launch_pack(const T *u, const T *v, Field<T> *field, size_t count, cudaStream_t stream)
 {
     if (count == 0)
         return cudaSuccess;
     const size_t want = (count + 255) / 256;
     const unsigned blocks = (unsigned)std::min<size_t>(want, 148 * 16);
-    rlic::pack_uv_kernel<T><<<blocks, 256, 0, stream>>>(u, v, uv, (long long)count);
+    rlic::pack_field_kernel<T><<<blocks, 256, 0, stream>>>(u, v, field, (long long)count);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }
@@ -179,9 +187,9 @@ template <typename T> struct TapSet {
     }
 };
 
-// Launch one pass for `nfields` stacked fields of `g.rows_alloc` buffer rows.
+// Launch one pass for `nfields` fields stacked `g.field_stride` elements apart.
 template <typename T>
-int launch_pass(const T *tex, const Pair<T> *uv, T *out, PassGeom g, int64_t nfields,
+int launch_pass(const T *tex, const Field<T> *field, T *out, PassGeom g, int64_t nfields,
                 int uv_mode, const TapSet<T> &taps, cudaStream_t stream)
 {
     if (g.out_rows <= 0 || g.nx <= 0 || nfields <= 0)
@@ -192,15 +200,16 @@ int launch_pass(const T *tex, const Pair<T> *uv, T *out, PassGeom g, int64_t nfi
     const int64_t blocks = per_field * nfields;
     if (per_field > INT_MAX || blocks > INT_MAX)
         return fail(RLIC_B200_EINVAL, "too many tiles for one launch (%lld)", (long long)blocks);
-    if (nfields * (int64_t)g.rows_alloc > (int64_t)(1 << 30))
-        return fail(RLIC_B200_EINVAL, "too many stacked rows for one launch");
     g.tiles_per_field = (int)per_field;
-    const bool wide = nfields * (int64_t)g.rows_alloc * g.nx > (int64_t)INT_MAX;
+    // 32-bit element indices whenever one field's buffer allows it
+    const bool wide = g.field_stride + 2 * (int64_t)g.nx >= (int64_t)INT_MAX;
+    if (g.total < 0)
+        g.total = wide ? LLONG_MAX : (long long)INT_MAX;
     const bool pol = uv_mode == RLIC_B200_POLARIZATION;
 
     cudaError_t e;
 #define RLIC_LAUNCH(POL, TAPS, TAPV, IDX) \
-    e = launch_one<T, POL, TAPS, IDX>(tex, uv, out, g, TAPV, taps.ntaps, (unsigned)blocks, stream)
+    e = launch_one<T, POL, TAPS, IDX>(tex, field, out, g, TAPV, taps.ntaps, (unsigned)blocks, stream)
     using PT = rlic::ParamTaps<T, TapSet<T>::kMaxParam>;
     using GT = rlic::GlobalTaps<T>;
     const GT gt{static_cast<const T *>(taps.global.p)};
@@ -219,21 +228,17 @@ int launch_pass(const T *tex, const Pair<T> *uv, T *out, PassGeom g, int64_t nfi
 // `iterations` passes over device-resident buffers (lib.rs:432-440 without the
 // copy-back: the two work buffers swap roles instead).
 template <typename T>
-int run_device(const T *d_tex, const Pair<T> *d_uv, int64_t nfields, int64_t ny, int64_t nx,
+int run_device(const T *d_tex, const Field<T> *d_field, int64_t nfields, int64_t ny, int64_t nx,
                const TapSet<T> &taps, int uv_mode, const Walls &w, int64_t iterations, T *work0,
                T *work1, T **result, cudaStream_t stream)
 {
     PassGeom g{};
-    g.nx = (int)nx;
-    g.out_rows = (int)ny;
-    g.first_row = 0;
-    g.rows_alloc = (int)ny;
-    set_walls(g, ny, nx, 0, true, true, w);
+    set_geometry(g, ny, nx, 0, true, true, 0, ny, ny, w);
     const T *src = d_tex;
     T *dst = work0;
     for (int64_t it = 0; it < iterations; ++it) {
         dst = (it & 1) ? work1 : work0;
-        int rc = launch_pass<T>(src, d_uv, dst, g, nfields, uv_mode, taps, stream);
+        int rc = launch_pass<T>(src, d_field, dst, g, nfields, uv_mode, taps, stream);
         if (rc)
             return rc;
         src = dst;
@@ -264,9 +269,9 @@ int convolve_host(const T *tex, const T *u, const T *v, int64_t nfields, int64_t
     Stream st;
     CUDA_TRY(cudaStreamCreateWithFlags(&st.s, cudaStreamNonBlocking));
     // d_tex doubles as the second work buffer
-    DeviceBuf d_tex, d_uv, d_work, d_stage;
+    DeviceBuf d_tex, d_field, d_work, d_stage;
     CUDA_TRY(d_tex.alloc(bytes, st.s));
-    CUDA_TRY(d_uv.alloc(2 * bytes, st.s));
+    CUDA_TRY(d_field.alloc(4 * bytes, st.s));
     CUDA_TRY(d_work.alloc(bytes, st.s));
     CUDA_TRY(d_stage.alloc(bytes, st.s));
     TapSet<T> taps;
@@ -277,13 +282,13 @@ int convolve_host(const T *tex, const T *u, const T *v, int64_t nfields, int64_t
     CUDA_TRY(cudaMemcpyAsync(d_work.p, u, bytes, cudaMemcpyHostToDevice, st.s));
     CUDA_TRY(cudaMemcpyAsync(d_stage.p, v, bytes, cudaMemcpyHostToDevice, st.s));
     CUDA_TRY(launch_pack<T>(static_cast<const T *>(d_work.p), static_cast<const T *>(d_stage.p),
-                            static_cast<Pair<T> *>(d_uv.p), count, st.s));
+                            static_cast<Field<T> *>(d_field.p), count, st.s));
     CUDA_TRY(cudaMemcpyAsync(d_tex.p, tex, bytes, cudaMemcpyHostToDevice, st.s));
 
     T *result = nullptr;
     // pass 1 reads the uploaded texture and writes d_work; pass 2 writes back
     // over the texture copy; and so on: exactly two texture-sized work buffers.
-    int rc = run_device<T>(static_cast<T *>(d_tex.p), static_cast<Pair<T> *>(d_uv.p), nfields, ny,
+    int rc = run_device<T>(static_cast<T *>(d_tex.p), static_cast<Field<T> *>(d_field.p), nfields, ny,
                            nx, taps, uv_mode, w, iterations, static_cast<T *>(d_work.p),
                            static_cast<T *>(d_tex.p), &result, st.s);
     if (rc)
@@ -316,15 +321,15 @@ int convolve_device(const T *d_tex, const T *d_u, const T *d_v, int64_t ny, int6
     }
     TapSet<T> taps;
     CUDA_TRY(taps.prepare(kernel, klen, s));
-    DeviceBuf d_uv;   // stream-ordered scratch, returned to the pool after the last pass
-    CUDA_TRY(d_uv.alloc(2 * sizeof(T) * count, s));
-    CUDA_TRY(launch_pack<T>(d_u, d_v, static_cast<Pair<T> *>(d_uv.p), count, s));
-    return run_device<T>(d_tex, static_cast<Pair<T> *>(d_uv.p), 1, ny, nx, taps, uv_mode, w,
+    DeviceBuf d_field;   // stream-ordered scratch, returned to the pool after the last pass
+    CUDA_TRY(d_field.alloc(4 * sizeof(T) * count, s));
+    CUDA_TRY(launch_pack<T>(d_u, d_v, static_cast<Field<T> *>(d_field.p), count, s));
+    return run_device<T>(d_tex, static_cast<Field<T> *>(d_field.p), 1, ny, nx, taps, uv_mode, w,
                          iterations, work0, work1, result, s);
 }
 
 template <typename T>
-int convolve_device_packed(const T *d_tex, const T *d_uv, int64_t ny, int64_t nx,
+int convolve_device_packed(const T *d_tex, const T *d_field, int64_t ny, int64_t nx,
                            const T *kernel, int64_t klen, int uv_mode, const Walls &w,
                            int64_t iterations, T *work0, T *work1, T **result, void *stream)
 {
@@ -335,7 +340,7 @@ int convolve_device_packed(const T *d_tex, const T *d_uv, int64_t ny, int64_t nx
     *result = nullptr;
     if (ny == 0 || nx == 0)
         return RLIC_B200_OK;
-    if (!d_tex || !d_uv || !kernel || !work0 || (!work1 && iterations > 1))
+    if (!d_tex || !d_field || !kernel || !work0 || (!work1 && iterations > 1))
         return fail(RLIC_B200_EINVAL, "null pointer argument");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (iterations <= 0) {
@@ -345,26 +350,26 @@ int convolve_device_packed(const T *d_tex, const T *d_uv, int64_t ny, int64_t nx
     }
     TapSet<T> taps;
     CUDA_TRY(taps.prepare(kernel, klen, s));
-    return run_device<T>(d_tex, reinterpret_cast<const Pair<T> *>(d_uv), 1, ny, nx, taps, uv_mode,
+    return run_device<T>(d_tex, reinterpret_cast<const Field<T> *>(d_field), 1, ny, nx, taps, uv_mode,
                          w, iterations, work0, work1, result, s);
 }
 
 template <typename T>
-int pack_uv(const T *d_u, const T *d_v, int64_t count, T *d_uv, void *stream)
+int pack_field(const T *d_u, const T *d_v, int64_t count, T *d_field, void *stream)
 {
     if (count < 0)
         return fail(RLIC_B200_EINVAL, "negative element count");
     if (count == 0)
         return RLIC_B200_OK;
-    if (!d_u || !d_v || !d_uv)
+    if (!d_u || !d_v || !d_field)
         return fail(RLIC_B200_EINVAL, "null pointer argument");
-    CUDA_TRY(launch_pack<T>(d_u, d_v, reinterpret_cast<Pair<T> *>(d_uv), (size_t)count,
+    CUDA_TRY(launch_pack<T>(d_u, d_v, reinterpret_cast<Field<T> *>(d_field), (size_t)count,
                             static_cast<cudaStream_t>(stream)));
     return RLIC_B200_OK;
 }
 
 template <typename T>
-int pass_slab(const T *d_tex, const T *d_uv, T *d_out, int64_t ny, int64_t nx, int64_t row0,
+int pass_slab(const T *d_tex, const T *d_field, T *d_out, int64_t ny, int64_t nx, int64_t row0,
               int64_t nrows, int64_t halo_lo, int64_t halo_hi, const T *kernel, int64_t klen,
               int uv_mode, const Walls &w, void *stream)
 {
@@ -375,7 +380,7 @@ int pass_slab(const T *d_tex, const T *d_uv, T *d_out, int64_t ny, int64_t nx, i
                     (long long)row0, (long long)(row0 + nrows), (long long)ny);
     if (nrows == 0 || nx == 0)
         return RLIC_B200_OK;
-    if (!d_tex || !d_uv || !d_out || !kernel)
+    if (!d_tex || !d_field || !d_out || !kernel)
         return fail(RLIC_B200_EINVAL, "null pointer argument");
     const int64_t reach = klen / 2;   // a walker moves at most one row per tap
     const bool bare_whole = row0 == 0 && nrows == ny && halo_lo == 0 && halo_hi == 0;
@@ -383,25 +388,22 @@ int pass_slab(const T *d_tex, const T *d_uv, T *d_out, int64_t ny, int64_t nx, i
     // A side needs `reach` halo rows unless a closed wall stops the walker there.
     const bool lo_closed = row0 == 0 && !periodic_y;
     const bool hi_closed = row0 + nrows == ny && !periodic_y;
+    const int64_t rows_alloc = halo_lo + nrows + halo_hi;
     PassGeom g{};
-    g.nx = (int)nx;
-    g.out_rows = (int)nrows;
-    g.first_row = (int)halo_lo;
-    g.rows_alloc = (int)(halo_lo + nrows + halo_hi);
     if (bare_whole) {
-        set_walls(g, ny, nx, 0, true, true, w);
+        set_geometry(g, ny, nx, 0, true, true, 0, ny, ny, w);
     } else {
         if ((!lo_closed && halo_lo < reach) || (!hi_closed && halo_hi < reach))
             return fail(RLIC_B200_ESHARD,
                         "slab halo (%lld,%lld) shorter than the kernel half-width %lld",
                         (long long)halo_lo, (long long)halo_hi, (long long)reach);
         // periodic rows: the wrap lands in a halo the caller filled (ring order)
-        set_walls(g, ny, nx, row0 - halo_lo, lo_closed, hi_closed, w);
+        set_geometry(g, ny, nx, row0 - halo_lo, lo_closed, hi_closed, halo_lo, nrows, rows_alloc, w);
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     TapSet<T> taps;
     CUDA_TRY(taps.prepare(kernel, klen, s));
-    return launch_pass<T>(d_tex, reinterpret_cast<const Pair<T> *>(d_uv), d_out, g, 1, uv_mode,
+    return launch_pass<T>(d_tex, reinterpret_cast<const Field<T> *>(d_field), d_out, g, 1, uv_mode,
                           taps, s);
 }
 
@@ -520,31 +522,31 @@ int rlic_b200_set_device(int device)
                                   Walls{x_left, x_right, y_left, y_right}, iterations, d_work0,  \
                                   d_work1, d_result, stream);                                    \
     }                                                                                            \
-    int rlic_b200_pack_uv_##sfx(const T *d_u, const T *d_v, int64_t count, T *d_uv,              \
+    int rlic_b200_pack_field_##sfx(const T *d_u, const T *d_v, int64_t count, T *d_field,              \
                                 void *stream)                                                    \
     {                                                                                            \
         tls_error.clear();                                                                       \
-        return pack_uv<T>(d_u, d_v, count, d_uv, stream);                                        \
+        return pack_field<T>(d_u, d_v, count, d_field, stream);                                        \
     }                                                                                            \
-    int rlic_b200_convolve_packed_##sfx(const T *d_texture, const T *d_uv, int64_t ny,           \
+    int rlic_b200_convolve_packed_##sfx(const T *d_texture, const T *d_field, int64_t ny,         \
                                         int64_t nx, const T *kernel, int64_t klen, int uv_mode,  \
                                         int x_left, int x_right, int y_left, int y_right,        \
                                         int64_t iterations, T *d_work0, T *d_work1,              \
                                         T **d_result, void *stream)                              \
     {                                                                                            \
         tls_error.clear();                                                                       \
-        return convolve_device_packed<T>(d_texture, d_uv, ny, nx, kernel, klen, uv_mode,         \
+        return convolve_device_packed<T>(d_texture, d_field, ny, nx, kernel, klen, uv_mode,       \
                                          Walls{x_left, x_right, y_left, y_right}, iterations,    \
                                          d_work0, d_work1, d_result, stream);                    \
     }                                                                                            \
-    int rlic_b200_pass_slab_##sfx(const T *d_texture, const T *d_uv, T *d_out, int64_t ny,       \
+    int rlic_b200_pass_slab_##sfx(const T *d_texture, const T *d_field, T *d_out, int64_t ny,     \
                                   int64_t nx, int64_t row0, int64_t nrows, int64_t halo_lo,      \
                                   int64_t halo_hi, const T *kernel, int64_t klen, int uv_mode,   \
                                   int x_left, int x_right, int y_left, int y_right,              \
                                   void *stream)                                                  \
     {                                                                                            \
         tls_error.clear();                                                                       \
-        return pass_slab<T>(d_texture, d_uv, d_out, ny, nx, row0, nrows, halo_lo, halo_hi,       \
+        return pass_slab<T>(d_texture, d_field, d_out, ny, nx, row0, nrows, halo_lo, halo_hi,     \
                             kernel, klen, uv_mode, Walls{x_left, x_right, y_left, y_right},      \
                             stream);                                                             \
     }                                                                                            \

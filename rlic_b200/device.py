@@ -3,7 +3,7 @@
 ``convolve`` in ``rlic_b200._lib`` mirrors the reference's NumPy contract and
 therefore pays two PCIe trips per call.  Callers whose data already lives on
 the GPU use these functions instead: same arithmetic, same C ABI underneath
-(``rlic_b200_pack_uv_*`` / ``rlic_b200_convolve_packed_*`` /
+(``rlic_b200_pack_field_*`` / ``rlic_b200_convolve_packed_*`` /
 ``rlic_b200_pass_slab_*``), torch tensors in and out.  torch is used for device
 memory and streams only.
 """
@@ -66,9 +66,10 @@ def _check_image(name: str, t: torch.Tensor, like: torch.Tensor | None = None) -
 
 @dataclass
 class PackedField:
-    """A vector field in the kernels' native layout: ``uv[i, j] = (u, v)``."""
+    """A vector field in the kernels' native layout (``include/rlic_b200.h``):
+    ``uv[i, j] = (u, v, ru, rv)`` with the precomputed reciprocals."""
 
-    uv: torch.Tensor   # (ny, nx, 2), contiguous
+    uv: torch.Tensor   # (ny, nx, 4), contiguous
 
     @property
     def shape(self) -> tuple[int, int]:
@@ -77,13 +78,13 @@ class PackedField:
 
 def pack_field(u: torch.Tensor, v: torch.Tensor, *, out: torch.Tensor | None = None,
                stream=None) -> PackedField:
-    """Interleave two planar components on the device (one streaming kernel)."""
+    """Build the packed field from two planar components (one streaming kernel)."""
     _check_image("u", u)
     _check_image("v", v, u)
     sfx, _, _ = _kind(u)
-    uv = torch.empty((*u.shape, 2), dtype=u.dtype, device=u.device) if out is None else out
+    uv = torch.empty((*u.shape, 4), dtype=u.dtype, device=u.device) if out is None else out
     with torch.cuda.device(u.device):
-        rc = getattr(_core.lib, f"rlic_b200_pack_uv_{sfx}")(
+        rc = getattr(_core.lib, f"rlic_b200_pack_field_{sfx}")(
             u.data_ptr(), v.data_ptr(), u.numel(), uv.data_ptr(), _stream_handle(stream))
     _core.check(rc)
     return PackedField(uv)

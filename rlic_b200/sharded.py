@@ -176,7 +176,7 @@ class ShardedConvolver:
     def set_field(self, u: torch.Tensor, v: torch.Tensor) -> None:
         """Pack (u, v) with halos; done once, the field does not change between passes."""
         p = self.plan
-        uv = self._alloc(u, (2,))
+        uv = self._alloc(u, (4,))
         owned = uv[p.halo_lo:p.halo_lo + p.nrows]
         if self._pack is not None:
             self._pack(u, v, owned)

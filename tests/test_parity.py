@@ -203,13 +203,16 @@ def test_c2_full_size_against_oracle_bands_and_properties():
 
 
 def test_transpose_symmetry_at_scale():
-    # reference tests/test_convolution.py:69-82, on a tie-free random field, 2048^2 f32
+    # reference tests/test_convolution.py:69-82 on a random 1024^2 f64 field.  The
+    # property needs tie-free walks (ties go to y, which a transpose turns into x):
+    # in f64 an exact tx == ty has probability ~2^-53 per step; in f32 at this size
+    # a handful of ties do occur, so f32 is not asserted.
     rng = np.random.default_rng(21)
-    n = 2048
-    tex = rng.random((n, n), dtype=np.float32)
-    u = rng.random((n, n), dtype=np.float32) - np.float32(0.5)
-    v = rng.random((n, n), dtype=np.float32) - np.float32(0.5)
-    k = workloads.triangle_kernel(65, np.float32)
+    n = 1024
+    tex = rng.random((n, n))
+    u = rng.random((n, n)) - 0.5
+    v = rng.random((n, n)) - 0.5
+    k = workloads.triangle_kernel(65, np.float64)
     a = rlic.convolve(tex, u, v, kernel=k, iterations=3, boundaries="periodic")
     b = rlic.convolve(tex.T, v.T, u.T, kernel=k, iterations=3, boundaries="periodic").T
     assert_array_equal(a, b)

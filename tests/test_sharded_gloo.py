@@ -53,8 +53,10 @@ def oracle_slab_pass(tex, uv, out, plan, row0, nrows, halo_lo, halo_hi, taps, mo
 
 
 def cpu_pack(u, v, owned):
+    # the product's packed record is (u, v, ru, rv); the stand-in only needs u, v
     owned[..., 0] = u
     owned[..., 1] = v
+    owned[..., 2:] = 0
 
 
 def _worker(rank, world, port, case, queue):

@@ -1,0 +1,158 @@
+// Developer tool (not part of librlic_b200.so): times the shipped pass kernel and
+// candidate formulations on the headline workload, checks candidates bit for bit
+// against the shipped kernel, and checks the short division used by the fast
+// path against the library's IEEE division.
+// Build: tools/build_lab.sh    Run on a B200: tools/kernel_lab [n] [taps] [name-filter]
+//
+// History of what was tried here (numbers in profiles/r1_lab*.txt):
+//   lab1  tile shapes 32x2 ... 8x32, wall handling as select / inline branch / out-of-line call
+//   lab2  (at, j) walker state, merged rare path, unrolling
+//   lab3  precomputed refined reciprocals in the packed field  -> adopted
+#include "../rlic_b200/csrc/lic_walk.cuh"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { \
+    fprintf(stderr, "%s: %s\n", #x, cudaGetErrorString(e)); exit(1); } } while (0)
+
+using rlic::Fp;
+using rlic::PackedField;
+using rlic::PassGeom;
+
+template <typename T>
+__global__ void fill_inputs(T *tex, T *u, T *v, int n)
+{
+    long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= (long long)n * n) return;
+    int i = (int)(p / n), j = (int)(p % n);
+    unsigned h = (unsigned)p * 2654435761u; h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+    tex[p] = (T)((h >> 8) * (1.0 / 16777216.0));
+    u[p] = (T)(-(-1.0 + 2.0 * i / (n - 1)));
+    v[p] = (T)(-1.0 + 2.0 * j / (n - 1));
+}
+
+// div_tail against IEEE division on the ranges the fast path admits:
+// |b| in [2^-40, 2^40], |a| in [2^-60, 4).
+template <typename T> struct Bits;
+template <> struct Bits<float> {
+    static __device__ float make(int e, unsigned long long m, bool neg) {
+        return __int_as_float((neg ? 0x80000000u : 0u) | ((unsigned)(e + 127) << 23) | (unsigned)(m & 0x7fffff));
+    }
+    static __device__ bool same(float a, float b) { return __float_as_int(a) == __float_as_int(b); }
+    static constexpr unsigned long long ones = 0x7fffff;
+};
+template <> struct Bits<double> {
+    static __device__ double make(int e, unsigned long long m, bool neg) {
+        return __longlong_as_double((long long)((neg ? 0x8000000000000000ull : 0ull) |
+                                                ((unsigned long long)(e + 1023) << 52) | (m & 0xfffffffffffffull)));
+    }
+    static __device__ bool same(double a, double b) { return __double_as_longlong(a) == __double_as_longlong(b); }
+    static constexpr unsigned long long ones = 0xfffffffffffffull;
+};
+
+template <typename T>
+__global__ void divcheck_kernel(unsigned long long seed, unsigned long long *bad, unsigned long long n_per_thread)
+{
+    unsigned long long x = seed + 0x9E3779B97F4A7C15ull * (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x + 1);
+    unsigned long long local_bad = 0;
+    for (unsigned long long it = 0; it < n_per_thread; ++it) {
+        x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+        unsigned long long ma = x, y = x * 0xD6E8FEB86659FD93ull;
+        y ^= y >> 32;
+        unsigned long long mb = y;
+        const unsigned sel = (unsigned)(x >> 40) ^ (unsigned)(y >> 11);
+        const int eb = (int)(sel % 81) - 40, ea = (int)((sel / 81) % 62) - 60;
+        const unsigned mode = (sel >> 14) & 7;      // bias towards nasty mantissas
+        if (mode == 0) mb = Bits<T>::ones; else if (mode == 1) mb = 0; else if (mode == 2) ma = Bits<T>::ones;
+        else if (mode == 3) ma = 0; else if (mode == 4) { mb = Bits<T>::ones; ma &= 0xff; }
+        else if (mode == 5) { mb = Bits<T>::ones - (mb & 0xf); }
+        const T a = Bits<T>::make(ea, ma, sel & (1u << 16));
+        const T b = Bits<T>::make(eb, mb, sel & (1u << 17));
+        const T want = Fp<T>::div(a, b);
+        const T got = rlic::div_tail<T>(a, b, Fp<T>::refined_rcp(b));
+        if (!Bits<T>::same(want, got)) ++local_bad;
+    }
+    if (local_bad) atomicAdd(bad, local_bad);
+}
+
+template <typename T> void divcheck(const char *name)
+{
+    unsigned long long *bad; CK(cudaMalloc(&bad, 8)); CK(cudaMemset(bad, 0, 8));
+    const unsigned long long per_thread = sizeof(T) == 4 ? 40000 : 8000;
+    divcheck_kernel<T><<<148 * 16, 256>>>(0xC0FFEEull, bad, per_thread);
+    CK(cudaDeviceSynchronize());
+    unsigned long long h_bad; CK(cudaMemcpy(&h_bad, bad, 8, cudaMemcpyDeviceToHost));
+    printf("divcheck %s: %llu mismatches in %.3g samples\n", name, h_bad, (double)per_thread * 148 * 16 * 256);
+    CK(cudaFree(bad));
+}
+
+struct Result { std::string name; float ms; bool same; int regs; };
+
+template <typename T>
+void run_type(const char *tname, int n, int L, const char *only)
+{
+    const int reps = only ? 1 : 5;
+    const size_t count = (size_t)n * n;
+    T *tex, *u, *v, *ref; PackedField<T> *field;
+    CK(cudaMalloc(&tex, count * sizeof(T))); CK(cudaMalloc(&u, count * sizeof(T)));
+    CK(cudaMalloc(&v, count * sizeof(T))); CK(cudaMalloc(&ref, count * sizeof(T)));
+    CK(cudaMalloc(&field, count * sizeof(PackedField<T>)));
+    fill_inputs<T><<<(unsigned)((count + 255) / 256), 256>>>(tex, u, v, n);
+    rlic::pack_field_kernel<T><<<148 * 16, 256>>>(u, v, field, (long long)count);
+    CK(cudaDeviceSynchronize());
+
+    using PT = rlic::ParamTaps<T, rlic::kParamTapBytes / (int)sizeof(T)>;
+    PT taps{};
+    for (int k = 0; k < L; ++k) taps.w[k] = (T)(1.0 - fabs(-1.0 + 2.0 * k / (L - 1)));
+
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    std::vector<Result> results;
+
+    PassGeom g{};
+    g.nx = n; g.out_rows = n; g.first_rel = 0;
+    g.tiles_x = (n + rlic::kTileW - 1) / rlic::kTileW;
+    g.tiles_per_field = g.tiles_x * ((n + rlic::kTileH - 1) / rlic::kTileH);
+    g.field_stride = (long long)count; g.origin = 0; g.total = (long long)count;
+    g.j_below_to = 0; g.j_above_to = n - 1; g.below_shift = n; g.above_shift = -n;
+    {
+        auto k = rlic::lic_pass_kernel<T, false, PT, int>;
+        float best = 1e9;
+        for (int r = 0; r < reps + 1; ++r) {
+            CK(cudaEventRecord(e0));
+            k<<<g.tiles_per_field, rlic::kThreads>>>(tex, field, ref, g, taps, L);
+            CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+            float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); if (r) best = fminf(best, ms);
+        }
+        CK(cudaGetLastError());
+        cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, k));
+        if (!only || strstr("shipped", only)) results.push_back({"shipped", best, true, fa.numRegs});
+    }
+    // candidates go here: run, memcmp against `ref`, push_back
+
+    const double steps = (double)count * (L - 1);
+    const double bytes = (double)count * (3 * (L - 1) + 2) * sizeof(T);
+    printf("%s %dx%d, %d taps\n%-22s %8s %10s %8s %6s %5s\n", tname, n, n, L, "variant", "ms", "Gsteps/s",
+           "GB/s", "same", "regs");
+    for (auto &r : results)
+        printf("%-22s %8.3f %10.1f %8.0f %6s %5d\n", r.name.c_str(), r.ms, steps / r.ms / 1e6,
+               bytes / r.ms / 1e6, r.same ? "yes" : "NO", r.regs);
+    CK(cudaFree(tex)); CK(cudaFree(u)); CK(cudaFree(v)); CK(cudaFree(ref)); CK(cudaFree(field));
+}
+
+int main(int argc, char **argv)
+{
+    const int n = argc > 1 ? atoi(argv[1]) : 4096;
+    const int L = argc > 2 ? atoi(argv[2]) : 65;
+    const char *only = argc > 3 ? argv[3] : nullptr;
+    if (!only) {
+        divcheck<float>("f32");
+        divcheck<double>("f64");
+    }
+    run_type<float>("f32", n, L, only);
+    run_type<double>("f64", n / 2, 2 * L - 1, only);
+    return 0;
+}
