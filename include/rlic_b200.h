@@ -93,6 +93,30 @@ int rlic_b200_convolve_f64(const double *texture, const double *u, const double 
                            int x_left, int x_right, int y_left, int y_right,
                            int64_t iterations, double *out);
 
+/*
+ * Same as rlic_b200_convolve_*, with the reference's `np.any(texture < 0)`
+ * validation (_lib.py:174-179) fused into the upload: *texture_has_negative is
+ * set to 1 when the texture holds a negative element (NaN does not count, as on
+ * the host), else 0.  The result in `out` is unspecified in that case; the
+ * Python layer raises the reference's ValueError.  Saves a host pass over the
+ * texture that costs more than a GPU iteration on large images.
+ */
+int rlic_b200_convolve_checked_f32(const float *texture, const float *u, const float *v,
+                                   int64_t ny, int64_t nx,
+                                   const float *kernel, int64_t klen,
+                                   int uv_mode,
+                                   int x_left, int x_right, int y_left, int y_right,
+                                   int64_t iterations, float *out,
+                                   int *texture_has_negative);
+
+int rlic_b200_convolve_checked_f64(const double *texture, const double *u, const double *v,
+                                   int64_t ny, int64_t nx,
+                                   const double *kernel, int64_t klen,
+                                   int uv_mode,
+                                   int x_left, int x_right, int y_left, int y_right,
+                                   int64_t iterations, double *out,
+                                   int *texture_has_negative);
+
 /* Device used by the host entry points on the calling thread. */
 int rlic_b200_set_device(int device);
 

@@ -45,6 +45,8 @@ def _signatures(real) -> dict[str, list]:
     walls = [_int] * 4
     return {
         "convolve": [p, p, p, _i64, _i64, p, _i64, _int, *walls, _i64, p],
+        "convolve_checked": [p, p, p, _i64, _i64, p, _i64, _int, *walls, _i64, p,
+                             ctypes.POINTER(_int)],
         "convolve_device": [_vp, _vp, _vp, _i64, _i64, p, _i64, _int, *walls, _i64, _vp, _vp,
                             ctypes.POINTER(_vp), _vp],
         "pack_field": [_vp, _vp, _i64, _vp, _vp],
@@ -139,7 +141,10 @@ def _as_image(name: str, arr, dtype: np.dtype, ndim: int) -> np.ndarray:
     return np.ascontiguousarray(arr)
 
 
-def _convolve(sfx: str, real, texture, uv, kernel, boundaries, iterations):
+NEGATIVE_TEXTURE_MESSAGE = "Found invalid texture element(s). Expected only positive values."
+
+
+def _convolve(sfx: str, real, texture, uv, kernel, boundaries, iterations, check_texture=False):
     dtype = np.dtype(real)
     u, v, uv_mode = uv
     texture = _as_image("texture", texture, dtype, 2)
@@ -151,7 +156,7 @@ def _convolve(sfx: str, real, texture, uv, kernel, boundaries, iterations):
     ny, nx = texture.shape
     out = np.empty((ny, nx), dtype=dtype)
     p = ctypes.POINTER(real)
-    rc = getattr(lib, f"rlic_b200_convolve_{sfx}")(
+    args = [
         texture.ctypes.data_as(p),
         u.ctypes.data_as(p),
         v.ctypes.data_as(p),
@@ -163,14 +168,22 @@ def _convolve(sfx: str, real, texture, uv, kernel, boundaries, iterations):
         *wall_codes(boundaries),
         int(iterations),
         out.ctypes.data_as(p),
-    )
-    check(rc)
+    ]
+    if check_texture:
+        negative = _int(0)
+        check(getattr(lib, f"rlic_b200_convolve_checked_{sfx}")(*args, ctypes.byref(negative)))
+        if negative.value:
+            raise ValueError(NEGATIVE_TEXTURE_MESSAGE)
+    else:
+        check(getattr(lib, f"rlic_b200_convolve_{sfx}")(*args))
     return out
 
 
-def convolve_f32(texture, uv, kernel, boundaries, iterations=1):
-    return _convolve("f32", ctypes.c_float, texture, uv, kernel, boundaries, iterations)
+def convolve_f32(texture, uv, kernel, boundaries, iterations=1, *, check_texture=False):
+    """``check_texture=True`` additionally performs the reference's "no negative
+    texture values" validation on the device, during the upload."""
+    return _convolve("f32", ctypes.c_float, texture, uv, kernel, boundaries, iterations, check_texture)
 
 
-def convolve_f64(texture, uv, kernel, boundaries, iterations=1):
-    return _convolve("f64", ctypes.c_double, texture, uv, kernel, boundaries, iterations)
+def convolve_f64(texture, uv, kernel, boundaries, iterations=1, *, check_texture=False):
+    return _convolve("f64", ctypes.c_double, texture, uv, kernel, boundaries, iterations, check_texture)

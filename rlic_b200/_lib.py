@@ -29,10 +29,21 @@ _KNOWN_UV_MODES = ["velocity", "polarization"]
 _SUPPORTED_DTYPES: list[np.dtype] = [np.dtype("float32"), np.dtype("float64")]
 
 
-def _check_inputs(texture, u, v, kernel, uv_mode, boundaries, iterations):
-    """Run every validator; return (problems, parsed boundaries)."""
+_NEGATIVE_TEXTURE = _core.NEGATIVE_TEXTURE_MESSAGE
+# textures at least this large have their sign check done on the GPU, during the upload
+_DEVICE_CHECK_MIN_SIZE = 1 << 16
+
+
+def _check_inputs(texture, u, v, kernel, uv_mode, boundaries, iterations, defer_sign_check=False):
+    """Run every validator, in the reference's order; return (problems, walls, deferred).
+
+    With ``defer_sign_check`` the O(pixels) ``texture < 0`` scan is skipped and
+    ``deferred`` is the position its error would take in ``problems``: the caller
+    either lets the GPU perform it (when nothing else is wrong) or calls again
+    without deferring, so the outcome is the same as checking eagerly."""
     problems: list[Exception] = []
     add = problems.append
+    deferred = None
 
     if iterations < 0:
         add(
@@ -63,8 +74,10 @@ def _check_inputs(texture, u, v, kernel, uv_mode, boundaries, iterations):
                 f"Expected a texture with exactly two dimensions. Got texture.ndim={texture.ndim}"
             )
         )
-    if np.any(texture < 0):
-        add(ValueError("Found invalid texture element(s). Expected only positive values."))
+    if defer_sign_check:
+        deferred = len(problems)
+    elif np.any(texture < 0):
+        add(ValueError(_NEGATIVE_TEXTURE))
     if u.shape != texture.shape or v.shape != texture.shape:
         add(
             ValueError(
@@ -87,7 +100,7 @@ def _check_inputs(texture, u, v, kernel, uv_mode, boundaries, iterations):
         add(TypeError(f"Invalid boundary specification {boundaries}"))
     else:
         problems.extend(walls.collect_exceptions())
-    return problems, walls
+    return problems, walls, deferred
 
 
 def convolve(
@@ -150,7 +163,18 @@ def convolve(
     upload).  Results are bit-identical to rLIC built with its default
     features (fma + branchless); see DESIGN.md.
     """
-    problems, walls = _check_inputs(texture, u, v, kernel, uv_mode, boundaries, iterations)
+    # The sign scan of a large texture costs more on the host than a GPU pass
+    # (SURVEY.md 8(f).3): when every other check passes it is fused into the upload.
+    defer = iterations > 0 and getattr(texture, "size", 0) >= _DEVICE_CHECK_MIN_SIZE
+    problems, walls, deferred = _check_inputs(
+        texture, u, v, kernel, uv_mode, boundaries, iterations, defer_sign_check=defer
+    )
+    if problems and deferred is not None:
+        # something else is wrong: evaluate the sign check here so that it takes
+        # its place in the group
+        problems, walls, deferred = _check_inputs(
+            texture, u, v, kernel, uv_mode, boundaries, iterations
+        )
     if len(problems) == 1:
         raise problems[0]
     if problems:
@@ -166,4 +190,5 @@ def convolve(
         run = _core.convolve_f64
     else:
         raise AssertionError
-    return run(texture, (u, v, uv_mode), kernel, (walls.x, walls.y), iterations)
+    return run(texture, (u, v, uv_mode), kernel, (walls.x, walls.y), iterations,
+               check_texture=deferred is not None)

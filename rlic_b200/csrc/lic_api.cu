@@ -19,6 +19,8 @@
 #include <thread>
 #include <vector>
 
+#include <sys/mman.h>
+
 namespace {
 
 using rlic::PassGeom;
@@ -65,6 +67,44 @@ struct DeviceBuf {
 };
 
 struct Walls { int x_left, x_right, y_left, y_right; };
+
+// Fault in the pages of a host buffer that is about to be overwritten by a
+// device-to-host copy.  A freshly allocated NumPy result has no physical pages
+// yet; letting the copy engine's staging path fault them in one by one costs
+// ~12 ms per 64 MiB, while doing it here overlaps with the passes still running
+// on the GPU.  Best effort: hints only, the contents are never read.
+void prefault_for_write(void *ptr, size_t bytes)
+{
+    if (bytes < (size_t)1 << 20)
+        return;
+    const uintptr_t page = 4096, huge = (uintptr_t)2 << 20;
+    const uintptr_t begin = (uintptr_t)ptr, end = begin + bytes;
+#ifdef MADV_HUGEPAGE
+    const uintptr_t hb = (begin + huge - 1) & ~(huge - 1), he = end & ~(huge - 1);
+    if (he > hb)
+        madvise((void *)hb, he - hb, MADV_HUGEPAGE);
+#endif
+    const uintptr_t pb = begin & ~(page - 1), pe = (end + page - 1) & ~(page - 1);
+    const unsigned nthreads = bytes >= ((size_t)16 << 20) ? 4 : 1;
+    auto populate = [=](uintptr_t a, uintptr_t b) {
+#ifdef MADV_POPULATE_WRITE
+        if (madvise((void *)a, b - a, MADV_POPULATE_WRITE) == 0)
+            return;
+#endif
+        for (uintptr_t q = a < begin ? begin : a; q < b && q < end; q += page)
+            *(volatile char *)q = 0;   // we own every byte of [begin, end)
+    };
+    std::vector<std::thread> helpers;
+    const uintptr_t chunk = (((pe - pb) / nthreads) + huge - 1) & ~(huge - 1);
+    for (unsigned t = 1; t < nthreads; ++t) {
+        const uintptr_t a = pb + t * chunk, b = std::min(pe, a + chunk);
+        if (a < b)
+            helpers.emplace_back(populate, a, b);
+    }
+    populate(pb, std::min(pe, pb + chunk));
+    for (auto &h : helpers)
+        h.join();
+}
 
 // Keep freed stream-ordered allocations cached in the device pool instead of
 // returning them to the OS at every synchronisation (first call per device).
@@ -247,11 +287,48 @@ int run_device(const T *d_tex, const Field<T> *d_field, int64_t nfields, int64_t
     return RLIC_B200_OK;
 }
 
+struct Events {
+    std::vector<cudaEvent_t> ev;
+    ~Events() { for (cudaEvent_t e : ev) cudaEventDestroy(e); }
+    cudaError_t make(size_t n)
+    {
+        for (size_t i = 0; i < n; ++i) {
+            cudaEvent_t e;
+            cudaError_t rc = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+            if (rc != cudaSuccess)
+                return rc;
+            ev.push_back(e);
+        }
+        return cudaSuccess;
+    }
+};
+
+// One pass restricted to rows [r0, r1) of a whole image (no halos): lets the
+// first pass start on the rows already uploaded and the last pass hand finished
+// rows to the download while later rows are still being computed.
+template <typename T>
+int launch_rows(const T *src, const Field<T> *field, T *dst, int64_t nfields, int64_t ny, int64_t nx,
+                int64_t r0, int64_t r1, int uv_mode, const Walls &w, const TapSet<T> &taps,
+                cudaStream_t stream)
+{
+    PassGeom g{};
+    set_geometry(g, ny, nx, 0, true, true, r0, r1 - r0, ny, w);
+    // the kernel numbers output rows from the first computed row
+    return launch_pass<T>(src, field, dst + (size_t)r0 * (size_t)nx, g, nfields, uv_mode, taps, stream);
+}
+
+// Host entry: upload -> passes -> download, pipelined over row bands.
+//   stream `io`  : uploads (band by band: u, v, interleave, texture) and downloads
+//   stream `run` : the passes; pass 1 of a band waits only for the bands it can
+//                  reach (kernel half-width), the last pass releases each band
+//                  to the download as soon as it is done.
 template <typename T>
 int convolve_host(const T *tex, const T *u, const T *v, int64_t nfields, int64_t ny, int64_t nx,
                   const T *kernel, int64_t klen, int uv_mode, const Walls &w,
-                  int64_t iterations, T *out, int device)
+                  int64_t iterations, T *out, int device, int *texture_has_negative = nullptr)
 {
+    if (texture_has_negative)
+        *texture_has_negative = 0;
     if (int rc = check_common(ny, nx, klen, uv_mode, w))
         return rc;
     const size_t count = (size_t)nfields * (size_t)ny * (size_t)nx;
@@ -265,36 +342,130 @@ int convolve_host(const T *tex, const T *u, const T *v, int64_t nfields, int64_t
     }
     const size_t bytes = count * sizeof(T);
 
+    // Row bands (single images only; a batch chunk is pipelined by its caller).
+    const int64_t reach = klen / 2;
+    int64_t nbands = 1;
+    if (nfields == 1) {
+        nbands = std::min<int64_t>(8, (int64_t)(count >> 21));           // >= 2 Mpix per band
+        nbands = std::min<int64_t>(nbands, ny / std::max<int64_t>(2 * reach, 64));
+        nbands = std::max<int64_t>(nbands, 1);
+    }
+    int64_t band_rows = (ny + nbands - 1) / nbands;
+    band_rows = (band_rows + rlic::kTileH - 1) / rlic::kTileH * rlic::kTileH;
+    nbands = (ny + band_rows - 1) / band_rows;
+    const bool periodic_y = w.y_left == RLIC_B200_PERIODIC || w.y_right == RLIC_B200_PERIODIC;
+    auto band_begin = [&](int64_t b) { return std::min(ny, b * band_rows); };
+
     CUDA_TRY(use_device(device));
-    Stream st;
-    CUDA_TRY(cudaStreamCreateWithFlags(&st.s, cudaStreamNonBlocking));
-    // d_tex doubles as the second work buffer
-    DeviceBuf d_tex, d_field, d_work, d_stage;
-    CUDA_TRY(d_tex.alloc(bytes, st.s));
-    CUDA_TRY(d_field.alloc(4 * bytes, st.s));
-    CUDA_TRY(d_work.alloc(bytes, st.s));
-    CUDA_TRY(d_stage.alloc(bytes, st.s));
+    Stream io, run;
+    CUDA_TRY(cudaStreamCreateWithFlags(&io.s, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&run.s, cudaStreamNonBlocking));
+    // d_tex doubles as the second work buffer.  u lands in the (still unused)
+    // work buffer, v in a staging buffer.
+    DeviceBuf d_tex, d_field, d_work, d_stage, d_flag;
+    CUDA_TRY(d_tex.alloc(bytes, io.s));
+    CUDA_TRY(d_field.alloc(4 * bytes, io.s));
+    CUDA_TRY(d_work.alloc(bytes, io.s));
+    CUDA_TRY(d_stage.alloc(bytes, io.s));
+    if (texture_has_negative) {
+        CUDA_TRY(d_flag.alloc(sizeof(int), io.s));
+        CUDA_TRY(cudaMemsetAsync(d_flag.p, 0, sizeof(int), io.s));
+    }
     TapSet<T> taps;
-    CUDA_TRY(taps.prepare(kernel, klen, st.s));
+    CUDA_TRY(taps.prepare(kernel, klen, io.s));
+    Events uploaded, done;
+    CUDA_TRY(uploaded.make((size_t)nbands));
+    CUDA_TRY(done.make((size_t)nbands));
 
-    // u lands in the (still unused) work buffer, v in a staging buffer that is
-    // returned to the pool as soon as the interleave has been enqueued.
-    CUDA_TRY(cudaMemcpyAsync(d_work.p, u, bytes, cudaMemcpyHostToDevice, st.s));
-    CUDA_TRY(cudaMemcpyAsync(d_stage.p, v, bytes, cudaMemcpyHostToDevice, st.s));
-    CUDA_TRY(launch_pack<T>(static_cast<const T *>(d_work.p), static_cast<const T *>(d_stage.p),
-                            static_cast<Field<T> *>(d_field.p), count, st.s));
-    CUDA_TRY(cudaMemcpyAsync(d_tex.p, tex, bytes, cudaMemcpyHostToDevice, st.s));
+    T *const t_tex = static_cast<T *>(d_tex.p);
+    T *const t_work = static_cast<T *>(d_work.p);
+    T *const t_stage = static_cast<T *>(d_stage.p);
+    Field<T> *const t_field = static_cast<Field<T> *>(d_field.p);
+    // pass n writes work[(n-1) % 2]: d_work, then back over the texture copy, ...
+    // exactly two texture-sized work buffers (README.md:158-164 of the reference)
+    T *const bufs[2] = {t_work, t_tex};
+    const bool single = iterations == 1;
 
-    T *result = nullptr;
-    // pass 1 reads the uploaded texture and writes d_work; pass 2 writes back
-    // over the texture copy; and so on: exactly two texture-sized work buffers.
-    int rc = run_device<T>(static_cast<T *>(d_tex.p), static_cast<Field<T> *>(d_field.p), nfields, ny,
-                           nx, taps, uv_mode, w, iterations, static_cast<T *>(d_work.p),
-                           static_cast<T *>(d_tex.p), &result, st.s);
-    if (rc)
-        return rc;
-    CUDA_TRY(cudaMemcpyAsync(out, result, bytes, cudaMemcpyDeviceToHost, st.s));
-    CUDA_TRY(cudaStreamSynchronize(st.s));
+    auto first_pass_band = [&](int64_t b) -> int {
+        // rows this band's walkers can reach must be on the device
+        const int64_t last_row = std::min(ny - 1, band_begin(b + 1) - 1 + reach);
+        const int64_t need = periodic_y ? nbands - 1 : std::min(nbands - 1, last_row / band_rows);
+        CUDA_TRY(cudaStreamWaitEvent(run.s, uploaded.ev[(size_t)need], 0));
+        int rc = launch_rows<T>(t_tex, t_field, bufs[0], nfields, ny, nx, band_begin(b),
+                                band_begin(b + 1), uv_mode, w, taps, run.s);
+        if (rc)
+            return rc;
+        if (single)
+            CUDA_TRY(cudaEventRecord(done.ev[(size_t)b], run.s));
+        return RLIC_B200_OK;
+    };
+
+    // ---- uploads, with pass 1 trailing behind them ----
+    int64_t next_band = 0;   // next band of pass 1 to launch
+    for (int64_t b = 0; b < nbands; ++b) {
+        const size_t off = (size_t)band_begin(b) * (size_t)nx * (size_t)nfields;
+        const size_t n = (size_t)(band_begin(b + 1) - band_begin(b)) * (size_t)nx * (size_t)nfields;
+        CUDA_TRY(cudaMemcpyAsync(t_work + off, u + off, n * sizeof(T), cudaMemcpyHostToDevice, io.s));
+        CUDA_TRY(cudaMemcpyAsync(t_stage + off, v + off, n * sizeof(T), cudaMemcpyHostToDevice, io.s));
+        CUDA_TRY(launch_pack<T>(t_work + off, t_stage + off, t_field + off, n, io.s));
+        CUDA_TRY(cudaMemcpyAsync(t_tex + off, tex + off, n * sizeof(T), cudaMemcpyHostToDevice, io.s));
+        if (texture_has_negative) {
+            const unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, 148 * 16);
+            rlic::any_negative_kernel<T><<<blocks, 256, 0, io.s>>>(t_tex + off, (long long)n,
+                                                                    static_cast<int *>(d_flag.p));
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            CUDA_TRY(cudaGetLastError());
+        }
+        CUDA_TRY(cudaEventRecord(uploaded.ev[(size_t)b], io.s));
+        // launch every band of pass 1 whose reach is now covered
+        while (next_band < nbands && !periodic_y) {
+            const int64_t last_row = std::min(ny - 1, band_begin(next_band + 1) - 1 + reach);
+            if (std::min(nbands - 1, last_row / band_rows) > b)
+                break;
+            if (int rc = first_pass_band(next_band))
+                return rc;
+            ++next_band;
+        }
+    }
+    for (; next_band < nbands; ++next_band)
+        if (int rc = first_pass_band(next_band))
+            return rc;
+
+    // ---- middle passes: whole image ----
+    const T *src = bufs[0];
+    T *result = bufs[0];
+    for (int64_t it = 1; it < iterations; ++it) {
+        T *dst = bufs[it & 1];
+        const bool last = it == iterations - 1;
+        if (!last) {
+            if (int rc = launch_rows<T>(src, t_field, dst, nfields, ny, nx, 0, ny, uv_mode, w, taps, run.s))
+                return rc;
+        } else {
+            for (int64_t b = 0; b < nbands; ++b) {   // last pass: band by band
+                if (int rc = launch_rows<T>(src, t_field, dst, nfields, ny, nx, band_begin(b),
+                                            band_begin(b + 1), uv_mode, w, taps, run.s))
+                    return rc;
+                CUDA_TRY(cudaEventRecord(done.ev[(size_t)b], run.s));
+            }
+        }
+        src = dst;
+        result = dst;
+    }
+
+    // ---- downloads, trailing behind the last pass ----
+    // the passes are running: get the destination's pages ready meanwhile
+    prefault_for_write(out, bytes);
+    for (int64_t b = 0; b < nbands; ++b) {
+        const size_t off = (size_t)band_begin(b) * (size_t)nx * (size_t)nfields;
+        const size_t n = (size_t)(band_begin(b + 1) - band_begin(b)) * (size_t)nx * (size_t)nfields;
+        CUDA_TRY(cudaStreamWaitEvent(io.s, done.ev[(size_t)b], 0));
+        CUDA_TRY(cudaMemcpyAsync(out + off, result + off, n * sizeof(T), cudaMemcpyDeviceToHost, io.s));
+    }
+    if (texture_has_negative)
+        CUDA_TRY(cudaMemcpyAsync(texture_has_negative, d_flag.p, sizeof(int), cudaMemcpyDeviceToHost,
+                                 io.s));
+    CUDA_TRY(cudaStreamSynchronize(io.s));
+    CUDA_TRY(cudaStreamSynchronize(run.s));
     return RLIC_B200_OK;
 }
 
@@ -441,30 +612,40 @@ int convolve_batch(const T *tex, const T *u, const T *v, int64_t nfields, int64_
     // chunk: enough fields to fill the GPU (~16 Mpix) but at least 1
     const int64_t chunk = std::max<int64_t>(1, (int64_t)((size_t)(16u << 20) / field_elems));
 
-    std::vector<int> rcs(devs.size(), 0);
-    std::vector<std::string> msgs(devs.size());
+    // Two host threads per device take chunks alternately: while one chunk is
+    // being computed or downloaded, the next one is already uploading.
+    const int lanes = 2;
+    std::vector<int> rcs(devs.size() * lanes, 0);
+    std::vector<std::string> msgs(devs.size() * lanes);
+    std::vector<std::atomic<int64_t>> cursor(devs.size());
     std::vector<std::thread> workers;
     for (int64_t d = 0; d < nd; ++d) {
         const int64_t f0 = nfields * d / nd, f1 = nfields * (d + 1) / nd;
-        workers.emplace_back([&, d, f0, f1]() {
-            int rc = 0;
-            for (int64_t f = f0; f < f1 && !rc; f += chunk) {
-                const int64_t n = std::min(chunk, f1 - f);
-                const size_t off = (size_t)f * field_elems;
-                rc = convolve_host<T>(tex + off, u + off, v + off, n, ny, nx, kernel, klen, uv_mode,
-                                      w, iterations, out + off, devs[(size_t)d]);
-            }
-            rcs[(size_t)d] = rc;
-            if (rc)
-                msgs[(size_t)d] = tls_error;
-        });
+        cursor[(size_t)d].store(f0);
+        for (int lane = 0; lane < lanes; ++lane) {
+            workers.emplace_back([&, d, f1, lane]() {
+                int rc = 0;
+                while (!rc) {
+                    const int64_t f = cursor[(size_t)d].fetch_add(chunk);
+                    if (f >= f1)
+                        break;
+                    const int64_t n = std::min(chunk, f1 - f);
+                    const size_t off = (size_t)f * field_elems;
+                    rc = convolve_host<T>(tex + off, u + off, v + off, n, ny, nx, kernel, klen,
+                                          uv_mode, w, iterations, out + off, devs[(size_t)d]);
+                }
+                rcs[(size_t)d * lanes + lane] = rc;
+                if (rc)
+                    msgs[(size_t)d * lanes + lane] = tls_error;
+            });
+        }
     }
     for (auto &t : workers)
         t.join();
-    for (size_t d = 0; d < devs.size(); ++d)
-        if (rcs[d]) {
-            tls_error = msgs[d];
-            return rcs[d];
+    for (size_t i = 0; i < rcs.size(); ++i)
+        if (rcs[i]) {
+            tls_error = msgs[i];
+            return rcs[i];
         }
     return RLIC_B200_OK;
 }
@@ -510,6 +691,18 @@ int rlic_b200_set_device(int device)
         return convolve_host<T>(texture, u, v, 1, ny, nx, kernel, klen, uv_mode,                 \
                                 Walls{x_left, x_right, y_left, y_right}, iterations, out,        \
                                 tls_device);                                                     \
+    }                                                                                            \
+    int rlic_b200_convolve_checked_##sfx(const T *texture, const T *u, const T *v, int64_t ny,   \
+                                         int64_t nx, const T *kernel, int64_t klen, int uv_mode, \
+                                         int x_left, int x_right, int y_left, int y_right,       \
+                                         int64_t iterations, T *out, int *texture_has_negative)  \
+    {                                                                                            \
+        tls_error.clear();                                                                       \
+        if (!texture_has_negative)                                                               \
+            return fail(RLIC_B200_EINVAL, "texture_has_negative is null");                       \
+        return convolve_host<T>(texture, u, v, 1, ny, nx, kernel, klen, uv_mode,                 \
+                                Walls{x_left, x_right, y_left, y_right}, iterations, out,        \
+                                tls_device, texture_has_negative);                               \
     }                                                                                            \
     int rlic_b200_convolve_device_##sfx(const T *d_texture, const T *d_u, const T *d_v,          \
                                         int64_t ny, int64_t nx, const T *kernel, int64_t klen,   \

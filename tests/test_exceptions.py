@@ -68,8 +68,22 @@ def test_zero_and_nan_texture_values_pass_validation():
     tex = np.zeros((4, 4))
     tex[1, 1] = np.nan
     z = np.zeros((4, 4))
-    problems, walls = _check_inputs(tex, z, z, np.ones(3), "velocity", "closed", 1)
-    assert problems == [] and walls is not None
+    problems, walls, deferred = _check_inputs(tex, z, z, np.ones(3), "velocity", "closed", 1)
+    assert problems == [] and walls is not None and deferred is None
+
+
+def test_negative_values_in_a_large_texture_join_the_group_in_order():
+    # large textures defer their sign scan to the GPU, unless something else is
+    # wrong: then it must still appear, in the reference's position (after ndim,
+    # before the shape mismatch)
+    tex = np.ones((300, 300))
+    tex[7, 7] = -1.0
+    with pytest.RaisesGroup(
+        pytest.RaisesExc(ValueError, match=r"^Found invalid texture element"),
+        pytest.RaisesExc(ValueError, match=r"^Shape mismatch"),
+        match=r"^Invalid inputs were received\.",
+    ):
+        rlic.convolve(tex, U, V, kernel=KERNEL)
 
 
 @pytest.mark.parametrize(

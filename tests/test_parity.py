@@ -228,13 +228,24 @@ def test_c2_full_size_full_oracle():
     assert_array_equal(got, want)
 
 
-def test_mismatch_fraction_against_the_pypi_x86_64_variant():
-    # informational bound: the fma+branching build (PyPI x86_64 wheels) may
-    # differ in the last bits; north_star tolerance is 1e-5 of the range in f32
+def test_mismatch_fraction_against_the_pypi_x86_64_variant(capsys):
+    """Informational: the published x86_64 wheels are built fma-only (branching
+    edge-time formula, cd.yml:89,139,210), the crate default and this package are
+    fma+branchless.  The two differ by one ulp in an edge time now and then, which
+    occasionally flips a `tx < ty` decision and sends a walker down another path
+    (SURVEY.md section 0.3).  Report how rare that is; it must stay a tiny
+    minority and everything else must agree to north_star's 1e-5 of the range."""
     w = workloads.vortex_noise(512, iterations=1)
     got = rlic.convolve(w.texture, w.u, w.v, kernel=w.kernel)
     other = oracle.convolve(w.texture, w.u, w.v, kernel=w.kernel, variant=oracle.VARIANT_FMA)
-    assert np.abs(got - other).max() <= 1e-5 * np.ptp(other)
+    err = np.abs(got - other) / np.ptp(other)
+    diverged = float(np.mean(err > 1e-5))
+    bit_equal = float(np.mean(got == other))
+    with capsys.disabled():
+        print(f"\n[vs fma-only build] bit-equal {bit_equal:.4%}, beyond 1e-5 of range {diverged:.4%}, "
+              f"max {err.max():.3e}")
+    assert diverged < 5e-3
+    assert bit_equal > 0.5
 
 
 def test_concurrent_calls_are_independent():
@@ -273,6 +284,18 @@ def test_batch_entry_point_matches_per_field_calls():
     bnd = (("closed", "closed"), ("periodic", "periodic"))
     for f in range(nf):
         assert_array_equal(out[f], oracle.convolve(tex[f], u[f], v[f], kernel=k, boundaries=bnd, iterations=3))
+
+
+def test_negative_texture_is_caught_on_the_device():
+    # >= 65536 pixels: the sign check runs on the GPU during the upload
+    tex, u, v, k = random_case((300, 300), np.float32, 5, seed=2)
+    tex[123, 45] = -1e-30
+    with pytest.raises(ValueError, match=r"^Found invalid texture element\(s\)\. Expected only positive values\.$"):
+        rlic.convolve(tex, u, v, kernel=k)
+    tex[123, 45] = np.nan      # NaN is not negative
+    tex[0, 0] = 0.0
+    tex[1, 1] = -0.0           # neither is -0.0 (np.any(tex < 0) is False)
+    check(tex, u, v, k)
 
 
 def test_launch_counter_counts_passes():
