@@ -131,7 +131,41 @@ void run_type(const char *tname, int n, int L, const char *only)
         cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, k));
         if (!only || strstr("shipped", only)) results.push_back({"shipped", best, true, fa.numRegs});
     }
-    // candidates go here: run, memcmp against `ref`, push_back
+    std::vector<T> h_ref(count), h_out(count);
+    CK(cudaMemcpy(h_ref.data(), ref, count * sizeof(T), cudaMemcpyDeviceToHost));
+    T *out; CK(cudaMalloc(&out, count * sizeof(T)));
+#define CAND(NAME, TW, TH, UNROLL, MINB, FLAVOR) do { \
+        if (only && !strstr(NAME, only)) break; \
+        auto k = rlic::lic_pass_kernel<T, false, PT, int, TW, TH, UNROLL, MINB, FLAVOR>; \
+        PassGeom gc = g; \
+        gc.tiles_x = (n + TW - 1) / TW; \
+        gc.tiles_per_field = gc.tiles_x * ((n + TH - 1) / TH); \
+        float best = 1e9; \
+        CK(cudaMemset(out, 0, count * sizeof(T))); \
+        for (int r = 0; r < reps + 1; ++r) { \
+            CK(cudaEventRecord(e0)); \
+            k<<<gc.tiles_per_field, TW * TH>>>(tex, field, out, gc, taps, L); \
+            CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); \
+            float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); if (r) best = fminf(best, ms); \
+        } \
+        CK(cudaGetLastError()); \
+        CK(cudaMemcpy(h_out.data(), out, count * sizeof(T), cudaMemcpyDeviceToHost)); \
+        bool same = memcmp(h_out.data(), h_ref.data(), count * sizeof(T)) == 0; \
+        cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, k)); \
+        results.push_back({NAME, best, same, fa.numRegs}); \
+    } while (0)
+    //    name              TW  TH  unroll minblocks flavor
+    CAND("16x16 u2 b8 f0", 16, 16, 2, 8, 0);
+    CAND("16x16 u2 b6 f0", 16, 16, 2, 6, 0);
+    CAND("16x16 u4 b8 f0", 16, 16, 4, 8, 0);
+    CAND("16x16 u2 b8 f1", 16, 16, 2, 8, 1);
+    CAND("16x16 u2 b6 f1", 16, 16, 2, 6, 1);
+    CAND("16x16 u4 b8 f1", 16, 16, 4, 8, 1);
+    CAND("16x16 u4 b6 f1", 16, 16, 4, 6, 1);
+    CAND("32x8 u2 b8 f1", 32, 8, 2, 8, 1);
+    CAND("32x32 u2 b2 f1", 32, 32, 2, 2, 1);
+    CAND("32x32 u2 b2 f0", 32, 32, 2, 2, 0);
+    CK(cudaFree(out));
 
     const double steps = (double)count * (L - 1);
     const double bytes = (double)count * (3 * (L - 1) + 2) * sizeof(T);
