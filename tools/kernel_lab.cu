@@ -134,9 +134,9 @@ void run_type(const char *tname, int n, int L, const char *only)
     std::vector<T> h_ref(count), h_out(count);
     CK(cudaMemcpy(h_ref.data(), ref, count * sizeof(T), cudaMemcpyDeviceToHost));
     T *out; CK(cudaMalloc(&out, count * sizeof(T)));
-#define CAND(NAME, TW, TH, UNROLL, MINB, FLAVOR) do { \
+#define CAND(NAME, TW, TH, UNROLL, MINB, FLAVOR, ADMIT) do { \
         if (only && !strstr(NAME, only)) break; \
-        auto k = rlic::lic_pass_kernel<T, false, PT, int, TW, TH, UNROLL, MINB, FLAVOR>; \
+        auto k = rlic::lic_pass_kernel<T, false, PT, int, TW, TH, UNROLL, MINB, FLAVOR, ADMIT>; \
         PassGeom gc = g; \
         gc.tiles_x = (n + TW - 1) / TW; \
         gc.tiles_per_field = gc.tiles_x * ((n + TH - 1) / TH); \
@@ -154,17 +154,17 @@ void run_type(const char *tname, int n, int L, const char *only)
         cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, k)); \
         results.push_back({NAME, best, same, fa.numRegs}); \
     } while (0)
-    //    name              TW  TH  unroll minblocks flavor
-    CAND("16x16 u2 b8 f0", 16, 16, 2, 8, 0);
-    CAND("16x16 u2 b6 f0", 16, 16, 2, 6, 0);
-    CAND("16x16 u4 b8 f0", 16, 16, 4, 8, 0);
-    CAND("16x16 u2 b8 f1", 16, 16, 2, 8, 1);
-    CAND("16x16 u2 b6 f1", 16, 16, 2, 6, 1);
-    CAND("16x16 u4 b8 f1", 16, 16, 4, 8, 1);
-    CAND("16x16 u4 b6 f1", 16, 16, 4, 6, 1);
-    CAND("32x8 u2 b8 f1", 32, 8, 2, 8, 1);
-    CAND("32x32 u2 b2 f1", 32, 32, 2, 2, 1);
-    CAND("32x32 u2 b2 f0", 32, 32, 2, 2, 0);
+    //    name              TW  TH  unroll minblocks flavor admit
+    CAND("u4 b8 f1 a0", 16, 16, 4, 8, 1, 0);
+    CAND("u4 b8 f1 a1", 16, 16, 4, 8, 1, 1);
+    CAND("u4 b8 f1 a2", 16, 16, 4, 8, 1, 2);
+    CAND("u4 b8 f1 a3", 16, 16, 4, 8, 1, 3);
+    CAND("u2 b8 f1 a2", 16, 16, 2, 8, 1, 2);
+    CAND("u2 b8 f1 a3", 16, 16, 2, 8, 1, 3);
+    CAND("u2 b6 f0 a0", 16, 16, 2, 6, 0, 0);
+    CAND("u2 b6 f0 a2", 16, 16, 2, 6, 0, 2);
+    CAND("u2 b6 f0 a3", 16, 16, 2, 6, 0, 3);
+    CAND("u2 b6 f1 a0", 16, 16, 2, 6, 1, 0);
     CK(cudaFree(out));
 
     const double steps = (double)count * (L - 1);
