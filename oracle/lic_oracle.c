@@ -15,8 +15,9 @@
  *     (NaN-field scaling kernel[mid]**n, transpose symmetry, eye(5) polarization
  *     cases, default-argument equalities)
  *   - a second, independent pure-Python restatement (oracle/pyoracle.py)
- * It is NOT pinned against output arrays produced by the reference itself;
- * DESIGN.md says so under "Oracle".
+ * It is NOT pinned against output arrays produced by the reference itself:
+ * with respect to reference-generated outputs the status is "parity unpinned"
+ * (DESIGN.md section 3 says the same).
  *
  * Arithmetic variants mirror the reference's Cargo features
  * (Cargo.toml:27-30): bit 0 = fma, bit 1 = branchless.  Variant 3
