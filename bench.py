@@ -48,7 +48,9 @@ def measured_peak_gbs() -> tuple[float, str]:
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """Samples nvidia-smi clocks / throttle reasons; `mark_begin`/`mark_end` bracket the
+    timed region and only samples that arrived inside it are summarised (nvidia-smi takes
+    longer to start than a short timed region lasts, so it is started before the warm-up)."""
 
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -57,7 +59,8 @@ class ClockSampler:
     def __init__(self, index: int):
         self.index = index
         self.proc = None
-        self.lines: list[str] = []
+        self.lines: list[tuple[float, str]] = []
+        self.t0 = self.t1 = None
 
     def __enter__(self):
         try:
@@ -73,11 +76,17 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def __exit__(self, *exc):
         if self.proc is not None:
-            time.sleep(0.15)
+            time.sleep(0.05)
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=5)
@@ -87,7 +96,12 @@ class ClockSampler:
     def summary(self) -> dict:
         sm, smax, power, reasons = [], [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for line in self.lines:
+        inside = [l for t, l in self.lines if self.t0 is not None and self.t0 <= t <= (self.t1 or t) + 0.03]
+        where = "timed region"
+        if not inside:   # region shorter than one sampling period: fall back to the whole loaded run
+            inside = [l for _, l in self.lines]
+            where = "warm-up + timed region"
+        for line in inside:
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 8:
                 continue
@@ -103,7 +117,8 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax),
-                "power_w_max": max(power), "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w_max": max(power), "reasons": sorted(reasons), "samples": len(sm),
+                "sampled_during": where}
 
 
 def make_slab(rank: int, world: int):
@@ -277,21 +292,22 @@ def run_ours(args) -> dict:
                 events[1].record()
             return out
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
           for _ in range(args.steps)]
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches0 = _core.launch_count()
     with ClockSampler(local) as clocks:
+        for _ in range(max(args.warmup, 3)):
+            step()
         barrier()
+        launches0 = _core.launch_count()
+        clocks.mark_begin()
         t_begin.record()
         for k in range(args.steps):
             result = step(ev[k])
         t_end.record()
         barrier()
-    launches = _core.launch_count() - launches0
+        clocks.mark_end()
+        launches = _core.launch_count() - launches0
     total_ms = t_begin.elapsed_time(t_end)
     pass_ms = sum(a.elapsed_time(b) for a, b in ev)   # the 5 passes of every step
     if dist is not None:
