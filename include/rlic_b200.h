@@ -66,6 +66,11 @@ int rlic_b200_device_count(void);
  * (all threads, all devices).  bench.py reads it around the timed region. */
 int64_t rlic_b200_launch_count(void);
 
+/* Testing hook: when `on` is non-zero every later launch uses the 64-bit element
+ * index instantiation of the kernels, which is otherwise selected only for
+ * buffers of 2^31 elements or more (a 46341 x 46341 image). */
+void rlic_b200_debug_force_wide_index(int on);
+
 /*
  * HOST entry points — replace rlic._core.convolve_f32 / convolve_f64
  * (lib.rs:451-482 -> convolve_iteratively, lib.rs:408-443).

@@ -28,6 +28,7 @@ using rlic::PassGeom;
 thread_local std::string tls_error;
 thread_local int tls_device = 0;
 std::atomic<int64_t> g_launches{0};
+std::atomic<int> g_force_wide{0};   // testing hook: use 64-bit element indices for any size
 
 int fail(int code, const char *fmt, ...)
 {
@@ -242,7 +243,8 @@ int launch_pass(const T *tex, const Field<T> *field, T *out, PassGeom g, int64_t
         return fail(RLIC_B200_EINVAL, "too many tiles for one launch (%lld)", (long long)blocks);
     g.tiles_per_field = (int)per_field;
     // 32-bit element indices whenever one field's buffer allows it
-    const bool wide = g.field_stride + 2 * (int64_t)g.nx >= (int64_t)INT_MAX;
+    const bool wide = g.field_stride + 2 * (int64_t)g.nx >= (int64_t)INT_MAX ||
+                      g_force_wide.load(std::memory_order_relaxed) != 0;
     if (g.total < 0)
         g.total = wide ? LLONG_MAX : (long long)INT_MAX;
     const bool pol = uv_mode == RLIC_B200_POLARIZATION;
@@ -669,6 +671,8 @@ int rlic_b200_device_count(void)
 }
 
 int64_t rlic_b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+void rlic_b200_debug_force_wide_index(int on) { g_force_wide.store(on ? 1 : 0); }
 
 int rlic_b200_set_device(int device)
 {

@@ -18,6 +18,7 @@ HEADER = (ROOT / "include" / "rlic_b200.h").read_text()
 def declared_symbols() -> list[str]:
     # every function prototype in the header: "<ret> rlic_b200_name("
     names = re.findall(r"^\s*(?:const\s+)?[A-Za-z_0-9]+\s*\*?\s*(rlic_b200_[a-z0-9_]+)\s*\(", HEADER, re.M)
+    assert "rlic_b200_debug_force_wide_index" in names
     return sorted(set(names))
 
 

@@ -298,6 +298,48 @@ def test_negative_texture_is_caught_on_the_device():
     check(tex, u, v, k)
 
 
+def test_64_bit_index_instantiation():
+    """Buffers of >= 2^31 elements use 64-bit element indices; force that code path
+    on ordinary sizes and hold it to the same bits."""
+    _core.lib.rlic_b200_debug_force_wide_index(1)
+    try:
+        for dtype, mode, walls in ((np.float32, "velocity", "closed"), (np.float64, "polarization", "periodic"),
+                                   (np.float32, "polarization", "x-periodic"), (np.float64, "velocity", "y-periodic")):
+            check(*random_case((70, 45), dtype, 19, seed=77), mode=mode, walls=walls, iterations=2)
+    finally:
+        _core.lib.rlic_b200_debug_force_wide_index(0)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_randomised_configurations(seed):
+    """Seeded fuzzing over shapes, kernel lengths, modes, walls, dtypes and field styles."""
+    rng = np.random.default_rng(1000 + seed)
+    dtype = [np.float32, np.float64][seed % 2]
+    ny, nx = (int(x) for x in rng.integers(1, 90, size=2))
+    klen = int(rng.integers(1, 80))
+    style = seed % 4
+    tex = rng.random((ny, nx)).astype(dtype)
+    if style == 0:      # smooth field with exact zeros on grid lines
+        y, x = np.meshgrid(np.linspace(-1, 1, ny), np.linspace(-1, 1, nx), indexing="ij")
+        u, v = np.sin(3 * y).astype(dtype), (x * y).astype(dtype)
+    elif style == 1:    # piecewise constant with sign flips and zero blocks
+        u = rng.choice([-1.0, 0.0, 1.0, 0.5], size=(ny, nx)).astype(dtype)
+        v = rng.choice([-2.0, 0.0, 1.0], size=(ny, nx)).astype(dtype)
+    elif style == 2:    # wide dynamic range, some non-finite
+        u = (rng.standard_normal((ny, nx)) * 10.0 ** rng.integers(-30, 30, size=(ny, nx))).astype(dtype)
+        v = (rng.standard_normal((ny, nx)) * 10.0 ** rng.integers(-30, 30, size=(ny, nx))).astype(dtype)
+        u[rng.random((ny, nx)) < 0.02] = np.nan
+        v[rng.random((ny, nx)) < 0.02] = np.inf
+    else:               # plain noise
+        u = (rng.random((ny, nx)) - 0.5).astype(dtype)
+        v = (rng.random((ny, nx)) - 0.5).astype(dtype)
+    kernel = (rng.random(klen) - 0.3).astype(dtype)
+    mode = ["velocity", "polarization"][int(rng.integers(2))]
+    walls = list(WALLS)[int(rng.integers(len(WALLS)))]
+    with np.errstate(all="ignore"):
+        check(tex, u, v, kernel, mode=mode, walls=walls, iterations=int(rng.integers(1, 4)))
+
+
 def test_launch_counter_counts_passes():
     tex, u, v, k = random_case((16, 16), np.float32, 5, seed=1, specials=False)
     before = _core.launch_count()
