@@ -155,16 +155,14 @@ void run_type(const char *tname, int n, int L, const char *only)
         results.push_back({NAME, best, same, fa.numRegs}); \
     } while (0)
     //    name              TW  TH  unroll minblocks flavor admit
-    CAND("u4 b8 f1 a0", 16, 16, 4, 8, 1, 0);
-    CAND("u4 b8 f1 a1", 16, 16, 4, 8, 1, 1);
-    CAND("u4 b8 f1 a2", 16, 16, 4, 8, 1, 2);
-    CAND("u4 b8 f1 a3", 16, 16, 4, 8, 1, 3);
-    CAND("u2 b8 f1 a2", 16, 16, 2, 8, 1, 2);
     CAND("u2 b8 f1 a3", 16, 16, 2, 8, 1, 3);
-    CAND("u2 b6 f0 a0", 16, 16, 2, 6, 0, 0);
+    CAND("u2 b7 f1 a3", 16, 16, 2, 7, 1, 3);
+    CAND("u2 b6 f1 a3", 16, 16, 2, 6, 1, 3);
+    CAND("u4 b8 f1 a3", 16, 16, 4, 8, 1, 3);
+    CAND("u4 b7 f1 a3", 16, 16, 4, 7, 1, 3);
+    CAND("u2 b7 f0 a2", 16, 16, 2, 7, 0, 2);
     CAND("u2 b6 f0 a2", 16, 16, 2, 6, 0, 2);
-    CAND("u2 b6 f0 a3", 16, 16, 2, 6, 0, 3);
-    CAND("u2 b6 f1 a0", 16, 16, 2, 6, 1, 0);
+    CAND("u2 b5 f0 a2", 16, 16, 2, 5, 0, 2);
     CK(cudaFree(out));
 
     const double steps = (double)count * (L - 1);
