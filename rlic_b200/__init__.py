@@ -11,6 +11,7 @@ Anne Archibald) are the behavioural reference only; see NOTICE.
 
 __all__ = [
     "convolve",
+    "convolve_batch",
 ]
 
-from rlic_b200._lib import convolve
+from rlic_b200._lib import convolve, convolve_batch

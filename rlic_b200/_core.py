@@ -13,6 +13,7 @@ RuntimeError at call time.  Nothing here computes on the CPU.
 from __future__ import annotations
 
 __all__ = [
+    "convolve_batch",
     "convolve_f32",
     "convolve_f64",
     "device_count",
@@ -176,6 +177,38 @@ def _convolve(sfx: str, real, texture, uv, kernel, boundaries, iterations, check
             raise ValueError(NEGATIVE_TEXTURE_MESSAGE)
     else:
         check(getattr(lib, f"rlic_b200_convolve_{sfx}")(*args))
+    return out
+
+
+def convolve_batch(textures, uv, kernel, boundaries, iterations=1, devices=None):
+    """``nfields`` independent images stored back to back (``(nfields, ny, nx)`` arrays of
+    one dtype), split whole-image over ``devices`` (default: every visible device).
+    Binding of ``rlic_b200_convolve_batch_*``."""
+    u, v, uv_mode = uv
+    dtype = textures.dtype
+    if dtype == np.dtype("float32"):
+        sfx, real = "f32", ctypes.c_float
+    elif dtype == np.dtype("float64"):
+        sfx, real = "f64", ctypes.c_double
+    else:
+        raise TypeError(f"argument 'textures': expected float32 or float64, got {dtype}")
+    textures = _as_image("textures", textures, dtype, 3)
+    u = _as_image("u", u, dtype, 3)
+    v = _as_image("v", v, dtype, 3)
+    kernel = _as_image("kernel", kernel, dtype, 1)
+    if u.shape != textures.shape or v.shape != textures.shape:
+        raise ValueError("textures, u and v must have identical shapes")
+    nf, ny, nx = textures.shape
+    out = np.empty_like(textures)
+    p = ctypes.POINTER(real)
+    dev_arr, ndev = None, 0
+    if devices is not None:
+        devices = [int(d) for d in devices]
+        dev_arr, ndev = (ctypes.c_int * len(devices))(*devices), len(devices)
+    check(getattr(lib, f"rlic_b200_convolve_batch_{sfx}")(
+        textures.ctypes.data_as(p), u.ctypes.data_as(p), v.ctypes.data_as(p), nf, ny, nx,
+        kernel.ctypes.data_as(p), kernel.size, mode_code(uv_mode), *wall_codes(boundaries),
+        int(iterations), dev_arr, ndev, out.ctypes.data_as(p)))
     return out
 
 

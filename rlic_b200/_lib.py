@@ -10,6 +10,7 @@ from __future__ import annotations
 
 __all__ = [
     "convolve",
+    "convolve_batch",
 ]
 
 from typing import TYPE_CHECKING
@@ -192,3 +193,55 @@ def convolve(
         raise AssertionError
     return run(texture, (u, v, uv_mode), kernel, (walls.x, walls.y), iterations,
                check_texture=deferred is not None)
+
+
+def convolve_batch(
+    textures,
+    /,
+    u,
+    v,
+    *,
+    kernel,
+    uv_mode: UVMode = "velocity",
+    boundaries: BoundarySpec = "closed",
+    iterations: int = 1,
+    devices=None,
+):
+    """``convolve`` for a stack of independent fields (extension; the reference accepts 2D only).
+
+    ``textures``, ``u``, ``v``: arrays of shape ``(nfields, ny, nx)`` and one dtype.
+    ``out[f]`` equals ``convolve(textures[f], u[f], v[f], ...)`` bit for bit; the
+    fields are split whole-image over ``devices`` (default: all visible GPUs) and
+    their uploads, passes and downloads overlap.  Arguments are validated with
+    the same rules and messages as :func:`convolve`, applied to the first field
+    for the per-image checks (every field shares shape and dtype).
+    """
+    for name, arr in (("textures", textures), ("u", u), ("v", v)):
+        if getattr(arr, "ndim", None) != 3:
+            raise ValueError(
+                f"Expected {name} with exactly three dimensions (nfields, ny, nx). "
+                f"Got {name}.ndim={getattr(arr, 'ndim', None)}"
+            )
+    if u.shape != textures.shape or v.shape != textures.shape:
+        raise ValueError(
+            "Shape mismatch: expected textures, u and v with identical shapes. "
+            f"Got textures.shape={textures.shape}, u.shape={u.shape}, v.shape={v.shape}"
+        )
+    if textures.shape[0] == 0:
+        return textures.copy()
+    # dtype / kernel / mode / boundary / iteration rules are those of a single image
+    problems, walls, _ = _check_inputs(
+        textures[0], u[0], v[0], kernel, uv_mode, boundaries, iterations, defer_sign_check=True
+    )
+    if not problems and np.any(textures < 0):
+        problems.append(ValueError(_NEGATIVE_TEXTURE))
+    if len(problems) == 1:
+        raise problems[0]
+    if problems:
+        raise ExceptionGroup("Invalid inputs were received.", problems)
+    assert walls is not None
+    if iterations == 0:
+        return textures.copy()
+    return _core.convolve_batch(
+        textures, (u, v, uv_mode), kernel, (walls.x, walls.y), iterations, devices
+    )

@@ -210,3 +210,20 @@ def test_signature_matches_the_reference():
     assert sig.parameters["uv_mode"].default == "velocity"
     assert sig.parameters["boundaries"].default == "closed"
     assert sig.parameters["iterations"].default == 1
+
+
+def test_batch_entry_validates_like_convolve():
+    tex = np.ones((3, 8, 8))
+    with pytest.raises(ValueError, match=r"^Expected textures with exactly three dimensions"):
+        rlic.convolve_batch(tex[0], tex[0], tex[0], kernel=KERNEL)
+    with pytest.raises(ValueError, match=r"^Shape mismatch: expected textures, u and v"):
+        rlic.convolve_batch(tex, tex[:2], tex, kernel=KERNEL)
+    with pytest.raises(ValueError, match=r"^Invalid uv_mode 'x'"):
+        rlic.convolve_batch(tex, tex, tex, kernel=KERNEL, uv_mode="x")
+    with pytest.raises(ValueError, match=r"^Found invalid texture element"):
+        rlic.convolve_batch(-tex, tex, tex, kernel=KERNEL)
+    with pytest.raises(TypeError, match=r"^Data types mismatch"):
+        rlic.convolve_batch(tex.astype("float32"), tex, tex, kernel=KERNEL)
+    out = rlic.convolve_batch(tex, tex, tex, kernel=KERNEL, iterations=0)
+    assert out is not tex and np.array_equal(out, tex)
+    assert rlic.convolve_batch(tex[:0], tex[:0], tex[:0], kernel=KERNEL).shape == (0, 8, 8)

@@ -340,6 +340,23 @@ def test_randomised_configurations(seed):
         check(tex, u, v, kernel, mode=mode, walls=walls, iterations=int(rng.integers(1, 4)))
 
 
+def test_public_batch_api_matches_per_field_convolve():
+    rng = np.random.default_rng(14)
+    nf, ny, nx = 7, 33, 65
+    tex = rng.random((nf, ny, nx))
+    u = rng.random((nf, ny, nx)) - 0.5
+    v = rng.random((nf, ny, nx)) - 0.5
+    u[3, 5, 5] = 0.0
+    v[4, 6, 6] = np.nan
+    k = workloads.triangle_kernel(17, np.float64)
+    got = rlic.convolve_batch(tex, u, v, kernel=k, uv_mode="polarization",
+                              boundaries={"x": "periodic", "y": "closed"}, iterations=2, devices=[0])
+    for f in range(nf):
+        want = rlic.convolve(tex[f], u[f], v[f], kernel=k, uv_mode="polarization",
+                             boundaries={"x": "periodic", "y": "closed"}, iterations=2)
+        assert_array_equal(got[f], want)
+
+
 def test_launch_counter_counts_passes():
     tex, u, v, k = random_case((16, 16), np.float32, 5, seed=1, specials=False)
     before = _core.launch_count()
