@@ -53,7 +53,7 @@ extern "C" {
 #define RLIC_B200_PERIODIC 1
 
 /* ABI version of this header; bumped on any signature change. */
-#define RLIC_B200_ABI_VERSION 1
+#define RLIC_B200_ABI_VERSION 2
 int rlic_b200_abi_version(void);
 
 /* Message of the last failure on the calling thread ("" if none). */
@@ -68,7 +68,7 @@ int64_t rlic_b200_launch_count(void);
 
 /* Testing hook: when `on` is non-zero every later launch uses the 64-bit element
  * index instantiation of the kernels, which is otherwise selected only for
- * buffers of 2^31 elements or more (a 46341 x 46341 image). */
+ * buffers of 2^31 cells or more (a 46340 x 46340 image). */
 void rlic_b200_debug_force_wide_index(int on);
 
 /*
@@ -127,102 +127,143 @@ int rlic_b200_set_device(int device);
 
 /*
  * DEVICE entry points — same computation on buffers already resident in HBM
- * (used by bench.py's device-resident `value` and
- * by the row-slab sharded driver).
+ * (used by bench.py's device-resident `value`).
  *
- *   d_texture, d_u, d_v : device pointers, ny x nx each, read only
- *   d_work0, d_work1    : device scratch, ny x nx each.  Pass n writes
- *                         work[(n-1) % 2]; the pointer holding the final result
- *                         is returned through *d_result.  (Two texture-sized
- *                         work buffers: the reference's memory contract,
- *                         README.md:158-164.)
+ *   d_texture, d_u, d_v : device pointers, dense ny x nx each, read only
+ *   d_out               : device pointer, dense ny x nx, receives the result
+ *                         (must not alias an input)
  *   kernel              : HOST pointer to the klen taps
  *   stream              : cudaStream_t, or NULL for the legacy default stream
  *
- * The call only enqueues work on `stream`; it does not synchronise.
+ * The call only enqueues work on `stream`; it does not synchronise.  Scratch
+ * (two padded texture buffers -- the reference's two work buffers,
+ * README.md:158-164 -- and the packed field) comes from the device's
+ * stream-ordered memory pool and is returned to it in stream order.
  */
 int rlic_b200_convolve_device_f32(const float *d_texture, const float *d_u, const float *d_v,
                                   int64_t ny, int64_t nx,
                                   const float *kernel, int64_t klen,
                                   int uv_mode,
                                   int x_left, int x_right, int y_left, int y_right,
-                                  int64_t iterations,
-                                  float *d_work0, float *d_work1,
-                                  float **d_result, void *stream);
+                                  int64_t iterations, float *d_out, void *stream);
 
 int rlic_b200_convolve_device_f64(const double *d_texture, const double *d_u, const double *d_v,
                                   int64_t ny, int64_t nx,
                                   const double *kernel, int64_t klen,
                                   int uv_mode,
                                   int x_left, int x_right, int y_left, int y_right,
-                                  int64_t iterations,
-                                  double *d_work0, double *d_work1,
-                                  double **d_result, void *stream);
+                                  int64_t iterations, double *d_out, void *stream);
 
 /*
- * Packed vector field.  The kernels read the field as one record per pixel,
- *     { u, v, ru, rv }        (4 scalars: 16 bytes for f32, 32 bytes for f64)
+ * Device buffer layout of the kernels ("padded").  An image region of `rows`
+ * rows by nx columns is held in (rows + 2) * (nx + 2) cells: a pitch of nx + 2
+ * and one guard row above and below.  The two extra cells of a row and the
+ * guard rows are WALL CELLS: in a texture buffer they mirror the pixel the
+ * boundary rule (lib.rs:83-95) sends a walker to, in the field buffer they hold
+ * a sentinel record with the offset to that pixel, so the walk needs neither a
+ * column counter nor wall compares.  rlic_b200_padded_cells(rows, nx) is that
+ * cell count.  The packed FIELD holds one record of 4 scalars per cell,
+ *     { u, v, ru, rv }        (16 bytes for f32, 32 bytes for f64)
  * where ru, rv are the refined reciprocals that an IEEE division by u, v
  * computes as its first stage; they are walker- and iteration-invariant, so they
- * are computed once per pixel here instead of twice per step in the walk.
- * Pixels with a zero, non-finite or extreme (outside [2^-40, 2^40]) component
- * carry ru = NaN and take the kernels' generic step.  The layout is private to
- * the library version that produced it: always build it with
- * rlic_b200_pack_field_*, from two planar device arrays of `count` scalars into
- * a device buffer of 4*count scalars, aligned to 4 scalars.  The *_packed_* and
- * *_slab_* entry points take that buffer, so callers running many passes over
- * one field pack once.
+ * are computed once per pixel instead of twice per step in the walk.  A
+ * component that is exactly 0 stores 2^120; pixels with a non-finite or extreme
+ * (outside [2^-40, 2^40]) component carry ru = NaN and take the kernels' generic
+ * step.  The layout is private to the library version that produced it: build
+ * it with the functions below, never by hand.
  */
-int rlic_b200_pack_field_f32(const float *d_u, const float *d_v, int64_t count,
+int64_t rlic_b200_padded_cells(int64_t rows, int64_t nx);
+
+/* Packed field of a whole image, from two dense planar device arrays into a
+ * device buffer of 4 * rlic_b200_padded_cells(ny, nx) scalars (aligned to 4
+ * scalars).  The wall sentinels depend on the boundary kinds. */
+int rlic_b200_pack_field_f32(const float *d_u, const float *d_v, int64_t ny, int64_t nx,
+                             int x_left, int x_right, int y_left, int y_right,
                              float *d_field, void *stream);
-int rlic_b200_pack_field_f64(const double *d_u, const double *d_v, int64_t count,
+int rlic_b200_pack_field_f64(const double *d_u, const double *d_v, int64_t ny, int64_t nx,
+                             int x_left, int x_right, int y_left, int y_right,
                              double *d_field, void *stream);
 
-/* Same as rlic_b200_convolve_device_* with the field already packed. */
+/* Same as rlic_b200_convolve_device_* with the field already packed (same ny,
+ * nx and boundary kinds as given to rlic_b200_pack_field_*): callers that run
+ * many convolutions over one field pack once. */
 int rlic_b200_convolve_packed_f32(const float *d_texture, const float *d_field,
                                   int64_t ny, int64_t nx,
                                   const float *kernel, int64_t klen,
                                   int uv_mode,
                                   int x_left, int x_right, int y_left, int y_right,
-                                  int64_t iterations,
-                                  float *d_work0, float *d_work1,
-                                  float **d_result, void *stream);
+                                  int64_t iterations, float *d_out, void *stream);
 int rlic_b200_convolve_packed_f64(const double *d_texture, const double *d_field,
                                   int64_t ny, int64_t nx,
                                   const double *kernel, int64_t klen,
                                   int uv_mode,
                                   int x_left, int x_right, int y_left, int y_right,
-                                  int64_t iterations,
-                                  double *d_work0, double *d_work1,
-                                  double **d_result, void *stream);
+                                  int64_t iterations, double *d_out, void *stream);
 
 /*
- * ONE PASS over a row slab — the building block of row-slab sharding
- * (SURVEY.md section 8(e)).  The image has `ny` x `nx` pixels globally; this
- * device holds global rows [row0 - halo_lo, row0 + nrows + halo_hi) of the
- * texture (d_texture) and of the packed field (d_field) in buffers whose first
- * row is global row `row0 - halo_lo`, and computes output rows
- * [row0, row0 + nrows) into d_out (first row = row0, no halo).
- * The image-level wall rules (lib.rs:83-95) are applied in global row numbers;
- * with y-periodic boundaries the wrap lands in the halo, which the caller has
- * filled from the neighbouring slab in ring order (rows -1, -2, ... are rows
- * ny-1, ny-2, ...).  halo_lo/halo_hi must be >= klen/2 unless a closed wall
- * bounds the slab on that side, otherwise RLIC_B200_ESHARD.
- * With row0 = 0, nrows = ny and no halo this is one pass of the whole image.
+ * ROW SLABS — the building blocks of row-slab sharding.
+ * The image has ny x nx pixels globally; a device holds global rows
+ * [row0 - halo_lo, row0 + nrows + halo_hi) in PADDED buffers of
+ * rlic_b200_padded_cells(halo_lo + nrows + halo_hi, nx) cells that the caller
+ * owns: two for the texture (ping-pong) and one, 4 scalars per cell, for the
+ * field.  Buffer row r (0 = first halo row) together with its two wall cells is
+ * the contiguous cell range [(r + 1) * (nx + 2) - 1, (r + 2) * (nx + 2) - 1):
+ * that is the unit a halo exchange copies.  halo_lo / halo_hi must be >= klen/2
+ * unless a closed wall bounds the slab on that side (else RLIC_B200_ESHARD);
+ * for y-periodic images the halos of the first and last slab wrap around (ring).
+ *
+ *   slab_pack_field    dense u, v of the OWNED rows (nrows x nx) -> packed records
+ *                      of the owned rows (+ the sentinels of any image wall this
+ *                      slab touches).  Halo rows arrive by exchange.
+ *   slab_pad_texture   dense texture of the owned rows -> padded buffer, likewise
+ *   pass_slab          one pass over owned rows [sub_row0, sub_row0 + sub_nrows),
+ *                      reading d_texture / d_field, writing d_out (all padded,
+ *                      same geometry); the wall cells of the written rows are
+ *                      kept up to date.  Walkers use the image-level wall rules
+ *                      in global row numbers, so the stitched result is
+ *                      bit-identical to an unsharded pass.
+ *   slab_unpad_texture padded owned rows -> dense nrows x nx
+ * A whole image is the slab row0 = 0, nrows = ny, no halos.
  */
-int rlic_b200_pass_slab_f32(const float *d_texture, const float *d_field,
-                            float *d_out,
+int rlic_b200_slab_pack_field_f32(const float *d_u, const float *d_v, int64_t ny, int64_t nx,
+                                  int64_t row0, int64_t nrows, int64_t halo_lo, int64_t halo_hi,
+                                  int x_left, int x_right, int y_left, int y_right,
+                                  float *d_field, void *stream);
+int rlic_b200_slab_pack_field_f64(const double *d_u, const double *d_v, int64_t ny, int64_t nx,
+                                  int64_t row0, int64_t nrows, int64_t halo_lo, int64_t halo_hi,
+                                  int x_left, int x_right, int y_left, int y_right,
+                                  double *d_field, void *stream);
+
+int rlic_b200_slab_pad_texture_f32(const float *d_texture, int64_t ny, int64_t nx,
+                                   int64_t row0, int64_t nrows, int64_t halo_lo, int64_t halo_hi,
+                                   int x_left, int x_right, int y_left, int y_right,
+                                   float *d_padded, void *stream);
+int rlic_b200_slab_pad_texture_f64(const double *d_texture, int64_t ny, int64_t nx,
+                                   int64_t row0, int64_t nrows, int64_t halo_lo, int64_t halo_hi,
+                                   int x_left, int x_right, int y_left, int y_right,
+                                   double *d_padded, void *stream);
+
+int rlic_b200_slab_unpad_texture_f32(const float *d_padded, int64_t ny, int64_t nx,
+                                     int64_t row0, int64_t nrows, int64_t halo_lo, int64_t halo_hi,
+                                     int x_left, int x_right, int y_left, int y_right,
+                                     float *d_texture, void *stream);
+int rlic_b200_slab_unpad_texture_f64(const double *d_padded, int64_t ny, int64_t nx,
+                                     int64_t row0, int64_t nrows, int64_t halo_lo, int64_t halo_hi,
+                                     int x_left, int x_right, int y_left, int y_right,
+                                     double *d_texture, void *stream);
+
+int rlic_b200_pass_slab_f32(const float *d_texture, const float *d_field, float *d_out,
                             int64_t ny, int64_t nx,
                             int64_t row0, int64_t nrows, int64_t halo_lo, int64_t halo_hi,
+                            int64_t sub_row0, int64_t sub_nrows,
                             const float *kernel, int64_t klen,
                             int uv_mode,
                             int x_left, int x_right, int y_left, int y_right,
                             void *stream);
-
-int rlic_b200_pass_slab_f64(const double *d_texture, const double *d_field,
-                            double *d_out,
+int rlic_b200_pass_slab_f64(const double *d_texture, const double *d_field, double *d_out,
                             int64_t ny, int64_t nx,
                             int64_t row0, int64_t nrows, int64_t halo_lo, int64_t halo_hi,
+                            int64_t sub_row0, int64_t sub_nrows,
                             const double *kernel, int64_t klen,
                             int uv_mode,
                             int x_left, int x_right, int y_left, int y_right,

@@ -30,7 +30,7 @@ import numpy as np
 _LIB_PATH = Path(__file__).resolve().parent / "librlic_b200.so"
 
 OK, EINVAL, ENODEVICE, ECUDA, ESHARD = range(5)
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _MODE_CODE = {"velocity": 0, "polarization": 1}
 _WALL_CODE = {"closed": 0, "periodic": 1}
@@ -44,18 +44,20 @@ def _signatures(real) -> dict[str, list]:
     """argtypes per entry point for one scalar type; mirrors include/rlic_b200.h."""
     p = ctypes.POINTER(real)
     walls = [_int] * 4
+    slab = [_i64] * 6   # ny, nx, row0, nrows, halo_lo, halo_hi
     return {
         "convolve": [p, p, p, _i64, _i64, p, _i64, _int, *walls, _i64, p],
         "convolve_checked": [p, p, p, _i64, _i64, p, _i64, _int, *walls, _i64, p,
                              ctypes.POINTER(_int)],
-        "convolve_device": [_vp, _vp, _vp, _i64, _i64, p, _i64, _int, *walls, _i64, _vp, _vp,
-                            ctypes.POINTER(_vp), _vp],
-        "pack_field": [_vp, _vp, _i64, _vp, _vp],
-        "convolve_packed": [_vp, _vp, _i64, _i64, p, _i64, _int, *walls, _i64, _vp, _vp,
-                            ctypes.POINTER(_vp), _vp],
-        "pass_slab": [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, p, _i64, _int, *walls, _vp],
         "convolve_batch": [p, p, p, _i64, _i64, _i64, p, _i64, _int, *walls, _i64,
                            ctypes.POINTER(_int), _int, p],
+        "convolve_device": [_vp, _vp, _vp, _i64, _i64, p, _i64, _int, *walls, _i64, _vp, _vp],
+        "pack_field": [_vp, _vp, _i64, _i64, *walls, _vp, _vp],
+        "convolve_packed": [_vp, _vp, _i64, _i64, p, _i64, _int, *walls, _i64, _vp, _vp],
+        "slab_pack_field": [_vp, _vp, *slab, *walls, _vp, _vp],
+        "slab_pad_texture": [_vp, *slab, *walls, _vp, _vp],
+        "slab_unpad_texture": [_vp, *slab, *walls, _vp, _vp],
+        "pass_slab": [_vp, _vp, _vp, *slab, _i64, _i64, p, _i64, _int, *walls, _vp],
     }
 
 
@@ -72,6 +74,8 @@ def _load() -> ctypes.CDLL:
     cdll.rlic_b200_last_error.restype = ctypes.c_char_p
     cdll.rlic_b200_device_count.restype = _int
     cdll.rlic_b200_launch_count.restype = _i64
+    cdll.rlic_b200_padded_cells.argtypes = [_i64, _i64]
+    cdll.rlic_b200_padded_cells.restype = _i64
     cdll.rlic_b200_set_device.argtypes = [_int]
     cdll.rlic_b200_set_device.restype = _int
     for sfx, real in (("f32", ctypes.c_float), ("f64", ctypes.c_double)):
@@ -102,6 +106,11 @@ def device_count() -> int:
 
 def launch_count() -> int:
     return int(lib.rlic_b200_launch_count())
+
+
+def padded_cells(rows: int, nx: int) -> int:
+    """Cells of the kernels' padded buffer for `rows` x `nx` pixels (include/rlic_b200.h)."""
+    return int(lib.rlic_b200_padded_cells(rows, nx))
 
 
 def check(rc: int) -> None:

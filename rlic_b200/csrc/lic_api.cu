@@ -115,51 +115,89 @@ int check_common(int64_t ny, int64_t nx, int64_t klen, int uv_mode, const Walls 
     return RLIC_B200_OK;
 }
 
-// Geometry of one pass over a buffer whose row 0 is global row `shift`
-// (wall rules: lib.rs:83-95).  `lo_wall` / `hi_wall`: whether the image edge on
-// that side can be reached from this buffer and must be acted on (always true
-// for a whole image).  Rows are counted from the first row that needs no action.
-void set_geometry(PassGeom &g, int64_t ny, int64_t nx, int64_t shift, bool lo_wall, bool hi_wall,
-                  int64_t first_row, int64_t out_rows, int64_t rows_alloc, const Walls &w)
+// Which rows of the global ny x nx image a device buffer holds: rows
+// [row0 - halo_lo, row0 + nrows + halo_hi), of which [row0, row0 + nrows) are
+// the ones a launch may compute.  A whole image is {0, ny, 0, 0}.
+struct Slab { int64_t row0, nrows, halo_lo, halo_hi; };
+
+int check_slab(int64_t ny, int64_t klen, const Slab &sl, const Walls &w)
 {
+    if (sl.row0 < 0 || sl.nrows < 0 || sl.row0 + sl.nrows > ny || sl.halo_lo < 0 || sl.halo_hi < 0)
+        return fail(RLIC_B200_ESHARD, "slab rows [%lld,%lld) outside image of %lld rows",
+                    (long long)sl.row0, (long long)(sl.row0 + sl.nrows), (long long)ny);
+    const int64_t reach = klen / 2;   // a walker moves at most one row per tap
+    const bool whole = sl.row0 == 0 && sl.nrows == ny && sl.halo_lo == 0 && sl.halo_hi == 0;
+    const bool periodic_y = w.y_left == RLIC_B200_PERIODIC || w.y_right == RLIC_B200_PERIODIC;
+    // A side needs `reach` halo rows unless a closed wall stops the walker there.
+    const bool lo_closed = sl.row0 == 0 && !periodic_y;
+    const bool hi_closed = sl.row0 + sl.nrows == ny && !periodic_y;
+    if (!whole && ((!lo_closed && sl.halo_lo < reach) || (!hi_closed && sl.halo_hi < reach)))
+        return fail(RLIC_B200_ESHARD, "slab halo (%lld,%lld) shorter than the kernel half-width %lld",
+                    (long long)sl.halo_lo, (long long)sl.halo_hi, (long long)reach);
+    return RLIC_B200_OK;
+}
+
+// Geometry of the padded buffers of a slab (wall rules: lib.rs:83-95).
+PassGeom make_geometry(int64_t ny, int64_t nx, const Slab &sl, const Walls &w)
+{
+    PassGeom g{};
     g.nx = (int)nx;
-    g.out_rows = (int)out_rows;
-    g.field_stride = rows_alloc * nx;
+    g.pitch = (int)nx + 2;
+    g.rows = (int)(sl.halo_lo + sl.nrows + sl.halo_hi);
+    g.field_stride = rlic::padded_cells(g.rows, nx);
+    const int64_t shift = sl.row0 - sl.halo_lo;   // global row of buffer row 0
+    const bool whole = sl.row0 == 0 && sl.nrows == ny && sl.halo_lo == 0 && sl.halo_hi == 0;
+    const bool periodic_y = w.y_left == RLIC_B200_PERIODIC || w.y_right == RLIC_B200_PERIODIC;
+    // a whole image wraps onto itself; a slab of a y-periodic image wraps into
+    // halos its owner filled (ring order), so it has no reachable row walls
+    g.lo_wall = whole || (sl.row0 == 0 && !periodic_y);
+    g.hi_wall = whole || (sl.row0 + sl.nrows == ny && !periodic_y);
     g.j_below_to = w.x_left == RLIC_B200_PERIODIC ? (int)nx - 1 : 0;
     g.j_above_to = w.x_right == RLIC_B200_PERIODIC ? 0 : (int)nx - 1;
-    // buffer row of the first row needing no action: global row 0 when the low
-    // wall is live, else buffer row 0 (a walker never gets above it: halo >= reach)
-    const int64_t i_min = lo_wall ? -shift : 0;
-    g.origin = i_min * nx;
-    g.first_rel = (int)(first_row - i_min);
-    const int64_t below_to = (w.y_left == RLIC_B200_PERIODIC ? ny - 1 : 0) - shift;   // buffer rows
-    const int64_t above_to = (w.y_right == RLIC_B200_PERIODIC ? 0 : ny - 1) - shift;
-    const int64_t span = (ny - shift) - i_min;   // rows until global row ny
-    g.below_shift = (below_to - i_min + 1) * nx;
-    g.above_shift = (above_to - i_min - span) * nx;
-    g.total = hi_wall ? span * nx : -1;          // -1: unreachable, resolved per index width
+    g.i_below_to = (int)((w.y_left == RLIC_B200_PERIODIC ? ny - 1 : 0) - shift);
+    g.i_above_to = (int)((w.y_right == RLIC_B200_PERIODIC ? 0 : ny - 1) - shift);
+    return g;
 }
 
 template <typename T> using Field = rlic::PackedField<T>;
 
-template <typename T, bool POL, typename Taps, typename Idx>
-cudaError_t launch_one(const T *tex, const Field<T> *field, T *out, const PassGeom &g,
-                       const Taps &taps, int ntaps, unsigned blocks, cudaStream_t stream)
+unsigned stream_blocks(long long items)
 {
-    rlic::lic_pass_kernel<T, POL, Taps, Idx>
-        <<<blocks, rlic::kThreads, 0, stream>>>(tex, field, out, g, taps, ntaps);
+    return (unsigned)std::max<long long>(1, std::min<long long>((items + 255) / 256, 148 * 16));
+}
+
+template <typename T>
+cudaError_t launch_pack(const T *u, const T *v, Field<T> *field, const PassGeom &g, int64_t rb,
+                        int64_t re, int64_t nfields, cudaStream_t stream)
+{
+    if (re <= rb || nfields <= 0)
+        return cudaSuccess;
+    rlic::pack_field_kernel<T><<<stream_blocks((re - rb + 2) * g.pitch * nfields), 256, 0, stream>>>(
+        u, v, field, g, (int)rb, (int)re, (long long)nfields);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }
 
 template <typename T>
-cudaError_t launch_pack(const T *u, const T *v, Field<T> *field, size_t count, cudaStream_t stream)
+cudaError_t launch_pad(const T *dense, T *padded, const PassGeom &g, int64_t rb, int64_t re,
+                       int64_t nfields, int *negative, cudaStream_t stream)
 {
-    if (count == 0)
+    if (re <= rb || nfields <= 0)
         return cudaSuccess;
-    const size_t want = (count + 255) / 256;
-    const unsigned blocks = (unsigned)std::min<size_t>(want, 148 * 16);
-    rlic::pack_field_kernel<T><<<blocks, 256, 0, stream>>>(u, v, field, (long long)count);
+    rlic::pad_texture_kernel<T><<<stream_blocks((re - rb + 2) * g.pitch * nfields), 256, 0, stream>>>(
+        dense, padded, g, (int)rb, (int)re, (long long)nfields, negative);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_unpad(const T *padded, T *dense, const PassGeom &g, int64_t rb, int64_t re,
+                         int64_t nfields, cudaStream_t stream)
+{
+    if (re <= rb || nfields <= 0)
+        return cudaSuccess;
+    rlic::unpad_texture_kernel<T><<<stream_blocks((re - rb) * g.nx * nfields), 256, 0, stream>>>(
+        padded, dense, g, (int)rb, (int)re, (long long)nfields);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }
@@ -190,25 +228,37 @@ template <typename T> struct TapSet {
     }
 };
 
-// Launch one pass for `nfields` fields stacked `g.field_stride` elements apart.
+template <typename T, bool POL, typename Taps, typename Idx>
+cudaError_t launch_one(const T *tex, const Field<T> *field, T *out, const PassGeom &g,
+                       const Taps &taps, int ntaps, unsigned blocks, cudaStream_t stream)
+{
+    rlic::lic_pass_kernel<T, POL, Taps, Idx>
+        <<<blocks, rlic::kThreads, 0, stream>>>(tex, field, out, g, taps, ntaps);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+// One pass over buffer rows [first_row, first_row + out_rows) of `nfields`
+// fields.  tex, field, out: padded buffers of geometry g.
 template <typename T>
 int launch_pass(const T *tex, const Field<T> *field, T *out, PassGeom g, int64_t nfields,
-                int uv_mode, const TapSet<T> &taps, cudaStream_t stream)
+                int64_t first_row, int64_t out_rows, int uv_mode, const TapSet<T> &taps,
+                cudaStream_t stream)
 {
-    if (g.out_rows <= 0 || g.nx <= 0 || nfields <= 0)
+    if (out_rows <= 0 || g.nx <= 0 || nfields <= 0)
         return RLIC_B200_OK;
+    g.first_row = (int)first_row;
+    g.out_rows = (int)out_rows;
     g.tiles_x = (g.nx + rlic::kTileW - 1) / rlic::kTileW;
-    const int64_t tiles_y = ((int64_t)g.out_rows + rlic::kTileH - 1) / rlic::kTileH;
+    const int64_t tiles_y = (out_rows + rlic::kTileH - 1) / rlic::kTileH;
     const int64_t per_field = tiles_y * g.tiles_x;
     const int64_t blocks = per_field * nfields;
     if (per_field > INT_MAX || blocks > INT_MAX)
         return fail(RLIC_B200_EINVAL, "too many tiles for one launch (%lld)", (long long)blocks);
     g.tiles_per_field = (int)per_field;
-    // 32-bit element indices whenever one field's buffer allows it
-    const bool wide = g.field_stride + 2 * (int64_t)g.nx >= (int64_t)INT_MAX ||
+    // 32-bit cell indices whenever one field's buffer allows it
+    const bool wide = g.field_stride >= (int64_t)INT_MAX ||
                       g_force_wide.load(std::memory_order_relaxed) != 0;
-    if (g.total < 0)
-        g.total = wide ? LLONG_MAX : (long long)INT_MAX;
     const bool pol = uv_mode == RLIC_B200_POLARIZATION;
 
     cudaError_t e;
@@ -229,28 +279,6 @@ int launch_pass(const T *tex, const Field<T> *field, T *out, PassGeom g, int64_t
     return RLIC_B200_OK;
 }
 
-// `iterations` passes over device-resident buffers (lib.rs:432-440 without the
-// copy-back: the two work buffers swap roles instead).
-template <typename T>
-int run_device(const T *d_tex, const Field<T> *d_field, int64_t nfields, int64_t ny, int64_t nx,
-               const TapSet<T> &taps, int uv_mode, const Walls &w, int64_t iterations, T *work0,
-               T *work1, T **result, cudaStream_t stream)
-{
-    PassGeom g{};
-    set_geometry(g, ny, nx, 0, true, true, 0, ny, ny, w);
-    const T *src = d_tex;
-    T *dst = work0;
-    for (int64_t it = 0; it < iterations; ++it) {
-        dst = (it & 1) ? work1 : work0;
-        int rc = launch_pass<T>(src, d_field, dst, g, nfields, uv_mode, taps, stream);
-        if (rc)
-            return rc;
-        src = dst;
-    }
-    *result = dst;
-    return RLIC_B200_OK;
-}
-
 struct Events {
     std::vector<cudaEvent_t> ev;
     ~Events() { for (cudaEvent_t e : ev) cudaEventDestroy(e); }
@@ -267,22 +295,9 @@ struct Events {
     }
 };
 
-// One pass restricted to rows [r0, r1) of a whole image (no halos): lets the
-// first pass start on the rows already uploaded and the last pass hand finished
-// rows to the download while later rows are still being computed.
-template <typename T>
-int launch_rows(const T *src, const Field<T> *field, T *dst, int64_t nfields, int64_t ny, int64_t nx,
-                int64_t r0, int64_t r1, int uv_mode, const Walls &w, const TapSet<T> &taps,
-                cudaStream_t stream)
-{
-    PassGeom g{};
-    set_geometry(g, ny, nx, 0, true, true, r0, r1 - r0, ny, w);
-    // the kernel numbers output rows from the first computed row
-    return launch_pass<T>(src, field, dst + (size_t)r0 * (size_t)nx, g, nfields, uv_mode, taps, stream);
-}
-
 // Host entry: upload -> passes -> download, pipelined over row bands.
-//   stream `io`  : uploads (band by band: u, v, interleave, texture) and downloads
+//   stream `io`  : uploads (band by band: u, v -> packed field; texture -> padded
+//                  buffer) and downloads (padded -> dense -> host)
 //   stream `run` : the passes; pass 1 of a band waits only for the bands it can
 //                  reach (kernel half-width), the last pass releases each band
 //                  to the download as soon as it is done.
@@ -305,6 +320,8 @@ int convolve_host(const T *tex, const T *u, const T *v, int64_t nfields, int64_t
         return RLIC_B200_OK;
     }
     const size_t bytes = count * sizeof(T);
+    const PassGeom g = make_geometry(ny, nx, Slab{0, ny, 0, 0}, w);
+    const size_t padded_bytes = (size_t)g.field_stride * (size_t)nfields * sizeof(T);
 
     // Row bands (single images only; a batch chunk is pipelined by its caller).
     const int64_t reach = klen / 2;
@@ -324,13 +341,16 @@ int convolve_host(const T *tex, const T *u, const T *v, int64_t nfields, int64_t
     Stream io, run;
     CUDA_TRY(cudaStreamCreateWithFlags(&io.s, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&run.s, cudaStreamNonBlocking));
-    // d_tex doubles as the second work buffer.  u lands in the (still unused)
-    // work buffer, v in a staging buffer.
-    DeviceBuf d_tex, d_field, d_work, d_stage, d_flag;
-    CUDA_TRY(d_tex.alloc(bytes, io.s));
-    CUDA_TRY(d_field.alloc(4 * bytes, io.s));
-    CUDA_TRY(d_work.alloc(bytes, io.s));
-    CUDA_TRY(d_stage.alloc(bytes, io.s));
+    // Two padded texture buffers (the uploaded texture's doubles as the second
+    // work buffer), the packed field, and dense staging for the three uploads
+    // (the texture's staging is reused for the download).
+    DeviceBuf d_tex, d_work, d_field, d_su, d_sv, d_st, d_flag;
+    CUDA_TRY(d_tex.alloc(padded_bytes, io.s));
+    CUDA_TRY(d_work.alloc(padded_bytes, io.s));
+    CUDA_TRY(d_field.alloc(4 * padded_bytes, io.s));
+    CUDA_TRY(d_su.alloc(bytes, io.s));
+    CUDA_TRY(d_sv.alloc(bytes, io.s));
+    CUDA_TRY(d_st.alloc(bytes, io.s));
     if (texture_has_negative) {
         CUDA_TRY(d_flag.alloc(sizeof(int), io.s));
         CUDA_TRY(cudaMemsetAsync(d_flag.p, 0, sizeof(int), io.s));
@@ -343,8 +363,11 @@ int convolve_host(const T *tex, const T *u, const T *v, int64_t nfields, int64_t
 
     T *const t_tex = static_cast<T *>(d_tex.p);
     T *const t_work = static_cast<T *>(d_work.p);
-    T *const t_stage = static_cast<T *>(d_stage.p);
+    T *const s_u = static_cast<T *>(d_su.p);
+    T *const s_v = static_cast<T *>(d_sv.p);
+    T *const s_t = static_cast<T *>(d_st.p);
     Field<T> *const t_field = static_cast<Field<T> *>(d_field.p);
+    int *const flag = static_cast<int *>(d_flag.p);
     // pass n writes work[(n-1) % 2]: d_work, then back over the texture copy, ...
     // exactly two texture-sized work buffers (README.md:158-164 of the reference)
     T *const bufs[2] = {t_work, t_tex};
@@ -355,8 +378,8 @@ int convolve_host(const T *tex, const T *u, const T *v, int64_t nfields, int64_t
         const int64_t last_row = std::min(ny - 1, band_begin(b + 1) - 1 + reach);
         const int64_t need = periodic_y ? nbands - 1 : std::min(nbands - 1, last_row / band_rows);
         CUDA_TRY(cudaStreamWaitEvent(run.s, uploaded.ev[(size_t)need], 0));
-        int rc = launch_rows<T>(t_tex, t_field, bufs[0], nfields, ny, nx, band_begin(b),
-                                band_begin(b + 1), uv_mode, w, taps, run.s);
+        int rc = launch_pass<T>(t_tex, t_field, bufs[0], g, nfields, band_begin(b),
+                                band_begin(b + 1) - band_begin(b), uv_mode, taps, run.s);
         if (rc)
             return rc;
         if (single)
@@ -367,21 +390,16 @@ int convolve_host(const T *tex, const T *u, const T *v, int64_t nfields, int64_t
     // ---- uploads, with pass 1 trailing behind them ----
     int64_t next_band = 0;   // next band of pass 1 to launch
     for (int64_t b = 0; b < nbands; ++b) {
-        const size_t off = (size_t)band_begin(b) * (size_t)nx * (size_t)nfields;
-        const size_t n = (size_t)(band_begin(b + 1) - band_begin(b)) * (size_t)nx * (size_t)nfields;
-        const HostToDevice uv_jobs[2] = {{t_work + off, u + off, n * sizeof(T)},
-                                         {t_stage + off, v + off, n * sizeof(T)}};
+        const int64_t rb = band_begin(b), re = band_begin(b + 1);
+        const size_t off = (size_t)rb * (size_t)nx * (size_t)nfields;
+        const size_t n = (size_t)(re - rb) * (size_t)nx * (size_t)nfields;
+        const HostToDevice uv_jobs[2] = {{s_u + off, u + off, n * sizeof(T)},
+                                         {s_v + off, v + off, n * sizeof(T)}};
         CUDA_TRY(upload(uv_jobs, 2, io.s));
-        CUDA_TRY(launch_pack<T>(t_work + off, t_stage + off, t_field + off, n, io.s));
-        const HostToDevice tex_job{t_tex + off, tex + off, n * sizeof(T)};
+        CUDA_TRY(launch_pack<T>(s_u + off, s_v + off, t_field, g, rb, re, nfields, io.s));
+        const HostToDevice tex_job{s_t + off, tex + off, n * sizeof(T)};
         CUDA_TRY(upload(&tex_job, 1, io.s));
-        if (texture_has_negative) {
-            const unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, 148 * 16);
-            rlic::any_negative_kernel<T><<<blocks, 256, 0, io.s>>>(t_tex + off, (long long)n,
-                                                                    static_cast<int *>(d_flag.p));
-            g_launches.fetch_add(1, std::memory_order_relaxed);
-            CUDA_TRY(cudaGetLastError());
-        }
+        CUDA_TRY(launch_pad<T>(s_t + off, t_tex, g, rb, re, nfields, flag, io.s));
         CUDA_TRY(cudaEventRecord(uploaded.ev[(size_t)b], io.s));
         // launch every band of pass 1 whose reach is now covered
         while (next_band < nbands && !periodic_y) {
@@ -397,19 +415,18 @@ int convolve_host(const T *tex, const T *u, const T *v, int64_t nfields, int64_t
         if (int rc = first_pass_band(next_band))
             return rc;
 
-    // ---- middle passes: whole image ----
+    // ---- middle passes: whole image; last pass: band by band ----
     const T *src = bufs[0];
     T *result = bufs[0];
     for (int64_t it = 1; it < iterations; ++it) {
         T *dst = bufs[it & 1];
-        const bool last = it == iterations - 1;
-        if (!last) {
-            if (int rc = launch_rows<T>(src, t_field, dst, nfields, ny, nx, 0, ny, uv_mode, w, taps, run.s))
+        if (it < iterations - 1) {
+            if (int rc = launch_pass<T>(src, t_field, dst, g, nfields, 0, ny, uv_mode, taps, run.s))
                 return rc;
         } else {
-            for (int64_t b = 0; b < nbands; ++b) {   // last pass: band by band
-                if (int rc = launch_rows<T>(src, t_field, dst, nfields, ny, nx, band_begin(b),
-                                            band_begin(b + 1), uv_mode, w, taps, run.s))
+            for (int64_t b = 0; b < nbands; ++b) {
+                if (int rc = launch_pass<T>(src, t_field, dst, g, nfields, band_begin(b),
+                                            band_begin(b + 1) - band_begin(b), uv_mode, taps, run.s))
                     return rc;
                 CUDA_TRY(cudaEventRecord(done.ev[(size_t)b], run.s));
             }
@@ -422,131 +439,206 @@ int convolve_host(const T *tex, const T *u, const T *v, int64_t nfields, int64_t
     // the passes are running: get the destination's pages ready meanwhile
     prefault_for_write(out, bytes);
     for (int64_t b = 0; b < nbands; ++b) {
-        const size_t off = (size_t)band_begin(b) * (size_t)nx * (size_t)nfields;
-        const size_t n = (size_t)(band_begin(b + 1) - band_begin(b)) * (size_t)nx * (size_t)nfields;
+        const int64_t rb = band_begin(b), re = band_begin(b + 1);
+        const size_t off = (size_t)rb * (size_t)nx * (size_t)nfields;
+        const size_t n = (size_t)(re - rb) * (size_t)nx * (size_t)nfields;
         CUDA_TRY(cudaStreamWaitEvent(io.s, done.ev[(size_t)b], 0));
-        CUDA_TRY(cudaMemcpyAsync(out + off, result + off, n * sizeof(T), cudaMemcpyDeviceToHost, io.s));
+        CUDA_TRY(launch_unpad<T>(result, s_t + off, g, rb, re, nfields, io.s));
+        CUDA_TRY(cudaMemcpyAsync(out + off, s_t + off, n * sizeof(T), cudaMemcpyDeviceToHost, io.s));
     }
     if (texture_has_negative)
-        CUDA_TRY(cudaMemcpyAsync(texture_has_negative, d_flag.p, sizeof(int), cudaMemcpyDeviceToHost,
-                                 io.s));
+        CUDA_TRY(cudaMemcpyAsync(texture_has_negative, flag, sizeof(int), cudaMemcpyDeviceToHost, io.s));
     CUDA_TRY(cudaStreamSynchronize(io.s));
     CUDA_TRY(cudaStreamSynchronize(run.s));
+    return RLIC_B200_OK;
+}
+
+// `iterations` passes from a dense device texture to a dense device result,
+// field already packed (lib.rs:432-440 without the copy-back: two padded work
+// buffers swap roles).
+template <typename T>
+int run_device(const T *d_tex, const Field<T> *d_field, int64_t ny, int64_t nx, const TapSet<T> &taps,
+               int uv_mode, const Walls &w, int64_t iterations, T *d_out, cudaStream_t s)
+{
+    const PassGeom g = make_geometry(ny, nx, Slab{0, ny, 0, 0}, w);
+    const size_t padded_bytes = (size_t)g.field_stride * sizeof(T);
+    DeviceBuf a, b;   // stream-ordered scratch, returned to the pool when the work is enqueued
+    CUDA_TRY(a.alloc(padded_bytes, s));
+    if (iterations > 1)
+        CUDA_TRY(b.alloc(padded_bytes, s));
+    DeviceBuf in;
+    CUDA_TRY(in.alloc(padded_bytes, s));
+    CUDA_TRY(launch_pad<T>(d_tex, static_cast<T *>(in.p), g, 0, ny, 1, nullptr, s));
+    const T *src = static_cast<const T *>(in.p);
+    T *dst = static_cast<T *>(a.p);
+    for (int64_t it = 0; it < iterations; ++it) {
+        // pass 1: in -> a; pass 2: a -> b; pass 3: b -> a; ...
+        dst = static_cast<T *>(it == 0 ? a.p : ((it & 1) ? b.p : a.p));
+        if (int rc = launch_pass<T>(src, d_field, dst, g, 1, 0, ny, uv_mode, taps, s))
+            return rc;
+        src = dst;
+    }
+    CUDA_TRY(launch_unpad<T>(dst, d_out, g, 0, ny, 1, s));
+    return RLIC_B200_OK;
+}
+
+template <typename T>
+int check_device_call(const void *a, const void *b, const void *c, const void *kernel, const void *out,
+                      int64_t ny, int64_t nx, int64_t klen, int uv_mode, const Walls &w)
+{
+    if (int rc = check_common(ny, nx, klen, uv_mode, w))
+        return rc;
+    if (ny == 0 || nx == 0)
+        return RLIC_B200_OK;
+    if (!a || !b || !c || !kernel || !out)
+        return fail(RLIC_B200_EINVAL, "null pointer argument");
     return RLIC_B200_OK;
 }
 
 template <typename T>
 int convolve_device(const T *d_tex, const T *d_u, const T *d_v, int64_t ny, int64_t nx,
                     const T *kernel, int64_t klen, int uv_mode, const Walls &w,
-                    int64_t iterations, T *work0, T *work1, T **result, void *stream)
+                    int64_t iterations, T *d_out, void *stream)
 {
-    if (int rc = check_common(ny, nx, klen, uv_mode, w))
+    if (int rc = check_device_call<T>(d_tex, d_u, d_v, kernel, d_out, ny, nx, klen, uv_mode, w))
         return rc;
-    if (!result)
-        return fail(RLIC_B200_EINVAL, "d_result is null");
-    *result = nullptr;
     if (ny == 0 || nx == 0)
         return RLIC_B200_OK;
-    if (!d_tex || !d_u || !d_v || !kernel || !work0 || (!work1 && iterations > 1))
-        return fail(RLIC_B200_EINVAL, "null pointer argument");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t count = (size_t)ny * (size_t)nx;
     if (iterations <= 0) {
-        CUDA_TRY(cudaMemsetAsync(work0, 0, sizeof(T) * count, s));
-        *result = work0;
+        CUDA_TRY(cudaMemsetAsync(d_out, 0, sizeof(T) * count, s));
         return RLIC_B200_OK;
     }
     TapSet<T> taps;
     CUDA_TRY(taps.prepare(kernel, klen, s));
-    DeviceBuf d_field;   // stream-ordered scratch, returned to the pool after the last pass
-    CUDA_TRY(d_field.alloc(4 * sizeof(T) * count, s));
-    CUDA_TRY(launch_pack<T>(d_u, d_v, static_cast<Field<T> *>(d_field.p), count, s));
-    return run_device<T>(d_tex, static_cast<Field<T> *>(d_field.p), 1, ny, nx, taps, uv_mode, w,
-                         iterations, work0, work1, result, s);
+    const PassGeom g = make_geometry(ny, nx, Slab{0, ny, 0, 0}, w);
+    DeviceBuf d_field;
+    CUDA_TRY(d_field.alloc(4 * sizeof(T) * (size_t)g.field_stride, s));
+    CUDA_TRY(launch_pack<T>(d_u, d_v, static_cast<Field<T> *>(d_field.p), g, 0, ny, 1, s));
+    return run_device<T>(d_tex, static_cast<Field<T> *>(d_field.p), ny, nx, taps, uv_mode, w,
+                         iterations, d_out, s);
 }
 
 template <typename T>
-int convolve_device_packed(const T *d_tex, const T *d_field, int64_t ny, int64_t nx,
-                           const T *kernel, int64_t klen, int uv_mode, const Walls &w,
-                           int64_t iterations, T *work0, T *work1, T **result, void *stream)
+int pack_field(const T *d_u, const T *d_v, int64_t ny, int64_t nx, const Walls &w, T *d_field,
+               void *stream)
 {
-    if (int rc = check_common(ny, nx, klen, uv_mode, w))
+    if (int rc = check_device_call<T>(d_u, d_v, d_field, d_field, d_field, ny, nx, 1, 0, w))
         return rc;
-    if (!result)
-        return fail(RLIC_B200_EINVAL, "d_result is null");
-    *result = nullptr;
     if (ny == 0 || nx == 0)
         return RLIC_B200_OK;
-    if (!d_tex || !d_field || !kernel || !work0 || (!work1 && iterations > 1))
-        return fail(RLIC_B200_EINVAL, "null pointer argument");
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (iterations <= 0) {
-        CUDA_TRY(cudaMemsetAsync(work0, 0, sizeof(T) * (size_t)ny * (size_t)nx, s));
-        *result = work0;
-        return RLIC_B200_OK;
-    }
-    TapSet<T> taps;
-    CUDA_TRY(taps.prepare(kernel, klen, s));
-    return run_device<T>(d_tex, reinterpret_cast<const Field<T> *>(d_field), 1, ny, nx, taps, uv_mode,
-                         w, iterations, work0, work1, result, s);
-}
-
-template <typename T>
-int pack_field(const T *d_u, const T *d_v, int64_t count, T *d_field, void *stream)
-{
-    if (count < 0)
-        return fail(RLIC_B200_EINVAL, "negative element count");
-    if (count == 0)
-        return RLIC_B200_OK;
-    if (!d_u || !d_v || !d_field)
-        return fail(RLIC_B200_EINVAL, "null pointer argument");
-    CUDA_TRY(launch_pack<T>(d_u, d_v, reinterpret_cast<Field<T> *>(d_field), (size_t)count,
+    const PassGeom g = make_geometry(ny, nx, Slab{0, ny, 0, 0}, w);
+    CUDA_TRY(launch_pack<T>(d_u, d_v, reinterpret_cast<Field<T> *>(d_field), g, 0, ny, 1,
                             static_cast<cudaStream_t>(stream)));
     return RLIC_B200_OK;
 }
 
 template <typename T>
-int pass_slab(const T *d_tex, const T *d_field, T *d_out, int64_t ny, int64_t nx, int64_t row0,
-              int64_t nrows, int64_t halo_lo, int64_t halo_hi, const T *kernel, int64_t klen,
-              int uv_mode, const Walls &w, void *stream)
+int convolve_packed(const T *d_tex, const T *d_field, int64_t ny, int64_t nx, const T *kernel,
+                    int64_t klen, int uv_mode, const Walls &w, int64_t iterations, T *d_out,
+                    void *stream)
+{
+    if (int rc = check_device_call<T>(d_tex, d_field, d_field, kernel, d_out, ny, nx, klen, uv_mode, w))
+        return rc;
+    if (ny == 0 || nx == 0)
+        return RLIC_B200_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (iterations <= 0) {
+        CUDA_TRY(cudaMemsetAsync(d_out, 0, sizeof(T) * (size_t)ny * (size_t)nx, s));
+        return RLIC_B200_OK;
+    }
+    TapSet<T> taps;
+    CUDA_TRY(taps.prepare(kernel, klen, s));
+    return run_device<T>(d_tex, reinterpret_cast<const Field<T> *>(d_field), ny, nx, taps, uv_mode, w,
+                         iterations, d_out, s);
+}
+
+// ---- slab building blocks (padded buffers owned by the caller) ----
+template <typename T>
+int slab_pack_field(const T *d_u, const T *d_v, int64_t ny, int64_t nx, const Slab &sl, const Walls &w,
+                    T *d_field, void *stream)
+{
+    if (int rc = check_common(ny, nx, 1, 0, w))
+        return rc;
+    if (int rc = check_slab(ny, 1, sl, w))
+        return rc;
+    if (sl.nrows == 0 || nx == 0)
+        return RLIC_B200_OK;
+    if (!d_u || !d_v || !d_field)
+        return fail(RLIC_B200_EINVAL, "null pointer argument");
+    const PassGeom g = make_geometry(ny, nx, sl, w);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    Field<T> *field = reinterpret_cast<Field<T> *>(d_field);
+    // owned rows from the planar components, with the sentinels of any image
+    // wall they touch; halo rows arrive from the neighbours, already packed
+    CUDA_TRY(launch_pack<T>(d_u, d_v, field, g, sl.halo_lo, sl.halo_lo + sl.nrows, 1, s));
+    return RLIC_B200_OK;
+}
+
+template <typename T>
+int slab_pad_texture(const T *d_tex, int64_t ny, int64_t nx, const Slab &sl, const Walls &w,
+                     T *d_padded, void *stream)
+{
+    if (int rc = check_common(ny, nx, 1, 0, w))
+        return rc;
+    if (int rc = check_slab(ny, 1, sl, w))
+        return rc;
+    if (sl.nrows == 0 || nx == 0)
+        return RLIC_B200_OK;
+    if (!d_tex || !d_padded)
+        return fail(RLIC_B200_EINVAL, "null pointer argument");
+    const PassGeom g = make_geometry(ny, nx, sl, w);
+    CUDA_TRY(launch_pad<T>(d_tex, d_padded, g, sl.halo_lo, sl.halo_lo + sl.nrows, 1, nullptr,
+                           static_cast<cudaStream_t>(stream)));
+    return RLIC_B200_OK;
+}
+
+template <typename T>
+int slab_unpad_texture(const T *d_padded, int64_t ny, int64_t nx, const Slab &sl, const Walls &w,
+                       T *d_tex, void *stream)
+{
+    if (int rc = check_common(ny, nx, 1, 0, w))
+        return rc;
+    if (int rc = check_slab(ny, 1, sl, w))
+        return rc;
+    if (sl.nrows == 0 || nx == 0)
+        return RLIC_B200_OK;
+    if (!d_tex || !d_padded)
+        return fail(RLIC_B200_EINVAL, "null pointer argument");
+    const PassGeom g = make_geometry(ny, nx, sl, w);
+    CUDA_TRY(launch_unpad<T>(d_padded, d_tex, g, sl.halo_lo, sl.halo_lo + sl.nrows, 1,
+                             static_cast<cudaStream_t>(stream)));
+    return RLIC_B200_OK;
+}
+
+template <typename T>
+int pass_slab(const T *d_tex, const T *d_field, T *d_out, int64_t ny, int64_t nx, const Slab &sl,
+              int64_t sub0, int64_t subn, const T *kernel, int64_t klen, int uv_mode,
+              const Walls &w, void *stream)
 {
     if (int rc = check_common(ny, nx, klen, uv_mode, w))
         return rc;
-    if (row0 < 0 || nrows < 0 || row0 + nrows > ny || halo_lo < 0 || halo_hi < 0)
-        return fail(RLIC_B200_ESHARD, "slab rows [%lld,%lld) outside image of %lld rows",
-                    (long long)row0, (long long)(row0 + nrows), (long long)ny);
-    if (nrows == 0 || nx == 0)
+    if (int rc = check_slab(ny, klen, sl, w))
+        return rc;
+    if (sub0 < 0 || subn < 0 || sub0 + subn > sl.nrows)
+        return fail(RLIC_B200_ESHARD, "rows [%lld,%lld) outside the slab's %lld rows",
+                    (long long)sub0, (long long)(sub0 + subn), (long long)sl.nrows);
+    if (subn == 0 || nx == 0)
         return RLIC_B200_OK;
     if (!d_tex || !d_field || !d_out || !kernel)
         return fail(RLIC_B200_EINVAL, "null pointer argument");
-    const int64_t reach = klen / 2;   // a walker moves at most one row per tap
-    const bool bare_whole = row0 == 0 && nrows == ny && halo_lo == 0 && halo_hi == 0;
-    const bool periodic_y = w.y_left == RLIC_B200_PERIODIC || w.y_right == RLIC_B200_PERIODIC;
-    // A side needs `reach` halo rows unless a closed wall stops the walker there.
-    const bool lo_closed = row0 == 0 && !periodic_y;
-    const bool hi_closed = row0 + nrows == ny && !periodic_y;
-    const int64_t rows_alloc = halo_lo + nrows + halo_hi;
-    PassGeom g{};
-    if (bare_whole) {
-        set_geometry(g, ny, nx, 0, true, true, 0, ny, ny, w);
-    } else {
-        if ((!lo_closed && halo_lo < reach) || (!hi_closed && halo_hi < reach))
-            return fail(RLIC_B200_ESHARD,
-                        "slab halo (%lld,%lld) shorter than the kernel half-width %lld",
-                        (long long)halo_lo, (long long)halo_hi, (long long)reach);
-        // periodic rows: the wrap lands in a halo the caller filled (ring order)
-        set_geometry(g, ny, nx, row0 - halo_lo, lo_closed, hi_closed, halo_lo, nrows, rows_alloc, w);
-    }
+    const PassGeom g = make_geometry(ny, nx, sl, w);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     TapSet<T> taps;
     CUDA_TRY(taps.prepare(kernel, klen, s));
-    return launch_pass<T>(d_tex, reinterpret_cast<const Field<T> *>(d_field), d_out, g, 1, uv_mode,
-                          taps, s);
+    return launch_pass<T>(d_tex, reinterpret_cast<const Field<T> *>(d_field), d_out, g, 1,
+                          sl.halo_lo + sub0, subn, uv_mode, taps, s);
 }
 
-// Whole fields split over devices; one host thread per device, fields
-// processed in chunks so uploads, passes and downloads of different chunks
-// overlap on two streams.
+// Whole fields split over devices.  Two host threads per device take chunks
+// alternately: while one chunk is being computed or downloaded, the next one is
+// already uploading.
 template <typename T>
 int convolve_batch(const T *tex, const T *u, const T *v, int64_t nfields, int64_t ny, int64_t nx,
                    const T *kernel, int64_t klen, int uv_mode, const Walls &w,
@@ -578,18 +670,16 @@ int convolve_batch(const T *tex, const T *u, const T *v, int64_t nfields, int64_
     // chunk: enough fields to fill the GPU (~16 Mpix) but at least 1
     const int64_t chunk = std::max<int64_t>(1, (int64_t)((size_t)(16u << 20) / field_elems));
 
-    // Two host threads per device take chunks alternately: while one chunk is
-    // being computed or downloaded, the next one is already uploading.
     const int lanes = 2;
     std::vector<int> rcs(devs.size() * lanes, 0);
     std::vector<std::string> msgs(devs.size() * lanes);
     std::vector<std::atomic<int64_t>> cursor(devs.size());
-    std::vector<std::thread> workers;
+    std::vector<std::thread> threads;
     for (int64_t d = 0; d < nd; ++d) {
         const int64_t f0 = nfields * d / nd, f1 = nfields * (d + 1) / nd;
         cursor[(size_t)d].store(f0);
         for (int lane = 0; lane < lanes; ++lane) {
-            workers.emplace_back([&, d, f1, lane]() {
+            threads.emplace_back([&, d, f1, lane]() {
                 int rc = 0;
                 while (!rc) {
                     const int64_t f = cursor[(size_t)d].fetch_add(chunk);
@@ -606,7 +696,7 @@ int convolve_batch(const T *tex, const T *u, const T *v, int64_t nfields, int64_
             });
         }
     }
-    for (auto &t : workers)
+    for (auto &t : threads)
         t.join();
     for (size_t i = 0; i < rcs.size(); ++i)
         if (rcs[i]) {
@@ -635,6 +725,8 @@ int rlic_b200_device_count(void)
 }
 
 int64_t rlic_b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int64_t rlic_b200_padded_cells(int64_t rows, int64_t nx) { return rlic::padded_cells(rows, nx); }
 
 void rlic_b200_debug_force_wide_index(int on) { g_force_wide.store(on ? 1 : 0); }
 
@@ -672,45 +764,6 @@ int rlic_b200_set_device(int device)
                                 Walls{x_left, x_right, y_left, y_right}, iterations, out,        \
                                 tls_device, texture_has_negative);                               \
     }                                                                                            \
-    int rlic_b200_convolve_device_##sfx(const T *d_texture, const T *d_u, const T *d_v,          \
-                                        int64_t ny, int64_t nx, const T *kernel, int64_t klen,   \
-                                        int uv_mode, int x_left, int x_right, int y_left,        \
-                                        int y_right, int64_t iterations, T *d_work0,             \
-                                        T *d_work1, T **d_result, void *stream)                  \
-    {                                                                                            \
-        tls_error.clear();                                                                       \
-        return convolve_device<T>(d_texture, d_u, d_v, ny, nx, kernel, klen, uv_mode,            \
-                                  Walls{x_left, x_right, y_left, y_right}, iterations, d_work0,  \
-                                  d_work1, d_result, stream);                                    \
-    }                                                                                            \
-    int rlic_b200_pack_field_##sfx(const T *d_u, const T *d_v, int64_t count, T *d_field,              \
-                                void *stream)                                                    \
-    {                                                                                            \
-        tls_error.clear();                                                                       \
-        return pack_field<T>(d_u, d_v, count, d_field, stream);                                        \
-    }                                                                                            \
-    int rlic_b200_convolve_packed_##sfx(const T *d_texture, const T *d_field, int64_t ny,         \
-                                        int64_t nx, const T *kernel, int64_t klen, int uv_mode,  \
-                                        int x_left, int x_right, int y_left, int y_right,        \
-                                        int64_t iterations, T *d_work0, T *d_work1,              \
-                                        T **d_result, void *stream)                              \
-    {                                                                                            \
-        tls_error.clear();                                                                       \
-        return convolve_device_packed<T>(d_texture, d_field, ny, nx, kernel, klen, uv_mode,       \
-                                         Walls{x_left, x_right, y_left, y_right}, iterations,    \
-                                         d_work0, d_work1, d_result, stream);                    \
-    }                                                                                            \
-    int rlic_b200_pass_slab_##sfx(const T *d_texture, const T *d_field, T *d_out, int64_t ny,     \
-                                  int64_t nx, int64_t row0, int64_t nrows, int64_t halo_lo,      \
-                                  int64_t halo_hi, const T *kernel, int64_t klen, int uv_mode,   \
-                                  int x_left, int x_right, int y_left, int y_right,              \
-                                  void *stream)                                                  \
-    {                                                                                            \
-        tls_error.clear();                                                                       \
-        return pass_slab<T>(d_texture, d_field, d_out, ny, nx, row0, nrows, halo_lo, halo_hi,     \
-                            kernel, klen, uv_mode, Walls{x_left, x_right, y_left, y_right},      \
-                            stream);                                                             \
-    }                                                                                            \
     int rlic_b200_convolve_batch_##sfx(const T *texture, const T *u, const T *v,                 \
                                        int64_t nfields, int64_t ny, int64_t nx, const T *kernel, \
                                        int64_t klen, int uv_mode, int x_left, int x_right,       \
@@ -721,6 +774,73 @@ int rlic_b200_set_device(int device)
         return convolve_batch<T>(texture, u, v, nfields, ny, nx, kernel, klen, uv_mode,          \
                                  Walls{x_left, x_right, y_left, y_right}, iterations, devices,   \
                                  ndev, out);                                                     \
+    }                                                                                            \
+    int rlic_b200_convolve_device_##sfx(const T *d_texture, const T *d_u, const T *d_v,          \
+                                        int64_t ny, int64_t nx, const T *kernel, int64_t klen,   \
+                                        int uv_mode, int x_left, int x_right, int y_left,        \
+                                        int y_right, int64_t iterations, T *d_out, void *stream) \
+    {                                                                                            \
+        tls_error.clear();                                                                       \
+        return convolve_device<T>(d_texture, d_u, d_v, ny, nx, kernel, klen, uv_mode,            \
+                                  Walls{x_left, x_right, y_left, y_right}, iterations, d_out,    \
+                                  stream);                                                       \
+    }                                                                                            \
+    int rlic_b200_pack_field_##sfx(const T *d_u, const T *d_v, int64_t ny, int64_t nx,           \
+                                   int x_left, int x_right, int y_left, int y_right,             \
+                                   T *d_field, void *stream)                                     \
+    {                                                                                            \
+        tls_error.clear();                                                                       \
+        return pack_field<T>(d_u, d_v, ny, nx, Walls{x_left, x_right, y_left, y_right}, d_field, \
+                             stream);                                                            \
+    }                                                                                            \
+    int rlic_b200_convolve_packed_##sfx(const T *d_texture, const T *d_field, int64_t ny,        \
+                                        int64_t nx, const T *kernel, int64_t klen, int uv_mode,  \
+                                        int x_left, int x_right, int y_left, int y_right,        \
+                                        int64_t iterations, T *d_out, void *stream)              \
+    {                                                                                            \
+        tls_error.clear();                                                                       \
+        return convolve_packed<T>(d_texture, d_field, ny, nx, kernel, klen, uv_mode,             \
+                                  Walls{x_left, x_right, y_left, y_right}, iterations, d_out,    \
+                                  stream);                                                       \
+    }                                                                                            \
+    int rlic_b200_slab_pack_field_##sfx(const T *d_u, const T *d_v, int64_t ny, int64_t nx,      \
+                                        int64_t row0, int64_t nrows, int64_t halo_lo,            \
+                                        int64_t halo_hi, int x_left, int x_right, int y_left,    \
+                                        int y_right, T *d_field, void *stream)                   \
+    {                                                                                            \
+        tls_error.clear();                                                                       \
+        return slab_pack_field<T>(d_u, d_v, ny, nx, Slab{row0, nrows, halo_lo, halo_hi},         \
+                                  Walls{x_left, x_right, y_left, y_right}, d_field, stream);     \
+    }                                                                                            \
+    int rlic_b200_slab_pad_texture_##sfx(const T *d_texture, int64_t ny, int64_t nx,             \
+                                         int64_t row0, int64_t nrows, int64_t halo_lo,           \
+                                         int64_t halo_hi, int x_left, int x_right, int y_left,   \
+                                         int y_right, T *d_padded, void *stream)                 \
+    {                                                                                            \
+        tls_error.clear();                                                                       \
+        return slab_pad_texture<T>(d_texture, ny, nx, Slab{row0, nrows, halo_lo, halo_hi},       \
+                                   Walls{x_left, x_right, y_left, y_right}, d_padded, stream);   \
+    }                                                                                            \
+    int rlic_b200_slab_unpad_texture_##sfx(const T *d_padded, int64_t ny, int64_t nx,            \
+                                           int64_t row0, int64_t nrows, int64_t halo_lo,         \
+                                           int64_t halo_hi, int x_left, int x_right, int y_left, \
+                                           int y_right, T *d_texture, void *stream)              \
+    {                                                                                            \
+        tls_error.clear();                                                                       \
+        return slab_unpad_texture<T>(d_padded, ny, nx, Slab{row0, nrows, halo_lo, halo_hi},      \
+                                     Walls{x_left, x_right, y_left, y_right}, d_texture,         \
+                                     stream);                                                    \
+    }                                                                                            \
+    int rlic_b200_pass_slab_##sfx(const T *d_texture, const T *d_field, T *d_out, int64_t ny,    \
+                                  int64_t nx, int64_t row0, int64_t nrows, int64_t halo_lo,      \
+                                  int64_t halo_hi, int64_t sub_row0, int64_t sub_nrows,          \
+                                  const T *kernel, int64_t klen, int uv_mode, int x_left,        \
+                                  int x_right, int y_left, int y_right, void *stream)            \
+    {                                                                                            \
+        tls_error.clear();                                                                       \
+        return pass_slab<T>(d_texture, d_field, d_out, ny, nx,                                   \
+                            Slab{row0, nrows, halo_lo, halo_hi}, sub_row0, sub_nrows, kernel,    \
+                            klen, uv_mode, Walls{x_left, x_right, y_left, y_right}, stream);     \
     }
 
 RLIC_DEFINE(float, f32)

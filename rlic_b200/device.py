@@ -66,40 +66,40 @@ def _check_image(name: str, t: torch.Tensor, like: torch.Tensor | None = None) -
 
 @dataclass
 class PackedField:
-    """A vector field in the kernels' native layout (``include/rlic_b200.h``):
-    ``uv[i, j] = (u, v, ru, rv)`` with the precomputed reciprocals."""
+    """A vector field in the kernels' private layout (``include/rlic_b200.h``): one
+    ``(u, v, ru, rv)`` record per cell of the padded buffer, wall sentinels included.
+    Tied to the image shape and boundary kinds it was packed for."""
 
-    uv: torch.Tensor   # (ny, nx, 4), contiguous
-
-    @property
-    def shape(self) -> tuple[int, int]:
-        return tuple(self.uv.shape[:2])
+    data: torch.Tensor   # flat, 4 * padded_cells(ny, nx) scalars
+    shape: tuple[int, int]
+    walls: tuple[int, int, int, int]
 
 
-def pack_field(u: torch.Tensor, v: torch.Tensor, *, out: torch.Tensor | None = None,
-               stream=None) -> PackedField:
+def pack_field(u: torch.Tensor, v: torch.Tensor, *, boundaries="closed", stream=None) -> PackedField:
     """Build the packed field from two planar components (one streaming kernel)."""
     _check_image("u", u)
     _check_image("v", v, u)
     sfx, _, _ = _kind(u)
-    uv = torch.empty((*u.shape, 4), dtype=u.dtype, device=u.device) if out is None else out
+    walls = _walls(boundaries)
+    ny, nx = u.shape
+    data = torch.empty(4 * _core.padded_cells(ny, nx), dtype=u.dtype, device=u.device)
     with torch.cuda.device(u.device):
         rc = getattr(_core.lib, f"rlic_b200_pack_field_{sfx}")(
-            u.data_ptr(), v.data_ptr(), u.numel(), uv.data_ptr(), _stream_handle(stream))
+            u.data_ptr(), v.data_ptr(), ny, nx, *walls, data.data_ptr(), _stream_handle(stream))
     _core.check(rc)
-    return PackedField(uv)
+    return PackedField(data, (ny, nx), walls)
 
 
 def convolve_device(texture: torch.Tensor, u: torch.Tensor | None = None, v: torch.Tensor | None = None,
                     *, kernel, field: PackedField | None = None, uv_mode: str = "velocity",
-                    boundaries="closed", iterations: int = 1,
-                    work: tuple[torch.Tensor, torch.Tensor] | None = None, stream=None) -> torch.Tensor:
-    """``rlic_b200.convolve`` for CUDA tensors; returns a new CUDA tensor.
+                    boundaries="closed", iterations: int = 1, out: torch.Tensor | None = None,
+                    stream=None) -> torch.Tensor:
+    """``rlic_b200.convolve`` for CUDA tensors; returns a new CUDA tensor (or ``out``).
 
-    Pass either planar ``u, v`` or a pre-packed ``field`` (saves the interleave
-    when the same field is reused).  ``work`` optionally supplies the two
-    texture-sized scratch tensors; the result is one of them.  Work is enqueued
-    on ``stream`` (default: torch's current stream) without synchronising.
+    Pass either planar ``u, v`` or a pre-packed ``field`` (saves the packing when
+    the same field is reused; it must have been packed with the same
+    ``boundaries``).  Work is enqueued on ``stream`` (default: torch's current
+    stream) without synchronising.
     """
     _check_image("texture", texture)
     sfx, real, np_dtype = _kind(texture)
@@ -111,24 +111,26 @@ def convolve_device(texture: torch.Tensor, u: torch.Tensor | None = None, v: tor
     mode = _core.mode_code(uv_mode)
     if iterations == 0:
         return texture.clone()
+    if out is None:
+        out = torch.empty_like(texture)
+    else:
+        _check_image("out", out, texture)
+    ny, nx = texture.shape
+    tap_ptr = taps.ctypes.data_as(ctypes.POINTER(real))
     with torch.cuda.device(texture.device):
         if field is None:
             if u is None or v is None:
                 raise TypeError("pass u and v, or field=")
             _check_image("u", u, texture)
             _check_image("v", v, texture)
-            field = pack_field(u, v, stream=stream)
-        elif field.shape != tuple(texture.shape) or field.uv.dtype != texture.dtype:
-            raise ValueError("field must match the texture's shape and dtype")
-        if work is None:
-            work = (torch.empty_like(texture), torch.empty_like(texture) if iterations > 1 else None)
-        w0, w1 = work
-        result = ctypes.c_void_p()
-        ny, nx = texture.shape
-        rc = getattr(_core.lib, f"rlic_b200_convolve_packed_{sfx}")(
-            texture.data_ptr(), field.uv.data_ptr(), ny, nx,
-            taps.ctypes.data_as(ctypes.POINTER(real)), taps.size, mode, *walls, int(iterations),
-            w0.data_ptr(), w1.data_ptr() if w1 is not None else None,
-            ctypes.byref(result), _stream_handle(stream))
+            rc = getattr(_core.lib, f"rlic_b200_convolve_device_{sfx}")(
+                texture.data_ptr(), u.data_ptr(), v.data_ptr(), ny, nx, tap_ptr, taps.size, mode,
+                *walls, int(iterations), out.data_ptr(), _stream_handle(stream))
+        else:
+            if field.shape != (ny, nx) or field.data.dtype != texture.dtype or field.walls != walls:
+                raise ValueError("field was packed for another shape, dtype or boundary kinds")
+            rc = getattr(_core.lib, f"rlic_b200_convolve_packed_{sfx}")(
+                texture.data_ptr(), field.data.data_ptr(), ny, nx, tap_ptr, taps.size, mode,
+                *walls, int(iterations), out.data_ptr(), _stream_handle(stream))
     _core.check(rc)
-    return w0 if result.value == w0.data_ptr() else w1
+    return out

@@ -10,17 +10,22 @@ gloo in the CPU tests).  Each iteration computes the two edge strips first,
 ships them to the neighbours on a side stream, and computes the interior rows
 while that exchange is in flight.
 
+Buffers are the kernels' padded buffers (``include/rlic_b200.h``): a pitch of
+``nx + 2`` cells and a guard row above and below; buffer row ``r`` together
+with its two wall cells is the contiguous cell range
+``[(r + 1) * pitch - 1, (r + 2) * pitch - 1)``, which is what travels.
+
 The per-pixel arithmetic is the single-GPU kernel's, in global row numbers, so
 the gathered result is bit-identical to an unsharded run.
 
-The compute step is injectable (``pass_fn``) so the exchange logic can be
-exercised without a GPU; the default is the CUDA slab pass of the C ABI.  There
+The compute steps are injectable (``ops``) so the exchange logic can be
+exercised without a GPU; the default is the CUDA slab API of the C ABI.  There
 is no CPU compute path in this package.
 """
 
 from __future__ import annotations
 
-__all__ = ["SlabPlan", "ShardedConvolver"]
+__all__ = ["SlabPlan", "ShardedConvolver", "CudaSlabOps"]
 
 import ctypes
 from dataclasses import dataclass
@@ -84,6 +89,23 @@ class SlabPlan:
     def rows_alloc(self) -> int:
         return self.halo_lo + self.nrows + self.halo_hi
 
+    @property
+    def pitch(self) -> int:
+        return self.nx + 2
+
+    @property
+    def cells(self) -> int:
+        """Cells of one padded buffer (include/rlic_b200.h: rlic_b200_padded_cells)."""
+        return (self.rows_alloc + 2) * self.pitch
+
+    def row_cells(self, a: int, b: int) -> slice:
+        """Cell range of buffer rows [a, b) with their wall cells."""
+        return slice((a + 1) * self.pitch - 1, (b + 1) * self.pitch - 1)
+
+    @property
+    def slab_args(self) -> tuple[int, int, int, int, int, int]:
+        return (self.ny, self.nx, self.row0, self.nrows, self.halo_lo, self.halo_hi)
+
     def validate(self) -> None:
         if self.world < 1 or not (0 <= self.rank < self.world):
             raise ValueError(f"bad rank {self.rank} of {self.world}")
@@ -97,27 +119,63 @@ class SlabPlan:
                 )
 
 
-def _cuda_pass(tex, uv, out, plan: SlabPlan, row0, nrows, halo_lo, halo_hi, taps, mode, walls):
-    """One CUDA pass over rows [row0, row0+nrows) of the global image."""
-    from rlic_b200 import _core
+class CudaSlabOps:
+    """The slab building blocks of the C ABI, on torch CUDA tensors."""
 
-    sfx, real = ("f32", ctypes.c_float) if tex.dtype == torch.float32 else ("f64", ctypes.c_double)
-    rc = getattr(_core.lib, f"rlic_b200_pass_slab_{sfx}")(
-        tex.data_ptr(), uv.data_ptr(), out.data_ptr(), plan.ny, plan.nx, row0, nrows, halo_lo,
-        halo_hi, taps.ctypes.data_as(ctypes.POINTER(real)), taps.size, mode, *walls,
-        int(torch.cuda.current_stream().cuda_stream))
-    _core.check(rc)
+    @staticmethod
+    def _kind(t):
+        return ("f32", ctypes.c_float) if t.dtype == torch.float32 else ("f64", ctypes.c_double)
+
+    @staticmethod
+    def _stream():
+        return int(torch.cuda.current_stream().cuda_stream)
+
+    @staticmethod
+    def _need_cuda(t):
+        if not t.is_cuda:
+            raise RuntimeError("rlic_b200 has no CPU fallback: pass CUDA tensors")
+
+    def pack_field(self, u, v, field, plan, walls):
+        from rlic_b200 import _core
+
+        self._need_cuda(u)
+        sfx, _ = self._kind(u)
+        _core.check(getattr(_core.lib, f"rlic_b200_slab_pack_field_{sfx}")(
+            u.data_ptr(), v.data_ptr(), *plan.slab_args, *walls, field.data_ptr(), self._stream()))
+
+    def pad_texture(self, texture, padded, plan, walls):
+        from rlic_b200 import _core
+
+        self._need_cuda(texture)
+        sfx, _ = self._kind(texture)
+        _core.check(getattr(_core.lib, f"rlic_b200_slab_pad_texture_{sfx}")(
+            texture.data_ptr(), *plan.slab_args, *walls, padded.data_ptr(), self._stream()))
+
+    def unpad_texture(self, padded, texture, plan, walls):
+        from rlic_b200 import _core
+
+        sfx, _ = self._kind(texture)
+        _core.check(getattr(_core.lib, f"rlic_b200_slab_unpad_texture_{sfx}")(
+            padded.data_ptr(), *plan.slab_args, *walls, texture.data_ptr(), self._stream()))
+
+    def pass_rows(self, src, field, dst, plan, a, b, taps, mode, walls):
+        from rlic_b200 import _core
+
+        sfx, real = self._kind(src)
+        _core.check(getattr(_core.lib, f"rlic_b200_pass_slab_{sfx}")(
+            src.data_ptr(), field.data_ptr(), dst.data_ptr(), *plan.slab_args, a, b - a,
+            taps.ctypes.data_as(ctypes.POINTER(real)), taps.size, mode, *walls, self._stream()))
 
 
 class ShardedConvolver:
     """Holds one rank's slab of a sharded image and runs ``convolve`` on it.
 
-    ``texture``, ``u``, ``v``: this rank's rows ``[plan.row0, plan.row1)`` (no halos),
-    tensors on the rank's device.
+    ``texture``, ``u``, ``v``: this rank's rows ``[plan.row0, plan.row1)`` (dense,
+    no halos), tensors on the rank's device.
     """
 
     def __init__(self, ny: int, nx: int, *, kernel, uv_mode: str = "velocity",
-                 boundaries="closed", group=None, pass_fn=None, pack_fn=None):
+                 boundaries="closed", group=None, ops=None):
         from rlic_b200 import _core   # enum tables only; no computation
 
         self.group = group
@@ -135,14 +193,14 @@ class ShardedConvolver:
         self.plan = SlabPlan(ny=ny, nx=nx, world=self.world, rank=self.rank,
                              reach=self.taps.size // 2, periodic_y=bs.y[0] == "periodic")
         self.plan.validate()
-        self._pass = pass_fn or _cuda_pass
-        self._pack = pack_fn
-        self.uv = None
+        self.ops = ops or CudaSlabOps()
+        self.field = None
         self.comm_stream = None
 
     # -- halo plumbing ------------------------------------------------------
-    def _exchange(self, buf: torch.Tensor, async_op: bool = False):
-        """Fill the halo rows of ``buf`` (rows_alloc x ...) from the neighbours.
+    def _exchange(self, buf: torch.Tensor, width: int = 1) -> None:
+        """Fill the halo rows of the flat padded buffer ``buf`` (``width`` scalars
+        per cell) from the neighbours.
 
         Every rank posts: send top rows up, send bottom rows down, receive the
         high halo from below, receive the low halo from above.  That order
@@ -151,74 +209,55 @@ class ShardedConvolver:
         """
         p = self.plan
         h, lo, n = p.reach, p.halo_lo, p.nrows
+
+        def rows(a, b):
+            s = p.row_cells(a, b)
+            return buf[s.start * width:s.stop * width]
+
         ops = []
         if p.up is not None:
-            ops.append(dist.P2POp(dist.isend, buf[lo:lo + h], p.up, self.group))
+            ops.append(dist.P2POp(dist.isend, rows(lo, lo + h), p.up, self.group))
         if p.down is not None:
-            ops.append(dist.P2POp(dist.isend, buf[lo + n - h:lo + n], p.down, self.group))
+            ops.append(dist.P2POp(dist.isend, rows(lo + n - h, lo + n), p.down, self.group))
         if p.down is not None:
-            ops.append(dist.P2POp(dist.irecv, buf[lo + n:lo + n + h], p.down, self.group))
+            ops.append(dist.P2POp(dist.irecv, rows(lo + n, lo + n + h), p.down, self.group))
         if p.up is not None:
-            ops.append(dist.P2POp(dist.irecv, buf[0:lo], p.up, self.group))
-        if not ops:
-            return []
-        reqs = dist.batch_isend_irecv(ops)
-        if not async_op:
-            for r in reqs:
-                r.wait()
-            return []
-        return reqs
+            ops.append(dist.P2POp(dist.irecv, rows(0, lo), p.up, self.group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
 
-    def _alloc(self, like: torch.Tensor, trailing=()) -> torch.Tensor:
-        p = self.plan
-        return torch.empty((p.rows_alloc, p.nx, *trailing), dtype=like.dtype, device=like.device)
+    def _alloc(self, like: torch.Tensor, width: int = 1) -> torch.Tensor:
+        # zero-filled: wall cells nobody can reach are never written
+        return torch.zeros(self.plan.cells * width, dtype=like.dtype, device=like.device)
 
     def set_field(self, u: torch.Tensor, v: torch.Tensor) -> None:
         """Pack (u, v) with halos; done once, the field does not change between passes."""
         p = self.plan
-        uv = self._alloc(u, (4,))
-        owned = uv[p.halo_lo:p.halo_lo + p.nrows]
-        if self._pack is not None:
-            self._pack(u, v, owned)
-        elif u.is_cuda:
-            from rlic_b200.device import pack_field
-
-            pack_field(u.contiguous(), v.contiguous(), out=owned)
-        else:
-            raise RuntimeError("rlic_b200 has no CPU fallback: pass CUDA tensors")
-        self._exchange(uv)
-        self.uv = uv
+        if tuple(u.shape) != (p.nrows, p.nx) or tuple(v.shape) != (p.nrows, p.nx):
+            raise ValueError(f"expected this rank's slab of shape {(p.nrows, p.nx)}")
+        field = self._alloc(u, 4)
+        self.ops.pack_field(u.contiguous(), v.contiguous(), field, p, self.walls)
+        self._exchange(field, 4)
+        self.field = field
 
     def _pass_rows(self, src, dst, a: int, b: int) -> None:
-        """Compute owned-relative rows [a, b) of ``dst`` from ``src`` (both with halos)."""
-        if b <= a:
-            return
-        p = self.plan
-        # rows of the buffers available around the strip
-        lo_avail = p.halo_lo + a
-        hi_avail = p.rows_alloc - (p.halo_lo + b)
-        closed_top = p.up is None and not p.periodic_y
-        closed_bottom = p.down is None and not p.periodic_y
-        halo_lo = lo_avail if not (closed_top and a == 0) else 0
-        halo_hi = hi_avail if not (closed_bottom and b == p.nrows) else 0
-        # a strip that starts at a closed image edge needs no halo there; any
-        # other side gets every row the buffer holds (>= reach by construction)
-        first = p.halo_lo + a - halo_lo
-        self._pass(src[first:], self.uv[first:], dst[p.halo_lo + a:], p, p.row0 + a, b - a,
-                   halo_lo, halo_hi, self.taps, self.mode, self.walls)
+        """Compute owned rows [a, b) of ``dst`` from ``src``."""
+        if b > a:
+            self.ops.pass_rows(src, self.field, dst, self.plan, a, b, self.taps, self.mode, self.walls)
 
     def convolve(self, texture: torch.Tensor, iterations: int = 1, overlap: bool = True) -> torch.Tensor:
         """Run ``iterations`` passes; returns this rank's rows of the result."""
-        if self.uv is None:
+        if self.field is None:
             raise RuntimeError("call set_field(u, v) first")
         p = self.plan
-        if texture.shape != (p.nrows, p.nx):
+        if tuple(texture.shape) != (p.nrows, p.nx):
             raise ValueError(f"expected this rank's slab of shape {(p.nrows, p.nx)}")
         if iterations <= 0:
             return texture.clone()
         src = self._alloc(texture)
         dst = self._alloc(texture)
-        src[p.halo_lo:p.halo_lo + p.nrows].copy_(texture)
+        self.ops.pad_texture(texture.contiguous(), src, p, self.walls)
         self._exchange(src)
         h = p.reach
         # strips first, interior while the strips travel: worth it only when
@@ -254,4 +293,6 @@ class ShardedConvolver:
                 self._pass_rows(src, dst, h, p.nrows - h)
                 main.wait_event(shipped)
             src, dst = dst, src
-        return src[p.halo_lo:p.halo_lo + p.nrows]
+        out = torch.empty_like(texture)
+        self.ops.unpad_texture(src, out, p, self.walls)
+        return out

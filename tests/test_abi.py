@@ -24,10 +24,11 @@ def declared_symbols() -> list[str]:
 
 def test_header_declares_the_expected_surface():
     names = declared_symbols()
-    for base in ("convolve", "convolve_checked", "convolve_device", "convolve_packed", "pack_field", "pass_slab", "convolve_batch"):
+    for base in ("convolve", "convolve_checked", "convolve_device", "convolve_packed", "pack_field",
+                 "pass_slab", "slab_pack_field", "slab_pad_texture", "slab_unpad_texture", "convolve_batch"):
         for sfx in ("f32", "f64"):
             assert f"rlic_b200_{base}_{sfx}" in names
-    for misc in ("abi_version", "last_error", "device_count", "launch_count", "set_device"):
+    for misc in ("abi_version", "last_error", "device_count", "launch_count", "set_device", "padded_cells"):
         assert f"rlic_b200_{misc}" in names
 
 

@@ -361,4 +361,5 @@ def test_launch_counter_counts_passes():
     tex, u, v, k = random_case((16, 16), np.float32, 5, seed=1, specials=False)
     before = _core.launch_count()
     rlic.convolve(tex, u, v, kernel=k, iterations=4)
-    assert _core.launch_count() - before == 4 + 1   # 4 passes + the field interleave
+    # 4 passes + field packing + texture padding + un-padding of the result
+    assert _core.launch_count() - before == 4 + 3

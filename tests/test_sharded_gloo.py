@@ -1,10 +1,11 @@
 """Row-slab sharding logic on CPU: world_size 2 and 3 over gloo.
 
-The halo plan, the message ordering and the strip/interior decomposition of
-``rlic_b200.sharded`` run for real; only the per-slab compute step is replaced by
-the CPU oracle (injected through ``pass_fn`` — test-only use of the oracle; the
-product default is the CUDA slab pass).  Buffers are poisoned outside the rows a
-rank legitimately holds, so a missing or misplaced halo shows up as a mismatch.
+The halo plan, the message ordering, the padded-buffer row ranges and the
+strip/interior decomposition of ``rlic_b200.sharded`` run for real; only the
+per-slab compute steps are replaced by the CPU oracle (injected through ``ops`` —
+test-only use of the oracle; the product default is the CUDA slab API).  Buffers
+are poisoned outside the rows a rank legitimately holds, so a missing or
+misplaced halo shows up as a mismatch.
 The sharded result must equal the unsharded oracle bit for bit.
 """
 
@@ -26,37 +27,103 @@ sys.path.insert(0, str(ROOT))
 WALL_NAMES = {0: "closed", 1: "periodic"}
 
 
-def oracle_slab_pass(tex, uv, out, plan, row0, nrows, halo_lo, halo_hi, taps, mode, walls):
-    """CPU stand-in for rlic_b200_pass_slab_*: same contract, computed by the oracle."""
-    import oracle
+class OracleSlabOps:
+    """CPU stand-in for the slab building blocks of the C ABI (rlic_b200_slab_* and
+    rlic_b200_pass_slab_*): same contract on the same padded buffers, computed by the
+    oracle.  Buffers are poisoned (NaN / huge) wherever a rank legitimately holds
+    nothing, and the wall cells of every row a pass may read are checked, so a
+    missing, misplaced or truncated halo message shows up as a failure."""
 
-    ny, nx = plan.ny, plan.nx
-    tex, uv = tex.numpy(), uv.numpy()
-    rows_alloc = halo_lo + nrows + halo_hi
-    periodic_y = walls[2] == 1
-    g_tex = np.full((ny, nx), np.nan, dtype=tex.dtype)        # poison: unread rows stay NaN
-    g_u = np.full((ny, nx), 1e30, dtype=tex.dtype)
-    g_v = np.full((ny, nx), -1e30, dtype=tex.dtype)
-    for k in range(rows_alloc):
-        g = row0 - halo_lo + k
-        if periodic_y:
-            g %= ny
-        elif not (0 <= g < ny):
-            raise AssertionError("buffer row outside a closed image")
-        g_tex[g] = tex[k]
-        g_u[g] = uv[k, :, 0]
-        g_v[g] = uv[k, :, 1]
-    bnd = ((WALL_NAMES[walls[0]], WALL_NAMES[walls[1]]), (WALL_NAMES[walls[2]], WALL_NAMES[walls[3]]))
-    band = oracle.pass_rows(g_tex, g_u, g_v, kernel=taps, rows=(row0, row0 + nrows),
-                            uv_mode="polarization" if mode else "velocity", boundaries=bnd)
-    out[:nrows].copy_(torch.from_numpy(band))
+    @staticmethod
+    def _walls(plan, walls):
+        ny, nx = plan.ny, plan.nx
+        periodic_y = walls[2] == 1
+        shift = plan.row0 - plan.halo_lo
+        return dict(
+            j_below_to=nx - 1 if walls[0] == 1 else 0,
+            j_above_to=0 if walls[1] == 1 else nx - 1,
+            i_below_to=(ny - 1 if walls[2] == 1 else 0) - shift,
+            i_above_to=(0 if walls[3] == 1 else ny - 1) - shift,
+            lo_wall=plan.world == 1 or (plan.row0 == 0 and not periodic_y),
+            hi_wall=plan.world == 1 or (plan.row1 == ny and not periodic_y),
+        )
 
+    @staticmethod
+    def _cell(plan, r, c):
+        """flat cell index of buffer row r, column c (c = -1 .. nx are the wall cells)"""
+        return (r + 1) * plan.pitch + c
 
-def cpu_pack(u, v, owned):
-    # the product's packed record is (u, v, ru, rv); the stand-in only needs u, v
-    owned[..., 0] = u
-    owned[..., 1] = v
-    owned[..., 2:] = 0
+    def _write_rows(self, flat, plan, walls, rows, values):
+        """values: dict row -> 1-D array of nx pixels; writes pixels and their wall cells"""
+        w = self._walls(plan, walls)
+        for r, line in values.items():
+            base = self._cell(plan, r, 0)
+            flat[base:base + plan.nx] = torch.from_numpy(np.ascontiguousarray(line))
+            flat[self._cell(plan, r, plan.nx)] = float(line[w["j_above_to"]])
+            flat[self._cell(plan, r, -1)] = float(line[w["j_below_to"]])
+            if w["lo_wall"] and r == w["i_below_to"]:
+                g = self._cell(plan, -1, 0)
+                flat[g:g + plan.nx] = torch.from_numpy(np.ascontiguousarray(line))
+            if w["hi_wall"] and r == w["i_above_to"]:
+                g = self._cell(plan, plan.rows_alloc, 0)
+                flat[g:g + plan.nx] = torch.from_numpy(np.ascontiguousarray(line))
+
+    def pack_field(self, u, v, field, plan, walls):
+        field[:] = float("nan")
+        f = field.view(-1, 4)
+        for k in range(plan.nrows):
+            r = plan.halo_lo + k
+            base = self._cell(plan, r, 0)
+            f[base:base + plan.nx, 0] = u[k]
+            f[base:base + plan.nx, 1] = v[k]
+            f[base:base + plan.nx, 2:] = 0
+            # stand-in sentinels: tag the wall cells of owned rows so that their transport can be checked
+            f[self._cell(plan, r, plan.nx), :] = 12345.0
+            f[self._cell(plan, r, -1), :] = 54321.0
+
+    def pad_texture(self, texture, padded, plan, walls):
+        padded[:] = float("nan")
+        tex = texture.numpy()
+        self._write_rows(padded, plan, walls, None,
+                         {plan.halo_lo + k: tex[k] for k in range(plan.nrows)})
+
+    def unpad_texture(self, padded, texture, plan, walls):
+        for k in range(plan.nrows):
+            base = self._cell(plan, plan.halo_lo + k, 0)
+            texture[k] = padded[base:base + plan.nx]
+
+    def pass_rows(self, src, field, dst, plan, a, b, taps, mode, walls):
+        import oracle
+
+        ny, nx = plan.ny, plan.nx
+        w = self._walls(plan, walls)
+        periodic_y = walls[2] == 1
+        f = field.view(-1, 4).numpy()
+        s = src.numpy()
+        g_tex = np.full((ny, nx), np.nan, dtype=s.dtype)        # poison: unread rows stay NaN
+        g_u = np.full((ny, nx), 1e30, dtype=s.dtype)
+        g_v = np.full((ny, nx), -1e30, dtype=s.dtype)
+        reach = taps.size // 2
+        lo = max(0, plan.halo_lo + a - reach)
+        hi = min(plan.rows_alloc, plan.halo_lo + b + reach)
+        for r in range(lo, hi):                                   # rows this pass may read
+            g = plan.row0 - plan.halo_lo + r
+            if periodic_y:
+                g %= ny
+            assert 0 <= g < ny, "buffer row outside a closed image"
+            base = self._cell(plan, r, 0)
+            g_tex[g] = s[base:base + nx]
+            g_u[g] = f[base:base + nx, 0]
+            g_v[g] = f[base:base + nx, 1]
+            # the wall cells must have travelled with their rows
+            assert s[self._cell(plan, r, nx)] == g_tex[g][w["j_above_to"]] or np.isnan(g_tex[g][w["j_above_to"]])
+            assert s[self._cell(plan, r, -1)] == g_tex[g][w["j_below_to"]] or np.isnan(g_tex[g][w["j_below_to"]])
+            assert f[self._cell(plan, r, nx), 0] == 12345.0 and f[self._cell(plan, r, -1), 0] == 54321.0
+        bnd = ((WALL_NAMES[walls[0]], WALL_NAMES[walls[1]]), (WALL_NAMES[walls[2]], WALL_NAMES[walls[3]]))
+        band = oracle.pass_rows(g_tex, g_u, g_v, kernel=taps, rows=(plan.row0 + a, plan.row0 + b),
+                                uv_mode="polarization" if mode else "velocity", boundaries=bnd)
+        self._write_rows(dst, plan, walls, None,
+                         {plan.halo_lo + a + k: band[k] for k in range(b - a)})
 
 
 def _worker(rank, world, port, case, queue):
@@ -77,7 +144,7 @@ def _worker(rank, world, port, case, queue):
         kernel = (rng.random(klen) + 0.1).astype(dtype)
 
         sc = ShardedConvolver(ny, nx, kernel=kernel, uv_mode=mode, boundaries=boundaries,
-                              pass_fn=oracle_slab_pass, pack_fn=cpu_pack)
+                              ops=OracleSlabOps())
         p = sc.plan
         assert (p.row0, p.row1) == (ny * rank // world, ny * (rank + 1) // world)
         mine = slice(p.row0, p.row1)
@@ -146,6 +213,8 @@ def test_plan_geometry():
     assert [p.up for p in ring] == [3, 0, 1, 2]
     assert [p.down for p in ring] == [1, 2, 3, 0]
     assert all(p.rows_alloc == 35 for p in ring)
+    assert ring[0].pitch == 10 and ring[0].cells == 37 * 10
+    assert ring[0].row_cells(0, 5) == slice(9, 59)      # rows 0..4 with their wall cells
     single = SlabPlan(ny=10, nx=8, world=1, rank=0, reach=5, periodic_y=True)
     assert single.up is None and single.down is None and single.rows_alloc == 10
 

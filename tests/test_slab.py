@@ -25,35 +25,69 @@ ROOT = Path(__file__).resolve().parent.parent
 
 
 def slab_pass_all(tex, u, v, kernel, bounds_spec, walls, mode, cuts):
+    """Cut the image into slabs, give every slab its halos by plain copies of padded
+    rows (ring order when y is periodic), run one slab pass each, stitch."""
     import torch
-
-    from rlic_b200.device import pack_field
 
     dev = torch.device("cuda", 0)
     ny, nx = tex.shape
+    P = nx + 2
     h = kernel.size // 2
     periodic_y = bounds_spec[1][0] == "periodic"
-    t_tex = torch.from_numpy(tex).to(dev)
-    field = pack_field(torch.from_numpy(np.ascontiguousarray(u)).to(dev),
-                       torch.from_numpy(np.ascontiguousarray(v)).to(dev)).uv
     sfx, real = ("f32", ctypes.c_float) if tex.dtype == np.float32 else ("f64", ctypes.c_double)
-    out = torch.empty_like(t_tex)
+    stream = lambda: int(torch.cuda.current_stream().cuda_stream)  # noqa: E731
+    lib = _core.lib
     edges = [0, *cuts, ny]
+    slabs = []
     for r0, r1 in zip(edges[:-1], edges[1:]):
         lo = h if (r0 > 0 or periodic_y) else 0
         hi = h if (r1 < ny or periodic_y) else 0
-        rows = (torch.arange(r0 - lo, r1 + hi, device=dev)) % ny   # ring order when wrapping
-        s_tex = t_tex[rows].contiguous()
-        s_field = field[rows].contiguous()
-        s_out = torch.empty((r1 - r0, nx), dtype=t_tex.dtype, device=dev)
-        rc = getattr(_core.lib, f"rlic_b200_pass_slab_{sfx}")(
-            s_tex.data_ptr(), s_field.data_ptr(), s_out.data_ptr(), ny, nx, r0, r1 - r0, lo, hi,
-            kernel.ctypes.data_as(ctypes.POINTER(real)), kernel.size, mode, *walls,
-            int(torch.cuda.current_stream().cuda_stream))
-        _core.check(rc)
-        out[r0:r1] = s_out
-    torch.cuda.synchronize()
-    return out.cpu().numpy()
+        args = (ny, nx, r0, r1 - r0, lo, hi)
+        cells = _core.padded_cells(lo + (r1 - r0) + hi, nx)
+        t_pad = torch.full((cells,), float("nan"), dtype=torch.from_numpy(tex).dtype, device=dev)
+        f_pad = torch.full((4 * cells,), float("nan"), dtype=t_pad.dtype, device=dev)
+        d_tex = torch.from_numpy(np.ascontiguousarray(tex[r0:r1])).to(dev)
+        d_u = torch.from_numpy(np.ascontiguousarray(u[r0:r1])).to(dev)
+        d_v = torch.from_numpy(np.ascontiguousarray(v[r0:r1])).to(dev)
+        _core.check(getattr(lib, f"rlic_b200_slab_pad_texture_{sfx}")(
+            d_tex.data_ptr(), *args, *walls, t_pad.data_ptr(), stream()))
+        _core.check(getattr(lib, f"rlic_b200_slab_pack_field_{sfx}")(
+            d_u.data_ptr(), d_v.data_ptr(), *args, *walls, f_pad.data_ptr(), stream()))
+        slabs.append(dict(r0=r0, r1=r1, lo=lo, hi=hi, args=args, tex=t_pad, field=f_pad))
+
+    def rows(s, buf, a, b, width):       # padded rows [a, b) of a slab buffer, with wall cells
+        return buf[((a + 1) * P - 1) * width:((b + 1) * P - 1) * width]
+
+    def owner(g):                         # slab and buffer row holding global row g
+        g %= ny
+        for s in slabs:
+            if s["r0"] <= g < s["r1"]:
+                return s, s["lo"] + g - s["r0"]
+        raise AssertionError
+
+    # halos, one global row at a time (a test, not a fast path)
+    for s in slabs:
+        wanted = list(range(s["r0"] - s["lo"], s["r0"])) + list(range(s["r1"], s["r1"] + s["hi"]))
+        for k, g in enumerate(wanted):
+            brow = k if k < s["lo"] else s["lo"] + (s["r1"] - s["r0"]) + (k - s["lo"])
+            src, srow = owner(g)
+            rows(s, s["tex"], brow, brow + 1, 1).copy_(rows(src, src["tex"], srow, srow + 1, 1))
+            rows(s, s["field"], brow, brow + 1, 4).copy_(rows(src, src["field"], srow, srow + 1, 4))
+
+    out = np.empty_like(tex)
+    for s in slabs:
+        n = s["r1"] - s["r0"]
+        o_pad = torch.zeros_like(s["tex"])
+        # two sub-ranges, as the overlapped multi-GPU driver issues them
+        for a, b in ((0, n // 3), (n // 3, n)):
+            _core.check(getattr(lib, f"rlic_b200_pass_slab_{sfx}")(
+                s["tex"].data_ptr(), s["field"].data_ptr(), o_pad.data_ptr(), *s["args"], a, b - a,
+                kernel.ctypes.data_as(ctypes.POINTER(real)), kernel.size, mode, *walls, stream()))
+        d_out = torch.empty((n, nx), dtype=o_pad.dtype, device=dev)
+        _core.check(getattr(lib, f"rlic_b200_slab_unpad_texture_{sfx}")(
+            o_pad.data_ptr(), *s["args"], *walls, d_out.data_ptr(), stream()))
+        out[s["r0"]:s["r1"]] = d_out.cpu().numpy()
+    return out
 
 
 CASES = {
@@ -85,16 +119,41 @@ def test_halo_shorter_than_the_reach_is_refused():
     import torch
 
     dev = torch.device("cuda", 0)
-    t = torch.zeros((40, 16), device=dev)
-    f = torch.zeros((40, 16, 4), device=dev)
-    o = torch.zeros((20, 16), device=dev)
+    cells = _core.padded_cells(40, 16)
+    t = torch.zeros(cells, device=dev)
+    f = torch.zeros(4 * cells, device=dev)
+    o = torch.zeros(cells, device=dev)
     k = np.ones(33, dtype=np.float32)
     rc = _core.lib.rlic_b200_pass_slab_f32(
-        t.data_ptr(), f.data_ptr(), o.data_ptr(), 100, 16, 30, 20, 10, 10,
+        t.data_ptr(), f.data_ptr(), o.data_ptr(), 100, 16, 30, 20, 10, 10, 0, 20,
         k.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), k.size, 0, 0, 0, 0, 0, None)
     assert rc == _core.ESHARD
     with pytest.raises(ValueError, match="halo"):
         _core.check(rc)
+
+
+def test_packed_field_reuse_and_out_argument():
+    import torch
+
+    import rlic_b200
+    from rlic_b200.device import convolve_device, pack_field
+
+    rng = np.random.default_rng(6)
+    tex = rng.random((90, 130))
+    u = rng.random((90, 130)) - 0.5
+    v = rng.random((90, 130)) - 0.5
+    k = np.linspace(0, 1, 15)
+    bnd = {"x": "periodic", "y": "closed"}
+    want = rlic_b200.convolve(tex, u, v, kernel=k, iterations=2, boundaries=bnd, uv_mode="polarization")
+    d = [torch.from_numpy(a).cuda() for a in (tex, u, v)]
+    field = pack_field(d[1], d[2], boundaries=bnd)
+    out = torch.empty_like(d[0])
+    got = convolve_device(d[0], field=field, kernel=k, iterations=2, boundaries=bnd,
+                          uv_mode="polarization", out=out)
+    assert got is out
+    np.testing.assert_array_equal(out.cpu().numpy(), want)
+    with pytest.raises(ValueError, match="packed for another"):
+        convolve_device(d[0], field=field, kernel=k, boundaries="closed")
 
 
 def test_device_entry_point_matches_host_entry_point():

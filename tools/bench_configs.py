@@ -37,17 +37,17 @@ def time_device(w, reps=5):
     tex = torch.from_numpy(np.ascontiguousarray(w.texture)).to(dev)
     u = torch.from_numpy(np.ascontiguousarray(w.u)).to(dev)
     v = torch.from_numpy(np.ascontiguousarray(w.v)).to(dev)
-    field = pack_field(u, v)
+    field = pack_field(u, v, boundaries=w.boundaries)
     del u, v
-    work = (torch.empty_like(tex), torch.empty_like(tex))
+    out = torch.empty_like(tex)
     kw = dict(kernel=w.kernel, uv_mode=w.uv_mode, boundaries=w.boundaries, iterations=w.iterations)
     for _ in range(2):
-        convolve_device(tex, field=field, work=work, **kw)
+        convolve_device(tex, field=field, out=out, **kw)
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(reps):
-        convolve_device(tex, field=field, work=work, **kw)
+        convolve_device(tex, field=field, out=out, **kw)
     b.record()
     torch.cuda.synchronize()
     return a.elapsed_time(b) / reps
