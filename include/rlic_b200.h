@@ -122,6 +122,18 @@ int rlic_b200_convolve_checked_f64(const double *texture, const double *u, const
                                    int64_t iterations, double *out,
                                    int *texture_has_negative);
 
+/*
+ * Page-locked host blocks for results.  `out` of the host entry points may be
+ * any host memory; a binding that has to return a freshly allocated array (as
+ * rlic.convolve does, src/lib.rs:442) can take the array's storage from here
+ * instead of from the heap: the download then needs neither page faults nor the
+ * driver's bounce buffer.  Blocks are cached and reused; at most 4 GiB are held
+ * (cached + handed out), beyond which rlic_b200_result_alloc returns NULL and
+ * the caller uses ordinary memory.  Also NULL without a CUDA device.
+ */
+void *rlic_b200_result_alloc(int64_t bytes);
+void rlic_b200_result_free(void *block);
+
 /* Device used by the host entry points on the calling thread. */
 int rlic_b200_set_device(int device);
 

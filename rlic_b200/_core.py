@@ -76,6 +76,10 @@ def _load() -> ctypes.CDLL:
     cdll.rlic_b200_launch_count.restype = _i64
     cdll.rlic_b200_padded_cells.argtypes = [_i64, _i64]
     cdll.rlic_b200_padded_cells.restype = _i64
+    cdll.rlic_b200_result_alloc.argtypes = [_i64]
+    cdll.rlic_b200_result_alloc.restype = _vp
+    cdll.rlic_b200_result_free.argtypes = [_vp]
+    cdll.rlic_b200_result_free.restype = None
     cdll.rlic_b200_set_device.argtypes = [_int]
     cdll.rlic_b200_set_device.restype = _int
     for sfx, real in (("f32", ctypes.c_float), ("f64", ctypes.c_double)):
@@ -140,6 +144,41 @@ def mode_code(uv_mode: str) -> int:
         raise ValueError(f"unknown uv_mode {uv_mode!r}") from None
 
 
+class _ResultBlock:
+    """Page-locked storage of one result array; returns to the library's pool when the
+    last array viewing it is garbage collected."""
+
+    __slots__ = ("ptr", "nbytes", "__weakref__")
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.ptr, self.nbytes = ptr, nbytes
+
+    @property
+    def __array_interface__(self):
+        return {"shape": (self.nbytes,), "typestr": "|u1", "data": (self.ptr, False), "version": 3}
+
+    def __del__(self):
+        try:
+            lib.rlic_b200_result_free(self.ptr)
+        except Exception:   # interpreter shutdown
+            pass
+
+
+# results at least this large are placed in page-locked memory (faster download)
+_PINNED_RESULT_MIN_BYTES = 1 << 20
+
+
+def new_result(shape, dtype) -> np.ndarray:
+    """A freshly allocated, writable, C-contiguous array for a result."""
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+    if nbytes >= _PINNED_RESULT_MIN_BYTES:
+        ptr = lib.rlic_b200_result_alloc(nbytes)
+        if ptr:
+            return np.asarray(_ResultBlock(ptr, nbytes)).view(dtype).reshape(shape)
+    return np.empty(shape, dtype=dtype)
+
+
 def _as_image(name: str, arr, dtype: np.dtype, ndim: int) -> np.ndarray:
     # the PyO3 signature rejects anything but an ndarray of the right dtype/rank
     if not isinstance(arr, np.ndarray) or arr.dtype != dtype or arr.ndim != ndim:
@@ -164,7 +203,7 @@ def _convolve(sfx: str, real, texture, uv, kernel, boundaries, iterations, check
     if u.shape != texture.shape or v.shape != texture.shape:
         raise ValueError("texture, u and v must have identical shapes")
     ny, nx = texture.shape
-    out = np.empty((ny, nx), dtype=dtype)
+    out = new_result((ny, nx), dtype)
     p = ctypes.POINTER(real)
     args = [
         texture.ctypes.data_as(p),
@@ -208,7 +247,7 @@ def convolve_batch(textures, uv, kernel, boundaries, iterations=1, devices=None)
     if u.shape != textures.shape or v.shape != textures.shape:
         raise ValueError("textures, u and v must have identical shapes")
     nf, ny, nx = textures.shape
-    out = np.empty_like(textures)
+    out = new_result(textures.shape, dtype)
     p = ctypes.POINTER(real)
     dev_arr, ndev = None, 0
     if devices is not None:

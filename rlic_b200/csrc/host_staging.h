@@ -238,4 +238,69 @@ cudaError_t upload(const HostToDevice *jobs, int njobs, cudaStream_t stream)
     return (cudaError_t)failed.load();
 }
 
+// ---------------------------------------------------------------------------
+// Page-locked result buffers.  A fresh NumPy result has no physical pages and is
+// pageable: faulting it in and letting the driver bounce the download through
+// its own staging costs ~4 ms per 64 MiB.  The Python binding may instead ask
+// for a page-locked block, wrap it in the ndarray it returns, and give it back
+// when that array is garbage collected.  Blocks are cached by size class and the
+// total (cached + handed out) is capped; past the cap the caller falls back to
+// ordinary memory.
+class ResultBlocks {
+public:
+    static constexpr size_t kCap = (size_t)4 << 30;   // bytes of page-locked memory this pool may hold
+    void *acquire(size_t bytes)
+    {
+        const size_t cls = size_class(bytes);
+        std::lock_guard<std::mutex> lk(mu_);
+        for (size_t i = 0; i < free_.size(); ++i)
+            if (free_[i].second == cls) {
+                void *p = free_[i].first;
+                free_.erase(free_.begin() + (long)i);
+                return p;
+            }
+        // make room by dropping cached blocks of other sizes, oldest first
+        while (total_ + cls > kCap && !free_.empty()) {
+            cudaFreeHost(free_.front().first);
+            total_ -= free_.front().second;
+            free_.erase(free_.begin());
+        }
+        if (total_ + cls > kCap)
+            return nullptr;
+        void *p = nullptr;
+        if (cudaHostAlloc(&p, cls, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        total_ += cls;
+        sizes_.push_back({p, cls});
+        return p;
+    }
+    void release(void *p)
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        for (auto &e : sizes_)
+            if (e.first == p) {
+                free_.push_back(e);
+                return;
+            }
+    }
+
+private:
+    static size_t size_class(size_t bytes)
+    {
+        const size_t mib = (size_t)1 << 20;
+        return std::max(mib, (bytes + mib - 1) / mib * mib);
+    }
+    std::mutex mu_;
+    std::vector<std::pair<void *, size_t>> free_, sizes_;
+    size_t total_ = 0;
+};
+
+ResultBlocks &result_blocks()
+{
+    static ResultBlocks *r = new ResultBlocks;
+    return *r;
+}
+
 }  // namespace

@@ -436,8 +436,9 @@ int convolve_host(const T *tex, const T *u, const T *v, int64_t nfields, int64_t
     }
 
     // ---- downloads, trailing behind the last pass ----
-    // the passes are running: get the destination's pages ready meanwhile
-    prefault_for_write(out, bytes);
+    // the passes are running: get a pageable destination's pages ready meanwhile
+    if (is_pageable(out))
+        prefault_for_write(out, bytes);
     for (int64_t b = 0; b < nbands; ++b) {
         const int64_t rb = band_begin(b), re = band_begin(b + 1);
         const size_t off = (size_t)rb * (size_t)nx * (size_t)nfields;
@@ -727,6 +728,19 @@ int rlic_b200_device_count(void)
 int64_t rlic_b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int64_t rlic_b200_padded_cells(int64_t rows, int64_t nx) { return rlic::padded_cells(rows, nx); }
+
+void *rlic_b200_result_alloc(int64_t bytes)
+{
+    if (bytes <= 0 || rlic_b200_device_count() == 0)
+        return nullptr;
+    return result_blocks().acquire((size_t)bytes);
+}
+
+void rlic_b200_result_free(void *block)
+{
+    if (block)
+        result_blocks().release(block);
+}
 
 void rlic_b200_debug_force_wide_index(int on) { g_force_wide.store(on ? 1 : 0); }
 

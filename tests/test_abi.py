@@ -28,7 +28,8 @@ def test_header_declares_the_expected_surface():
                  "pass_slab", "slab_pack_field", "slab_pad_texture", "slab_unpad_texture", "convolve_batch"):
         for sfx in ("f32", "f64"):
             assert f"rlic_b200_{base}_{sfx}" in names
-    for misc in ("abi_version", "last_error", "device_count", "launch_count", "set_device", "padded_cells"):
+    for misc in ("abi_version", "last_error", "device_count", "launch_count", "set_device", "padded_cells",
+                 "result_alloc", "result_free"):
         assert f"rlic_b200_{misc}" in names
 
 
@@ -99,6 +100,27 @@ def test_without_a_gpu_the_product_fails_loudly():
     img = np.random.default_rng(0).random((8, 8))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         rlic_b200.convolve(img, img, img, kernel=np.ones(3))
+
+
+def test_result_blocks_fall_back_without_a_device_and_recycle_with_one():
+    import gc
+
+    a = _core.new_result((600, 700), np.float32)     # 1.6 MB: above the pinned threshold
+    assert a.shape == (600, 700) and a.dtype == np.float32 and a.flags.c_contiguous and a.flags.writeable
+    a[:] = 3.0
+    assert float(a.sum()) == 3.0 * 600 * 700
+    if _core.device_count() == 0:
+        assert a.flags.owndata                       # ordinary memory: the pool is unavailable
+        return
+    ptr = a.ctypes.data
+    view = a[10:20]                                  # views keep the block alive
+    del a
+    gc.collect()
+    assert view[0, 0] == 3.0
+    del view
+    gc.collect()
+    b = _core.new_result((600, 700), np.float32)     # same size class: the block comes back
+    assert b.ctypes.data == ptr
 
 
 def test_product_never_imports_the_oracle():
