@@ -25,16 +25,23 @@ using rlic::Fp;
 using rlic::PackedField;
 using rlic::PassGeom;
 
+static int g_split_field = 0;   // 1: BASELINE config 3's field (u = -1 | +1 split at mid-width, v = 0)
+
 template <typename T>
-__global__ void fill_inputs(T *tex, T *u, T *v, int n)
+__global__ void fill_inputs(T *tex, T *u, T *v, int n, int split)
 {
     long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= (long long)n * n) return;
     int i = (int)(p / n), j = (int)(p % n);
     unsigned h = (unsigned)p * 2654435761u; h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
     tex[p] = (T)((h >> 8) * (1.0 / 16777216.0));
-    u[p] = (T)(-(-1.0 + 2.0 * i / (n - 1)));
-    v[p] = (T)(-1.0 + 2.0 * j / (n - 1));
+    if (split) {
+        u[p] = j < n / 2 ? (T)-1 : (T)1;
+        v[p] = (T)0;
+    } else {
+        u[p] = (T)(-(-1.0 + 2.0 * i / (n - 1)));
+        v[p] = (T)(-1.0 + 2.0 * j / (n - 1));
+    }
 }
 
 // div_tail against IEEE division on the ranges the fast path admits:
@@ -112,7 +119,7 @@ void run_type(const char *tname, int n, int L, const char *only)
     CK(cudaMalloc(&ptex, cells * sizeof(T))); CK(cudaMalloc(&ref, cells * sizeof(T)));
     CK(cudaMalloc(&out, cells * sizeof(T)));
     CK(cudaMalloc(&field, cells * sizeof(PackedField<T>)));
-    fill_inputs<T><<<(unsigned)((count + 255) / 256), 256>>>(tex, u, v, n);
+    fill_inputs<T><<<(unsigned)((count + 255) / 256), 256>>>(tex, u, v, n, g_split_field);
     rlic::pack_field_kernel<T><<<148 * 16, 256>>>(u, v, field, g, 0, n, 1);
     rlic::pad_texture_kernel<T><<<148 * 16, 256>>>(tex, ptex, g, 0, n, 1, nullptr);
     CK(cudaDeviceSynchronize());
@@ -162,6 +169,28 @@ void run_type(const char *tname, int n, int L, const char *only)
         cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, k)); \
         results.push_back({NAME, best, same, fa.numRegs}); \
     } while (0)
+#define CANDP(NAME, TW, TH, UNROLL, MINB, FLAVOR, ADMIT) do { \
+        if (only && !strstr(NAME, only)) break; \
+        auto k = rlic::lic_pass_kernel<T, true, PT, int, TW, TH, UNROLL, MINB, FLAVOR, ADMIT>; \
+        float best = 1e9; \
+        for (int r = 0; r < reps + 1; ++r) { \
+            CK(cudaEventRecord(e0)); \
+            k<<<g.tiles_per_field, TW * TH>>>(ptex, field, out, g, taps, L); \
+            CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); \
+            float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); if (r) best = fminf(best, ms); \
+        } \
+        CK(cudaGetLastError()); \
+        cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, k)); \
+        results.push_back({NAME, best, true, fa.numRegs}); \
+    } while (0)
+    CANDP("pol u2 b6 f0 a2", 16, 16, 2, 6, 0, 2);
+    CANDP("pol u2 b5 f0 a2", 16, 16, 2, 5, 0, 2);
+    CANDP("pol u2 b4 f0 a2", 16, 16, 2, 4, 0, 2);
+    CANDP("pol u2 b3 f0 a2", 16, 16, 2, 3, 0, 2);
+    CANDP("pol u4 b8 f1 a3", 16, 16, 4, 8, 1, 3);
+    CANDP("pol u2 b8 f0 a2", 16, 16, 2, 8, 0, 2);
+    CANDP("pol u2 b6 f1 a3", 16, 16, 2, 6, 1, 3);
+    CANDP("pol u2 b8 f1 a3", 16, 16, 2, 8, 1, 3);
     //    name              TW  TH  unroll minblocks flavor admit
     CAND("u2 b8 f1 a3", 16, 16, 2, 8, 1, 3);
     CAND("u4 b8 f1 a3", 16, 16, 4, 8, 1, 3);
@@ -170,6 +199,9 @@ void run_type(const char *tname, int n, int L, const char *only)
     CAND("u2 b8 f0 a2", 16, 16, 2, 8, 0, 2);
     CAND("u2 b6 f0 a2", 16, 16, 2, 6, 0, 2);
     CAND("u2 b6 f0 a0", 16, 16, 2, 6, 0, 0);
+    CAND("u2 b5 f0 a2", 16, 16, 2, 5, 0, 2);
+    CAND("u4 b6 f0 a2", 16, 16, 4, 6, 0, 2);
+    CAND("u1 b6 f0 a2", 16, 16, 1, 6, 0, 2);
     CAND("32x8 u2 b8 f1 a3", 32, 8, 2, 8, 1, 3);
 
     const double steps = (double)count * (L - 1);
@@ -188,6 +220,7 @@ int main(int argc, char **argv)
     const int n = argc > 1 ? atoi(argv[1]) : 4096;
     const int L = argc > 2 ? atoi(argv[2]) : 65;
     const char *only = argc > 3 ? argv[3] : nullptr;
+    g_split_field = argc > 4 ? atoi(argv[4]) : 0;
     if (!only) {
         divcheck<float>("f32");
         divcheck<double>("f64");
