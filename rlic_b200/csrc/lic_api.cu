@@ -71,19 +71,16 @@ struct Walls { int x_left, x_right, y_left, y_right; };
 
 // Keep freed stream-ordered allocations cached in the device pool instead of
 // returning them to the OS at every synchronisation (first call per device).
-cudaError_t use_device(int device)
+cudaError_t keep_pool_warm(int device)
 {
     static std::mutex mu;
     static std::vector<char> tuned;
-    cudaError_t e = cudaSetDevice(device);
-    if (e != cudaSuccess)
-        return e;
     std::lock_guard<std::mutex> lock(mu);
     if ((size_t)device >= tuned.size())
         tuned.resize((size_t)device + 1, 0);
     if (!tuned[(size_t)device]) {
         cudaMemPool_t pool;
-        e = cudaDeviceGetDefaultMemPool(&pool, device);
+        cudaError_t e = cudaDeviceGetDefaultMemPool(&pool, device);
         if (e != cudaSuccess)
             return e;
         uint64_t keep = UINT64_MAX;
@@ -93,6 +90,20 @@ cudaError_t use_device(int device)
         tuned[(size_t)device] = 1;
     }
     return cudaSuccess;
+}
+
+cudaError_t use_device(int device)
+{
+    cudaError_t e = cudaSetDevice(device);
+    return e != cudaSuccess ? e : keep_pool_warm(device);
+}
+
+// device entry points run on whatever device is current for the caller
+cudaError_t use_current_device()
+{
+    int device = 0;
+    cudaError_t e = cudaGetDevice(&device);
+    return e != cudaSuccess ? e : keep_pool_warm(device);
 }
 
 int check_common(int64_t ny, int64_t nx, int64_t klen, int uv_mode, const Walls &w)
@@ -463,6 +474,7 @@ int run_device(const T *d_tex, const Field<T> *d_field, int64_t ny, int64_t nx, 
 {
     const PassGeom g = make_geometry(ny, nx, Slab{0, ny, 0, 0}, w);
     const size_t padded_bytes = (size_t)g.field_stride * sizeof(T);
+    CUDA_TRY(use_current_device());
     DeviceBuf a, b;   // stream-ordered scratch, returned to the pool when the work is enqueued
     CUDA_TRY(a.alloc(padded_bytes, s));
     if (iterations > 1)
@@ -511,6 +523,7 @@ int convolve_device(const T *d_tex, const T *d_u, const T *d_v, int64_t ny, int6
         CUDA_TRY(cudaMemsetAsync(d_out, 0, sizeof(T) * count, s));
         return RLIC_B200_OK;
     }
+    CUDA_TRY(use_current_device());
     TapSet<T> taps;
     CUDA_TRY(taps.prepare(kernel, klen, s));
     const PassGeom g = make_geometry(ny, nx, Slab{0, ny, 0, 0}, w);
