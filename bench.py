@@ -439,7 +439,17 @@ def main() -> None:
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    line = run_reference(args) if args.impl == "reference" else run_ours(args)
+    # Only the JSON line may reach stdout: libraries (NCCL prints its version at
+    # communicator creation) get stderr instead, at the file-descriptor level.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        line = run_reference(args) if args.impl == "reference" else run_ours(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
     if line:
         print(json.dumps(line), flush=True)
 
