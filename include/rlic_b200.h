@@ -176,6 +176,9 @@ int rlic_b200_convolve_device_f64(const double *d_texture, const double *d_u, co
  * column counter nor wall compares.  rlic_b200_padded_cells(rows, nx) is that
  * cell count.  The packed FIELD holds one record of 4 scalars per cell,
  *     { u, v, ru, rv }        (16 bytes for f32, 32 bytes for f64)
+ * interleaved for f32; for f64 split into two planes of 2 scalars per cell,
+ * { u, v } for all cells of the buffer followed by { ru, rv } for all cells
+ * (a halo exchange of f64 field rows therefore moves two ranges),
  * where ru, rv are the refined reciprocals that an IEEE division by u, v
  * computes as its first stage; they are walker- and iteration-invariant, so they
  * are computed once per pixel instead of twice per step in the walk.  A

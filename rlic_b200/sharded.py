@@ -198,9 +198,16 @@ class ShardedConvolver:
         self.comm_stream = None
 
     # -- halo plumbing ------------------------------------------------------
-    def _exchange(self, buf: torch.Tensor, width: int = 1) -> None:
-        """Fill the halo rows of the flat padded buffer ``buf`` (``width`` scalars
-        per cell) from the neighbours.
+    @staticmethod
+    def field_layout(dtype) -> tuple[int, int]:
+        """(scalars per cell, planes) of a packed field buffer: f32 records are
+        interleaved (4 scalars per cell); f64 records are split into a {u, v}
+        and a {ru, rv} plane of 2 scalars per cell (include/rlic_b200.h)."""
+        return (4, 1) if dtype == torch.float32 else (2, 2)
+
+    def _exchange(self, buf: torch.Tensor, width: int = 1, planes: int = 1) -> None:
+        """Fill the halo rows of the flat padded buffer ``buf`` (``planes`` planes of
+        ``width`` scalars per cell) from the neighbours.
 
         Every rank posts: send top rows up, send bottom rows down, receive the
         high halo from below, receive the low halo from above.  That order
@@ -210,19 +217,21 @@ class ShardedConvolver:
         p = self.plan
         h, lo, n = p.reach, p.halo_lo, p.nrows
 
-        def rows(a, b):
+        def rows(plane, a, b):
             s = p.row_cells(a, b)
-            return buf[s.start * width:s.stop * width]
+            base = plane * p.cells
+            return buf[(base + s.start) * width:(base + s.stop) * width]
 
         ops = []
-        if p.up is not None:
-            ops.append(dist.P2POp(dist.isend, rows(lo, lo + h), p.up, self.group))
-        if p.down is not None:
-            ops.append(dist.P2POp(dist.isend, rows(lo + n - h, lo + n), p.down, self.group))
-        if p.down is not None:
-            ops.append(dist.P2POp(dist.irecv, rows(lo + n, lo + n + h), p.down, self.group))
-        if p.up is not None:
-            ops.append(dist.P2POp(dist.irecv, rows(0, lo), p.up, self.group))
+        for plane in range(planes):
+            if p.up is not None:
+                ops.append(dist.P2POp(dist.isend, rows(plane, lo, lo + h), p.up, self.group))
+            if p.down is not None:
+                ops.append(dist.P2POp(dist.isend, rows(plane, lo + n - h, lo + n), p.down, self.group))
+            if p.down is not None:
+                ops.append(dist.P2POp(dist.irecv, rows(plane, lo + n, lo + n + h), p.down, self.group))
+            if p.up is not None:
+                ops.append(dist.P2POp(dist.irecv, rows(plane, 0, lo), p.up, self.group))
         if ops:
             for req in dist.batch_isend_irecv(ops):
                 req.wait()
@@ -236,9 +245,10 @@ class ShardedConvolver:
         p = self.plan
         if tuple(u.shape) != (p.nrows, p.nx) or tuple(v.shape) != (p.nrows, p.nx):
             raise ValueError(f"expected this rank's slab of shape {(p.nrows, p.nx)}")
-        field = self._alloc(u, 4)
+        width, planes = self.field_layout(u.dtype)
+        field = self._alloc(u, width * planes)
         self.ops.pack_field(u.contiguous(), v.contiguous(), field, p, self.walls)
-        self._exchange(field, 4)
+        self._exchange(field, width, planes)
         self.field = field
 
     def _pass_rows(self, src, dst, a: int, b: int) -> None:

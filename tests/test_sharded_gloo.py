@@ -68,18 +68,31 @@ class OracleSlabOps:
                 g = self._cell(plan, plan.rows_alloc, 0)
                 flat[g:g + plan.nx] = torch.from_numpy(np.ascontiguousarray(line))
 
+    @staticmethod
+    def _uv_views(field, plan):
+        """(u, v, ru, rv) views over the cells of a packed-field buffer, following the
+        product's layout: interleaved records for f32, two planes for f64."""
+        if field.dtype == torch.float32:
+            f = field.view(-1, 4)
+            return f[:, 0], f[:, 1], f[:, 2], f[:, 3]
+        a = field[:2 * plan.cells].view(-1, 2)
+        b = field[2 * plan.cells:].view(-1, 2)
+        return a[:, 0], a[:, 1], b[:, 0], b[:, 1]
+
     def pack_field(self, u, v, field, plan, walls):
         field[:] = float("nan")
-        f = field.view(-1, 4)
+        fu, fv, fru, frv = self._uv_views(field, plan)
         for k in range(plan.nrows):
             r = plan.halo_lo + k
             base = self._cell(plan, r, 0)
-            f[base:base + plan.nx, 0] = u[k]
-            f[base:base + plan.nx, 1] = v[k]
-            f[base:base + plan.nx, 2:] = 0
+            fu[base:base + plan.nx] = u[k]
+            fv[base:base + plan.nx] = v[k]
+            fru[base:base + plan.nx] = 0
+            frv[base:base + plan.nx] = 0
             # stand-in sentinels: tag the wall cells of owned rows so that their transport can be checked
-            f[self._cell(plan, r, plan.nx), :] = 12345.0
-            f[self._cell(plan, r, -1), :] = 54321.0
+            for part in (fu, fv, fru, frv):
+                part[self._cell(plan, r, plan.nx)] = 12345.0
+                part[self._cell(plan, r, -1)] = 54321.0
 
     def pad_texture(self, texture, padded, plan, walls):
         padded[:] = float("nan")
@@ -98,7 +111,7 @@ class OracleSlabOps:
         ny, nx = plan.ny, plan.nx
         w = self._walls(plan, walls)
         periodic_y = walls[2] == 1
-        f = field.view(-1, 4).numpy()
+        fu, fv, fru, frv = (t.numpy() for t in self._uv_views(field, plan))
         s = src.numpy()
         g_tex = np.full((ny, nx), np.nan, dtype=s.dtype)        # poison: unread rows stay NaN
         g_u = np.full((ny, nx), 1e30, dtype=s.dtype)
@@ -113,12 +126,13 @@ class OracleSlabOps:
             assert 0 <= g < ny, "buffer row outside a closed image"
             base = self._cell(plan, r, 0)
             g_tex[g] = s[base:base + nx]
-            g_u[g] = f[base:base + nx, 0]
-            g_v[g] = f[base:base + nx, 1]
+            g_u[g] = fu[base:base + nx]
+            g_v[g] = fv[base:base + nx]
             # the wall cells must have travelled with their rows
             assert s[self._cell(plan, r, nx)] == g_tex[g][w["j_above_to"]] or np.isnan(g_tex[g][w["j_above_to"]])
             assert s[self._cell(plan, r, -1)] == g_tex[g][w["j_below_to"]] or np.isnan(g_tex[g][w["j_below_to"]])
-            assert f[self._cell(plan, r, nx), 0] == 12345.0 and f[self._cell(plan, r, -1), 0] == 54321.0
+            for part in (fu, fv, fru, frv):
+                assert part[self._cell(plan, r, nx)] == 12345.0 and part[self._cell(plan, r, -1)] == 54321.0
         bnd = ((WALL_NAMES[walls[0]], WALL_NAMES[walls[1]]), (WALL_NAMES[walls[2]], WALL_NAMES[walls[3]]))
         band = oracle.pass_rows(g_tex, g_u, g_v, kernel=taps, rows=(plan.row0 + a, plan.row0 + b),
                                 uv_mode="polarization" if mode else "velocity", boundaries=bnd)

@@ -55,8 +55,13 @@ def slab_pass_all(tex, u, v, kernel, bounds_spec, walls, mode, cuts):
             d_u.data_ptr(), d_v.data_ptr(), *args, *walls, f_pad.data_ptr(), stream()))
         slabs.append(dict(r0=r0, r1=r1, lo=lo, hi=hi, args=args, tex=t_pad, field=f_pad))
 
-    def rows(s, buf, a, b, width):       # padded rows [a, b) of a slab buffer, with wall cells
-        return buf[((a + 1) * P - 1) * width:((b + 1) * P - 1) * width]
+    def rows(s, buf, a, b, width, plane=0):   # padded rows [a, b) of a slab buffer, with wall cells
+        cells = (s["lo"] + s["r1"] - s["r0"] + s["hi"] + 2) * P
+        base = plane * cells
+        return buf[(base + (a + 1) * P - 1) * width:(base + (b + 1) * P - 1) * width]
+
+    # packed field: interleaved 4-scalar records for f32, two 2-scalar planes for f64
+    f_width, f_planes = (4, 1) if tex.dtype == np.float32 else (2, 2)
 
     def owner(g):                         # slab and buffer row holding global row g
         g %= ny
@@ -72,7 +77,9 @@ def slab_pass_all(tex, u, v, kernel, bounds_spec, walls, mode, cuts):
             brow = k if k < s["lo"] else s["lo"] + (s["r1"] - s["r0"]) + (k - s["lo"])
             src, srow = owner(g)
             rows(s, s["tex"], brow, brow + 1, 1).copy_(rows(src, src["tex"], srow, srow + 1, 1))
-            rows(s, s["field"], brow, brow + 1, 4).copy_(rows(src, src["field"], srow, srow + 1, 4))
+            for plane in range(f_planes):
+                rows(s, s["field"], brow, brow + 1, f_width, plane).copy_(
+                    rows(src, src["field"], srow, srow + 1, f_width, plane))
 
     out = np.empty_like(tex)
     for s in slabs:
