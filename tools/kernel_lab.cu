@@ -99,6 +99,58 @@ template <typename T> void divcheck(const char *name)
     CK(cudaFree(bad));
 }
 
+// Candidate: persistent CTAs that pull tiles from per-SM lists, so that the CTAs
+// resident on one SM work on adjacent tiles (a 4 x 2 block of 16 x 16 tiles) and
+// share L1 lines, instead of whatever tiles the hardware scheduler hands out.
+template <typename T, bool POL, typename Taps, int TW, int TH, int UNROLL, int MINB, int FLAVOR, int ADMIT, int SW, int SH>
+__global__ void __launch_bounds__(TW *TH, MINB)
+persistent_pass_kernel(const T *__restrict__ tex, const PackedField<T> *__restrict__ field,
+                       T *__restrict__ out, const __grid_constant__ PassGeom g,
+                       const __grid_constant__ Taps taps, const int ntaps, unsigned *counters, int nlists)
+{
+    using F = Fp<T>;
+    __shared__ unsigned s_item;
+    unsigned smid;
+    asm("mov.u32 %0, %%smid;" : "=r"(smid));
+    const int tiles_y = g.tiles_per_field / g.tiles_x;
+    const int sup_x = (g.tiles_x + SW - 1) / SW, sup_y = (tiles_y + SH - 1) / SH;
+    const int nsup = sup_x * sup_y;
+    const long long base = g.pitch;
+    tex += base;
+    out += base;
+    typename rlic::FieldAccess<T>::Ptr fcell = rlic::FieldAccess<T>::block(field, 0, g.field_stride) + g.pitch;
+    asm volatile("" : "+l"(tex), "+l"(fcell));
+    const int pitch = g.pitch;
+    const int kmid = ntaps >> 1;
+    int owner = (int)(smid % (unsigned)nlists);
+    for (int tries = 0; tries < nlists; ++tries, owner = (owner + 1 == nlists ? 0 : owner + 1)) {
+        for (;;) {
+            if (threadIdx.x == 0) s_item = atomicAdd(&counters[owner], 1u);
+            __syncthreads();
+            const unsigned k = s_item;
+            __syncthreads();
+            const int sup = owner + nlists * (int)(k / (SW * SH));
+            if (sup >= nsup) break;
+            const int slot = (int)(k % (SW * SH));
+            const int tile_x = (sup % sup_x) * SW + slot % SW;
+            const int tile_y = (sup / sup_x) * SH + slot / SW;
+            const int j = tile_x * TW + (int)(threadIdx.x % TW);
+            const int r = tile_y * TH + (int)(threadIdx.x / TW);
+            if (tile_x >= g.tiles_x || tile_y >= tiles_y || j >= g.nx || r >= g.out_rows) continue;
+            const int row = g.first_row + r;
+            const int at = row * pitch + j;
+            T acc = F::fma(taps.get(kmid), __ldg(tex + at), T(0));
+            acc = rlic::half_walk<T, POL, +1, Taps, int, UNROLL, FLAVOR, ADMIT>(acc, at, tex, fcell, taps, kmid + 1, ntaps, pitch, (int)g.field_stride);
+            acc = rlic::half_walk<T, POL, -1, Taps, int, UNROLL, FLAVOR, ADMIT>(acc, at, tex, fcell, taps, kmid - 1, -1, pitch, (int)g.field_stride);
+            out[at] = acc;
+            if (j == g.j_above_to) out[row * pitch + g.nx] = acc;
+            if (j == g.j_below_to) out[row * pitch - 1] = acc;
+            if (g.lo_wall && row == g.i_below_to) out[-pitch + j] = acc;
+            if (g.hi_wall && row == g.i_above_to) out[g.rows * pitch + j] = acc;
+        }
+    }
+}
+
 struct Result { std::string name; float ms; bool same; int regs; };
 
 template <typename T>
@@ -191,6 +243,40 @@ void run_type(const char *tname, int n, int L, const char *only)
     CANDP("pol u2 b8 f0 a2", 16, 16, 2, 8, 0, 2);
     CANDP("pol u2 b6 f1 a3", 16, 16, 2, 6, 1, 3);
     CANDP("pol u2 b8 f1 a3", 16, 16, 2, 8, 1, 3);
+    {
+        unsigned *counters; CK(cudaMalloc(&counters, 1024 * sizeof(unsigned)));
+        int nsm = 0; CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0));
+#define CANDPERS(NAME, MINB, UNROLL, FLAVOR, ADMIT, SW, SH) do { \
+        if (only && !strstr(NAME, only)) break; \
+        auto k = persistent_pass_kernel<T, false, PT, 16, 16, UNROLL, MINB, FLAVOR, ADMIT, SW, SH>; \
+        float best = 1e9; \
+        CK(cudaMemset(out, 0, cells * sizeof(T))); \
+        for (int r = 0; r < reps + 1; ++r) { \
+            CK(cudaMemset(counters, 0, 1024 * sizeof(unsigned))); \
+            CK(cudaEventRecord(e0)); \
+            k<<<nsm * MINB, 256>>>(ptex, field, out, g, taps, L, counters, nsm); \
+            CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); \
+            float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); if (r) best = fminf(best, ms); \
+        } \
+        CK(cudaGetLastError()); \
+        CK(cudaMemcpy(h_out.data(), out, cells * sizeof(T), cudaMemcpyDeviceToHost)); \
+        bool same = memcmp(h_out.data(), h_ref.data(), cells * sizeof(T)) == 0; \
+        cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, k)); \
+        results.push_back({NAME, best, same, fa.numRegs}); \
+    } while (0)
+        if (sizeof(T) == 4) {
+            CANDPERS("persist b8 4x2", 8, 4, 1, 3, 4, 2);
+            CANDPERS("persist b8 2x4", 8, 4, 1, 3, 2, 4);
+            CANDPERS("persist b8 8x1", 8, 4, 1, 3, 8, 1);
+            CANDPERS("persist b8 1x8", 8, 4, 1, 3, 1, 8);
+            CANDPERS("persist b8 4x4", 8, 4, 1, 3, 4, 4);
+        } else {
+            CANDPERS("persist b6 3x2", 6, 2, 0, 2, 3, 2);
+            CANDPERS("persist b6 2x3", 6, 2, 0, 2, 2, 3);
+            CANDPERS("persist b6 6x1", 6, 2, 0, 2, 6, 1);
+        }
+        CK(cudaFree(counters));
+    }
     //    name              TW  TH  unroll minblocks flavor admit
     CAND("u2 b8 f1 a3", 16, 16, 2, 8, 1, 3);
     CAND("u4 b8 f1 a3", 16, 16, 4, 8, 1, 3);
