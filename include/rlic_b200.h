@@ -129,7 +129,9 @@ int rlic_b200_convolve_checked_f64(const double *texture, const double *u, const
  * instead of from the heap: the download then needs neither page faults nor the
  * driver's bounce buffer.  Blocks are cached and reused; at most 4 GiB are held
  * (cached + handed out), beyond which rlic_b200_result_alloc returns NULL and
- * the caller uses ordinary memory.  Also NULL without a CUDA device.
+ * the caller uses ordinary memory.  Page-locking costs more than one download
+ * saves, so the first request of a size also returns NULL (one-shot calls stay
+ * on ordinary memory).  Also NULL without a CUDA device.
  */
 void *rlic_b200_result_alloc(int64_t bytes);
 void rlic_b200_result_free(void *block);

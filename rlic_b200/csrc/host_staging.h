@@ -13,6 +13,7 @@
 #include <cstdint>
 #include <cstring>
 #include <functional>
+#include <map>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -245,7 +246,10 @@ cudaError_t upload(const HostToDevice *jobs, int njobs, cudaStream_t stream)
 // for a page-locked block, wrap it in the ndarray it returns, and give it back
 // when that array is garbage collected.  Blocks are cached by size class and the
 // total (cached + handed out) is capped; past the cap the caller falls back to
-// ordinary memory.
+// ordinary memory.  Page-locking is itself expensive (~0.4 ms per MiB), far more
+// than it saves on one download, so a block is only allocated once a size class
+// has been asked for before: one-shot calls stay on ordinary memory, repeated
+// workloads get the fast path from their second call on.
 class ResultBlocks {
 public:
     static constexpr size_t kCap = (size_t)4 << 30;   // bytes of page-locked memory this pool may hold
@@ -259,6 +263,8 @@ public:
                 free_.erase(free_.begin() + (long)i);
                 return p;
             }
+        if (++requests_[cls] < 2)
+            return nullptr;
         // make room by dropping cached blocks of other sizes, oldest first
         while (total_ + cls > kCap && !free_.empty()) {
             cudaFreeHost(free_.front().first);
@@ -294,6 +300,7 @@ private:
     }
     std::mutex mu_;
     std::vector<std::pair<void *, size_t>> free_, sizes_;
+    std::map<size_t, int> requests_;
     size_t total_ = 0;
 };
 

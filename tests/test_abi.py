@@ -105,13 +105,16 @@ def test_without_a_gpu_the_product_fails_loudly():
 def test_result_blocks_fall_back_without_a_device_and_recycle_with_one():
     import gc
 
-    a = _core.new_result((600, 700), np.float32)     # 1.6 MB: above the pinned threshold
+    first = _core.new_result((600, 700), np.float32)  # 1.6 MB: above the pinned threshold
+    assert first.flags.owndata                        # a size seen for the first time stays on the heap
+    a = _core.new_result((600, 700), np.float32)
     assert a.shape == (600, 700) and a.dtype == np.float32 and a.flags.c_contiguous and a.flags.writeable
     a[:] = 3.0
     assert float(a.sum()) == 3.0 * 600 * 700
     if _core.device_count() == 0:
         assert a.flags.owndata                       # ordinary memory: the pool is unavailable
         return
+    assert not a.flags.owndata                       # second request of the size: page-locked block
     ptr = a.ctypes.data
     view = a[10:20]                                  # views keep the block alive
     del a
