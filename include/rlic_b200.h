@@ -131,7 +131,8 @@ int rlic_b200_convolve_checked_f64(const double *texture, const double *u, const
  * (cached + handed out), beyond which rlic_b200_result_alloc returns NULL and
  * the caller uses ordinary memory.  Page-locking costs more than one download
  * saves, so the first request of a size also returns NULL (one-shot calls stay
- * on ordinary memory).  Also NULL without a CUDA device.
+ * on ordinary memory), as do requests above 256 MiB.  Also NULL without a CUDA
+ * device.
  */
 void *rlic_b200_result_alloc(int64_t bytes);
 void rlic_b200_result_free(void *block);

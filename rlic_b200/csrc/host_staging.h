@@ -253,8 +253,11 @@ cudaError_t upload(const HostToDevice *jobs, int njobs, cudaStream_t stream)
 class ResultBlocks {
 public:
     static constexpr size_t kCap = (size_t)4 << 30;   // bytes of page-locked memory this pool may hold
+    static constexpr size_t kLargest = (size_t)256 << 20;   // bigger results stay on ordinary memory
     void *acquire(size_t bytes)
     {
+        if (bytes > kLargest)
+            return nullptr;   // page-locking would cost more than many downloads save
         const size_t cls = size_class(bytes);
         std::lock_guard<std::mutex> lk(mu_);
         for (size_t i = 0; i < free_.size(); ++i)

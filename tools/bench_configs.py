@@ -57,7 +57,9 @@ def time_host(w, reps=3):
     kw = w.kwargs()
     pin = lambda x: torch.from_numpy(np.ascontiguousarray(x)).pin_memory().numpy()  # noqa: E731
     tex, u, v = pin(w.texture), pin(w.u), pin(w.v)
-    rlic_b200.convolve(tex, u, v, **kw)
+    for _ in range(3):   # the result's page-locked block is set up on the second call of a size
+        out = rlic_b200.convolve(tex, u, v, **kw)
+    del out
     t0 = time.perf_counter()
     for _ in range(reps):
         rlic_b200.convolve(tex, u, v, **kw)
