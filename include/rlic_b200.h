@@ -71,6 +71,17 @@ int64_t rlic_b200_launch_count(void);
  * buffers of 2^31 cells or more (a 46340 x 46340 image). */
 void rlic_b200_debug_force_wide_index(int on);
 
+/* Testing hook (host code only, no GPU needed): what the padded layout puts in
+ * cell `cell` of the buffer of the slab {row0, nrows, halo_lo, halo_hi} of an
+ * ny x nx image: out[0] = 1 for a pixel; otherwise a wall cell with out[1] = 1
+ * if a walker can land on it; out[2], out[3] = buffer row and column of the pixel
+ * itself or of the pixel the wall rule (lib.rs:83-95) continues from; out[4] =
+ * that pixel's cell minus `cell` (the sentinel's shift). */
+int rlic_b200_debug_wall_cell(int64_t ny, int64_t nx, int64_t row0, int64_t nrows,
+                              int64_t halo_lo, int64_t halo_hi,
+                              int x_left, int x_right, int y_left, int y_right,
+                              int64_t cell, int64_t *out);
+
 /*
  * HOST entry points — replace rlic._core.convolve_f32 / convolve_f64
  * (lib.rs:451-482 -> convolve_iteratively, lib.rs:408-443).

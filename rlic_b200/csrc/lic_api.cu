@@ -742,6 +742,32 @@ int64_t rlic_b200_launch_count(void) { return g_launches.load(std::memory_order_
 
 int64_t rlic_b200_padded_cells(int64_t rows, int64_t nx) { return rlic::padded_cells(rows, nx); }
 
+int rlic_b200_debug_wall_cell(int64_t ny, int64_t nx, int64_t row0, int64_t nrows, int64_t halo_lo,
+                              int64_t halo_hi, int x_left, int x_right, int y_left, int y_right,
+                              int64_t cell, int64_t *out)
+{
+    tls_error.clear();
+    const Walls w{x_left, x_right, y_left, y_right};
+    if (int rc = check_common(ny, nx, 1, 0, w))
+        return rc;
+    const Slab sl{row0, nrows, halo_lo, halo_hi};
+    if (int rc = check_slab(ny, 1, sl, w))
+        return rc;
+    if (!out)
+        return fail(RLIC_B200_EINVAL, "null pointer argument");
+    const PassGeom g = make_geometry(ny, nx, sl, w);
+    if (cell < 0 || cell >= g.field_stride)
+        return fail(RLIC_B200_EINVAL, "cell %lld outside the buffer of %lld cells", (long long)cell,
+                    (long long)g.field_stride);
+    const rlic::CellSource s = rlic::cell_source(cell, g);
+    out[0] = s.pixel;
+    out[1] = s.reachable;
+    out[2] = s.row;
+    out[3] = s.col;
+    out[4] = s.shift;
+    return RLIC_B200_OK;
+}
+
 void *rlic_b200_result_alloc(int64_t bytes)
 {
     if (bytes <= 0 || rlic_b200_device_count() == 0)
