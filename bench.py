@@ -141,39 +141,27 @@ def gather_bytes_per_pixel() -> int:
 
 
 # ----------------------------------------------------------------------------
-def cpu_baseline(threads: int | None, budget_s: float, rank: int = 0) -> dict:
-    """Times the CPU oracle (restatement of the reference's Rust core) on a
-    band of rows of pass 1 of the same workload, sized for ~budget_s seconds."""
+def cpu_baseline(threads: int | None, budget_s: float) -> dict:
+    """Times the CPU oracle (restatement of the reference's Rust core) on a band of rows
+    of pass 1 of the same workload (walkers see the full image), sized for ~budget_s s."""
     import oracle
 
     texture, u, v, kernel = make_slab(0, 1)
     threads = threads or oracle.max_threads()
     # calibrate on a thin band (also warms the caches), then size the sample
     t0 = time.perf_counter()
-    oracle.convolve(texture[:64], u[:64], v[:64], kernel=kernel, threads=threads)
+    oracle.pass_rows(texture, u, v, kernel=kernel, rows=(0, 64), threads=threads)
     calib = time.perf_counter() - t0
     rows = int(min(N_SIDE, max(64, 64 * budget_s / max(calib, 1e-6))))
     rows -= rows % 8
     r0 = (N_SIDE - rows) // 2
-    import ctypes
-
-    out = np.zeros_like(texture)
-    # the band walks inside the full image (true halo context), row-parallel over threads
     t0 = time.perf_counter()
-    if threads == 1:
-        oracle.pass_rows(texture, u, v, kernel=kernel, rows=(r0, r0 + rows))
-    else:
-        # oracle.convolve on the band plus TAPS//2 rows of context each side
-        h = TAPS // 2
-        a, b = max(0, r0 - h), min(N_SIDE, r0 + rows + h)
-        oracle.convolve(texture[a:b], u[a:b], v[a:b], kernel=kernel, threads=threads)
-        rows = b - a
+    oracle.pass_rows(texture, u, v, kernel=kernel, rows=(r0, r0 + rows), threads=threads)
     dt = time.perf_counter() - t0
-    del out, ctypes
     mpix = rows * N_SIDE / dt / 1e6
     return {
         "value": mpix, "unit": METRIC, "cores": threads, "kind": "port",
-        "sample": (f"one pass over a {rows}-row band of the 4096x4096 f32 65-tap vortex workload "
+        "sample": (f"one pass over rows [{r0}, {r0 + rows}) of the 4096x4096 f32 65-tap vortex workload "
                    f"({rows * N_SIDE * (TAPS - 1) / 1e6:.0f} M pixel-steps) in {dt:.2f} s on {threads} "
                    "thread(s); C restatement of the reference's Rust core (oracle/lic_oracle.c, "
                    "fma+branchless), the reference itself is single-threaded"),

@@ -57,7 +57,7 @@ def lib() -> ctypes.CDLL:
             fn.restype = ctypes.c_int
             pr = getattr(_lib, f"lic_oracle_pass_rows_{sfx}")
             pr.argtypes = [p, p, p, ctypes.c_int64, ctypes.c_int64, p, ctypes.c_int64]
-            pr.argtypes += [ctypes.c_int] * 5 + [ctypes.c_int64, ctypes.c_int64, p]
+            pr.argtypes += [ctypes.c_int] * 5 + [ctypes.c_int64, ctypes.c_int64, ctypes.c_int, p]
             pr.restype = ctypes.c_int
             et = getattr(_lib, f"lic_oracle_edge_time_{sfx}")
             et.argtypes = [ct, ct, ctypes.c_int]
@@ -133,9 +133,9 @@ def convolve(
 
 
 def pass_rows(texture, u, v, *, kernel, rows, uv_mode="velocity",
-              boundaries=(("closed", "closed"), ("closed", "closed"))):
-    """One pass (crate-default arithmetic) over image rows ``rows=(r0, r1)`` only;
-    returns the ``(r1-r0, nx)`` band."""
+              boundaries=(("closed", "closed"), ("closed", "closed")), threads=1):
+    """One pass (crate-default arithmetic) over image rows ``rows=(r0, r1)`` only, on
+    ``threads`` threads; returns the ``(r1-r0, nx)`` band."""
     if isinstance(boundaries, str):
         boundaries = ((boundaries, boundaries), (boundaries, boundaries))
     texture = np.ascontiguousarray(texture)
@@ -152,7 +152,7 @@ def pass_rows(texture, u, v, *, kernel, rows, uv_mode="velocity",
         texture.ctypes.data_as(p), u.ctypes.data_as(p), v.ctypes.data_as(p), ny, nx,
         kernel.ctypes.data_as(p), kernel.size, _MODE_CODE[uv_mode],
         _BOUNDARY_CODE[xl], _BOUNDARY_CODE[xr], _BOUNDARY_CODE[yl], _BOUNDARY_CODE[yr],
-        r0, r1, out.ctypes.data_as(p),
+        r0, r1, threads, out.ctypes.data_as(p),
     )
     if rc != 0:
         raise RuntimeError(f"lic_oracle_pass_rows_{sfx} failed with code {rc}")

@@ -195,16 +195,16 @@ int lic_oracle_convolve_f64(const double *tex, const double *u, const double *v,
 
 /* One pass restricted to rows [row_begin,row_end): lets a test check a band of
  * a large image against the CUDA path without walking all of it.  Only those
- * rows of `out` are written.  Variant 3 (crate default) only. */
+ * rows of `out` are written, on `threads` threads.  Variant 3 (crate default) only. */
 int lic_oracle_pass_rows_f32(const float *tex, const float *u, const float *v,
                              int64_t ny, int64_t nx, const float *taps,
                              int64_t ntaps, int polarization, int x_left,
                              int x_right, int y_left, int y_right,
-                             int64_t row_begin, int64_t row_end, float *out)
+                             int64_t row_begin, int64_t row_end, int threads, float *out)
 {
     lic_geometry g = make_geometry(ny, nx, polarization, x_left, x_right, y_left, y_right);
     if (ntaps <= 0) return LIC_ORACLE_EMPTY_KERNEL;
-    pass_rows_f32_v3(tex, u, v, taps, (size_t)ntaps, &g, out, (size_t)row_begin, (size_t)row_end);
+    pass_band_f32_v3(tex, u, v, taps, (size_t)ntaps, &g, out, (size_t)row_begin, (size_t)row_end, threads);
     return 0;
 }
 
@@ -212,11 +212,11 @@ int lic_oracle_pass_rows_f64(const double *tex, const double *u, const double *v
                              int64_t ny, int64_t nx, const double *taps,
                              int64_t ntaps, int polarization, int x_left,
                              int x_right, int y_left, int y_right,
-                             int64_t row_begin, int64_t row_end, double *out)
+                             int64_t row_begin, int64_t row_end, int threads, double *out)
 {
     lic_geometry g = make_geometry(ny, nx, polarization, x_left, x_right, y_left, y_right);
     if (ntaps <= 0) return LIC_ORACLE_EMPTY_KERNEL;
-    pass_rows_f64_v3(tex, u, v, taps, (size_t)ntaps, &g, out, (size_t)row_begin, (size_t)row_end);
+    pass_band_f64_v3(tex, u, v, taps, (size_t)ntaps, &g, out, (size_t)row_begin, (size_t)row_end, threads);
     return 0;
 }
 
