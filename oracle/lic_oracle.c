@@ -15,9 +15,14 @@
  *     (NaN-field scaling kernel[mid]**n, transpose symmetry, eye(5) polarization
  *     cases, default-argument equalities)
  *   - a second, independent pure-Python restatement (oracle/pyoracle.py)
- * It is NOT pinned against output arrays produced by the reference itself:
- * with respect to reference-generated outputs the status is "parity unpinned"
- * (DESIGN.md section 3 says the same).
+ *   - the only outputs of the real rLIC available offline: the five LIC
+ *     panels of its README figures (static/*.png, seeded inputs), which this
+ *     oracle reproduces to within rounding of the 8-bit colours
+ *     (tests/test_reference_images.py; about 1/256 of the dynamic range per
+ *     pixel, so an algorithmic pin, not a bit-level one)
+ * It is NOT pinned against output ARRAYS produced by the reference itself:
+ * at the bit level the status is "parity unpinned" (DESIGN.md section 3 says
+ * the same).
  *
  * Arithmetic variants mirror the reference's Cargo features
  * (Cargo.toml:27-30): bit 0 = fma, bit 1 = branchless.  Variant 3
