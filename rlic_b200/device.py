@@ -4,8 +4,10 @@
 therefore pays two PCIe trips per call.  Callers whose data already lives on
 the GPU use these functions instead: same arithmetic, same C ABI underneath
 (``rlic_b200_pack_field_*`` / ``rlic_b200_convolve_packed_*`` /
-``rlic_b200_pass_slab_*``), torch tensors in and out.  torch is used for device
-memory and streams only.
+``rlic_b200_pass_slab_*``), torch tensors in and out.  Arrays of other libraries
+are taken without a copy through ``__cuda_array_interface__`` (CuPy, Numba) or
+DLPack; the result is a torch tensor, which exports both protocols.  torch is
+used for device memory and streams only.
 """
 
 from __future__ import annotations
@@ -55,9 +57,23 @@ def _host_taps(kernel, np_dtype) -> np.ndarray:
     return kernel
 
 
+def _as_tensor(x):
+    """View a foreign device array as a torch tensor (zero copy); tensors and
+    ``None`` pass through.  Host arrays come out as CPU tensors and are rejected
+    by ``_check_image``."""
+    if x is None or isinstance(x, torch.Tensor):
+        return x
+    if hasattr(x, "__cuda_array_interface__"):
+        return torch.as_tensor(x)
+    if hasattr(x, "__dlpack__"):
+        return torch.from_dlpack(x)
+    return x
+
+
 def _check_image(name: str, t: torch.Tensor, like: torch.Tensor | None = None) -> None:
     if not isinstance(t, torch.Tensor) or not t.is_cuda:
-        raise TypeError(f"{name} must be a CUDA tensor")
+        raise TypeError(f"{name} must be a CUDA tensor or an array exporting "
+                        "__cuda_array_interface__ / DLPack from device memory")
     if t.dim() != 2 or not t.is_contiguous():
         raise ValueError(f"{name} must be a contiguous 2-D tensor")
     if like is not None and (t.shape != like.shape or t.dtype != like.dtype or t.device != like.device):
@@ -77,6 +93,7 @@ class PackedField:
 
 def pack_field(u: torch.Tensor, v: torch.Tensor, *, boundaries="closed", stream=None) -> PackedField:
     """Build the packed field from two planar components (one streaming kernel)."""
+    u, v = _as_tensor(u), _as_tensor(v)
     _check_image("u", u)
     _check_image("v", v, u)
     sfx, _, _ = _kind(u)
@@ -101,6 +118,7 @@ def convolve_device(texture: torch.Tensor, u: torch.Tensor | None = None, v: tor
     ``boundaries``).  Work is enqueued on ``stream`` (default: torch's current
     stream) without synchronising.
     """
+    texture, u, v, out = _as_tensor(texture), _as_tensor(u), _as_tensor(v), _as_tensor(out)
     _check_image("texture", texture)
     sfx, real, np_dtype = _kind(texture)
     if iterations < 0:
