@@ -156,7 +156,7 @@ def cpu_baseline(threads: int | None, budget_s: float) -> dict:
     rows -= rows % 8
     r0 = (N_SIDE - rows) // 2
     t0 = time.perf_counter()
-    oracle.pass_rows(texture, u, v, kernel=kernel, rows=(r0, r0 + rows), threads=threads)
+    band = oracle.pass_rows(texture, u, v, kernel=kernel, rows=(r0, r0 + rows), threads=threads)
     dt = time.perf_counter() - t0
     mpix = rows * N_SIDE / dt / 1e6
     return {
@@ -167,6 +167,22 @@ def cpu_baseline(threads: int | None, budget_s: float) -> dict:
                    "fma+branchless), the reference itself is single-threaded"),
         "ns_per_pixel_step": dt / (rows * N_SIDE * (TAPS - 1)) * 1e9 * threads,
         "seconds": dt,
+        "_band": (r0, band),
+    }
+
+
+def parity_of_sample(one_pass: np.ndarray, r0: int, band: np.ndarray) -> dict:
+    """parity figures reported with the timing.  `band` is the
+    oracle's pass-1 output for rows [r0, r0+len(band)) (the CPU-baseline sample),
+    `one_pass` the CUDA path's iterations=1 result for the whole image."""
+    mine = one_pass[r0:r0 + band.shape[0]]
+    span = float(band.max() - band.min()) or 1.0
+    return {
+        "against": "CPU oracle (restatement of src/lib.rs), pass 1",
+        "rows": [r0, r0 + band.shape[0]], "pixels": int(band.size),
+        "bit_equal_fraction": float(np.mean(mine.view(np.uint32) == band.view(np.uint32))),
+        "max_abs_err_over_range": float(np.max(np.abs(mine.astype(np.float64) - band)) / span),
+        "tolerance": 1e-5,
     }
 
 
@@ -180,11 +196,13 @@ def run_reference(args) -> dict:
     per_step = max(2.0, min(20.0, 90.0 / max(1, args.steps + args.warmup)))
     for i in range(args.warmup + args.steps):
         info = cpu_baseline(None, per_step)
+        info.pop("_band", None)
         if i >= args.warmup:
             vals.append(info)
     mpix = statistics.mean(x["value"] for x in vals)
     ms = statistics.mean(x["seconds"] for x in vals) * 1e3
     single = cpu_baseline(1, 4.0)
+    single.pop("_band", None)
     info = dict(info)
     info["value"] = mpix
     info["single_thread_value"] = single["value"]
@@ -410,7 +428,15 @@ def run_ours(args) -> dict:
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(None, 12.0)
-        line["cpu_baseline"]["single_thread"] = cpu_baseline(1, 4.0)
+        r0, band = line["cpu_baseline"].pop("_band")
+        try:   # a reporting extra: never allowed to take the bench line down with it
+            one_pass = rlic_b200.convolve(h_tex, h_u, h_v, kernel=kernel, boundaries="closed", iterations=1)
+            line["parity"] = parity_of_sample(one_pass, r0, band)
+        except Exception as exc:  # noqa: BLE001
+            line["parity"] = {"error": f"{type(exc).__name__}: {exc}"}
+        single = cpu_baseline(1, 4.0)
+        single.pop("_band", None)
+        line["cpu_baseline"]["single_thread"] = single
     elif rank == 0:
         line["cpu_baseline"] = None
     if dist is not None:
