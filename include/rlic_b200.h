@@ -82,6 +82,16 @@ int rlic_b200_debug_wall_cell(int64_t ny, int64_t nx, int64_t row0, int64_t nrow
                               int x_left, int x_right, int y_left, int y_right,
                               int64_t cell, int64_t *out);
 
+/* Testing hook (host code only): the buffer geometry the kernels are launched with for
+ * that slab and a `klen`-tap kernel (the slab is checked as rlic_b200_pass_slab_* checks
+ * it).  out[0..9] = image width, pitch, rows held, cells per field, the columns a walker
+ * continues from after leaving through the left / right wall, the buffer rows after the
+ * top / bottom wall, and whether the top / bottom wall is reachable from this buffer. */
+int rlic_b200_debug_geometry(int64_t ny, int64_t nx, int64_t row0, int64_t nrows,
+                             int64_t halo_lo, int64_t halo_hi,
+                             int x_left, int x_right, int y_left, int y_right,
+                             int64_t klen, int64_t *out);
+
 /*
  * HOST entry points — replace rlic._core.convolve_f32 / convolve_f64
  * (lib.rs:451-482 -> convolve_iteratively, lib.rs:408-443).

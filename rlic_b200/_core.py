@@ -78,6 +78,8 @@ def _load() -> ctypes.CDLL:
     cdll.rlic_b200_padded_cells.restype = _i64
     cdll.rlic_b200_debug_wall_cell.argtypes = [_i64] * 6 + [_int] * 4 + [_i64, ctypes.POINTER(_i64)]
     cdll.rlic_b200_debug_wall_cell.restype = _int
+    cdll.rlic_b200_debug_geometry.argtypes = [_i64] * 6 + [_int] * 4 + [_i64, ctypes.POINTER(_i64)]
+    cdll.rlic_b200_debug_geometry.restype = _int
     cdll.rlic_b200_result_alloc.argtypes = [_i64]
     cdll.rlic_b200_result_alloc.restype = _vp
     cdll.rlic_b200_result_free.argtypes = [_vp]

@@ -768,6 +768,33 @@ int rlic_b200_debug_wall_cell(int64_t ny, int64_t nx, int64_t row0, int64_t nrow
     return RLIC_B200_OK;
 }
 
+int rlic_b200_debug_geometry(int64_t ny, int64_t nx, int64_t row0, int64_t nrows, int64_t halo_lo,
+                             int64_t halo_hi, int x_left, int x_right, int y_left, int y_right,
+                             int64_t klen, int64_t *out)
+{
+    tls_error.clear();
+    const Walls w{x_left, x_right, y_left, y_right};
+    if (int rc = check_common(ny, nx, klen, 0, w))
+        return rc;
+    const Slab sl{row0, nrows, halo_lo, halo_hi};
+    if (int rc = check_slab(ny, klen, sl, w))
+        return rc;
+    if (!out)
+        return fail(RLIC_B200_EINVAL, "null pointer argument");
+    const PassGeom g = make_geometry(ny, nx, sl, w);
+    out[0] = g.nx;
+    out[1] = g.pitch;
+    out[2] = g.rows;
+    out[3] = g.field_stride;
+    out[4] = g.j_below_to;
+    out[5] = g.j_above_to;
+    out[6] = g.i_below_to;
+    out[7] = g.i_above_to;
+    out[8] = g.lo_wall;
+    out[9] = g.hi_wall;
+    return RLIC_B200_OK;
+}
+
 void *rlic_b200_result_alloc(int64_t bytes)
 {
     if (bytes <= 0 || rlic_b200_device_count() == 0)

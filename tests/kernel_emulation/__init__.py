@@ -1,0 +1,134 @@
+"""The library's CUDA kernels run on the CPU -- TEST INFRASTRUCTURE, not a fallback.
+
+``rlic_b200/csrc/lic_walk.cuh`` (the streamline walk, the field packing with its wall
+sentinels, the texture padding) is compiled with g++ behind ``RLIC_HOST_EMULATION`` and a
+shim of the CUDA built-ins it uses (``cuda_on_cpu.h``), and driven block by block by
+``emulate.cpp``.  The tests compare it with the oracle on machines without a GPU, so a
+change to the kernel logic is checked before any GPU time is spent on it.  Buffer
+geometry comes from the library's own host code (``rlic_b200_debug_geometry``).
+
+What this cannot show: anything about nvcc's code generation or the hardware -- in
+particular the approximate reciprocal that seeds the packed field (see ``cuda_on_cpu.h``).
+The ``-m gpu`` parity tests remain the proof for the shipped binary.
+"""
+from __future__ import annotations
+
+import ctypes
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+from rlic_b200 import _core
+
+HERE = Path(__file__).resolve().parent
+LIB = HERE / "libkernel_emulation.so"
+KERNEL_SOURCE = HERE.parents[1] / "rlic_b200" / "csrc" / "lic_walk.cuh"
+FLAGS = ["-O2", "-std=c++17", "-march=x86-64-v3", "-ffp-contract=off", "-fPIC", "-shared", "-pthread"]
+
+_i64, _int = ctypes.c_int64, ctypes.c_int
+_lib = None
+
+
+def build(force: bool = False) -> Path:
+    deps = [HERE / "emulate.cpp", HERE / "cuda_on_cpu.h", KERNEL_SOURCE]
+    if force or not LIB.exists() or any(d.stat().st_mtime > LIB.stat().st_mtime for d in deps):
+        subprocess.run(["g++", *FLAGS, f"-I{HERE}", str(HERE / "emulate.cpp"), "-o", str(LIB)],
+                       check=True, capture_output=True, text=True)
+    return LIB
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        cdll = ctypes.CDLL(str(build()))
+        for sfx, real in (("f32", ctypes.c_float), ("f64", ctypes.c_double)):
+            p, g = ctypes.POINTER(real), ctypes.POINTER(_i64)
+            getattr(cdll, f"emu_pack_field_{sfx}").argtypes = [p, p, p, g, _i64, _i64, _i64]
+            getattr(cdll, f"emu_pack_field_{sfx}").restype = None
+            getattr(cdll, f"emu_pad_texture_{sfx}").argtypes = [p, p, g, _i64, _i64, _i64, ctypes.POINTER(_int)]
+            getattr(cdll, f"emu_pad_texture_{sfx}").restype = None
+            getattr(cdll, f"emu_unpad_texture_{sfx}").argtypes = [p, p, g, _i64, _i64, _i64]
+            getattr(cdll, f"emu_unpad_texture_{sfx}").restype = None
+            getattr(cdll, f"emu_pass_{sfx}").argtypes = [p, p, p, g, _i64, _i64, _i64, _int, p, _i64,
+                                                        _int, _int, _int]
+            getattr(cdll, f"emu_pass_{sfx}").restype = _int
+        _lib = cdll
+    return _lib
+
+
+def _kind(dtype):
+    return {"float32": ("f32", ctypes.c_float), "float64": ("f64", ctypes.c_double)}[np.dtype(dtype).name]
+
+
+def _ptr(a: np.ndarray, real):
+    return a.ctypes.data_as(ctypes.POINTER(real))
+
+
+def geometry(ny, nx, slab, walls, klen) -> np.ndarray:
+    """The library's buffer geometry for ``slab = (row0, nrows, halo_lo, halo_hi)``."""
+    out = np.zeros(10, dtype=np.int64)
+    rc = _core.lib.rlic_b200_debug_geometry(ny, nx, *slab, *walls, klen, _ptr(out, _i64))
+    _core.check(rc)
+    return out
+
+
+class Buffers:
+    """Padded device-style buffers of one slab (or a batch of whole images), on the host."""
+
+    def __init__(self, dtype, ny, nx, walls, klen, slab=None, nfields=1):
+        self.sfx, self.real = _kind(dtype)
+        self.dtype = np.dtype(dtype)
+        self.ny, self.nx, self.walls, self.nfields = ny, nx, walls, nfields
+        self.slab = slab or (0, ny, 0, 0)
+        self.geom = geometry(ny, nx, self.slab, walls, klen)
+        self.rows, self.cells = int(self.geom[2]), int(self.geom[3])
+        self.field = np.full(4 * self.cells * nfields, np.nan, dtype=self.dtype)
+        self.tex = [np.full(self.cells * nfields, np.nan, dtype=self.dtype) for _ in range(2)]
+        self._g = _ptr(self.geom, _i64)
+
+    def pack_field(self, u, v, rows=None):
+        rb, re = rows or (0, self.rows)
+        u, v = (np.ascontiguousarray(a, dtype=self.dtype) for a in (u, v))
+        assert u.size == self.nfields * (re - rb) * self.nx == v.size
+        getattr(lib(), f"emu_pack_field_{self.sfx}")(_ptr(u, self.real), _ptr(v, self.real),
+                                                     _ptr(self.field, self.real), self._g, rb, re, self.nfields)
+
+    def pad_texture(self, dense, which=0, rows=None) -> bool:
+        rb, re = rows or (0, self.rows)
+        dense = np.ascontiguousarray(dense, dtype=self.dtype)
+        assert dense.size == self.nfields * (re - rb) * self.nx
+        negative = _int(0)
+        getattr(lib(), f"emu_pad_texture_{self.sfx}")(_ptr(dense, self.real), _ptr(self.tex[which], self.real),
+                                                      self._g, rb, re, self.nfields, ctypes.byref(negative))
+        return bool(negative.value)
+
+    def unpad_texture(self, which, rows=None) -> np.ndarray:
+        rb, re = rows or (0, self.rows)
+        dense = np.empty((self.nfields, re - rb, self.nx), dtype=self.dtype)
+        getattr(lib(), f"emu_unpad_texture_{self.sfx}")(_ptr(self.tex[which], self.real), _ptr(dense, self.real),
+                                                        self._g, rb, re, self.nfields)
+        return dense[0] if self.nfields == 1 else dense
+
+    def run_pass(self, src, dst, taps, uv_mode, rows=None, wide=False, flavor=-1, admit=-1):
+        first, count = rows or (self.slab[2], self.slab[1])
+        taps = np.ascontiguousarray(taps, dtype=self.dtype)
+        rc = getattr(lib(), f"emu_pass_{self.sfx}")(
+            _ptr(self.tex[src], self.real), _ptr(self.field, self.real), _ptr(self.tex[dst], self.real),
+            self._g, self.nfields, first, count, _core.mode_code(uv_mode), _ptr(taps, self.real), taps.size,
+            int(wide), flavor, admit)
+        assert rc == 0, "no such formulation"
+
+
+def convolve(texture, u, v, *, kernel, uv_mode="velocity", boundaries=(("closed", "closed"),) * 2,
+             iterations=1, wide=False, flavor=-1, admit=-1) -> np.ndarray:
+    """The whole-image flow of ``run_device`` in lic_api.cu: pack, pad, passes, un-pad."""
+    ny, nx = texture.shape
+    b = Buffers(texture.dtype, ny, nx, _core.wall_codes(boundaries), len(kernel))
+    b.pack_field(u, v)
+    b.pad_texture(texture, 0)
+    src = 0
+    for _ in range(iterations):
+        b.run_pass(src, 1 - src, kernel, uv_mode, wide=wide, flavor=flavor, admit=admit)
+        src = 1 - src
+    return b.unpad_texture(src)

@@ -1,0 +1,194 @@
+// The library's kernels (rlic_b200/csrc/lic_walk.cuh), compiled for the CPU and driven
+// block by block.  TEST INFRASTRUCTURE: see cuda_on_cpu.h.  Built by
+// tests/kernel_emulation/__init__.py into tests/kernel_emulation/libkernel_emulation.so.
+//
+// The launch shapes mirror rlic_b200/csrc/lic_api.cu (launch_pack / launch_pad /
+// launch_unpad / launch_pass); the geometry is not restated here: the tests obtain it
+// from the library itself (rlic_b200_debug_geometry) and pass it in.
+#define RLIC_HOST_EMULATION 1
+#include "../../rlic_b200/csrc/lic_walk.cuh"
+
+#include <algorithm>
+#include <atomic>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+thread_local Dim3 threadIdx, blockIdx, blockDim, gridDim;
+
+namespace {
+
+using rlic::PassGeom;
+
+// geometry as rlic_b200_debug_geometry reports it
+PassGeom geometry_from(const int64_t *v)
+{
+    PassGeom g{};
+    g.nx = (int)v[0];
+    g.pitch = (int)v[1];
+    g.rows = (int)v[2];
+    g.field_stride = v[3];
+    g.j_below_to = (int)v[4];
+    g.j_above_to = (int)v[5];
+    g.i_below_to = (int)v[6];
+    g.i_above_to = (int)v[7];
+    g.lo_wall = (int)v[8];
+    g.hi_wall = (int)v[9];
+    return g;
+}
+
+unsigned stream_blocks(long long items)
+{
+    return (unsigned)std::max<long long>(1, std::min<long long>((items + 255) / 256, 148 * 16));
+}
+
+// Runs `body()` once per (block, thread) of a 1-D launch, blocks spread over host threads.
+// The kernels involved never synchronise within a block, so threads run to completion
+// one after another.
+template <typename Body> void launch(unsigned blocks, unsigned threads, Body body)
+{
+    const unsigned workers = std::max(1u, std::min(blocks, std::thread::hardware_concurrency()));
+    std::atomic<unsigned> next{0};
+    auto run = [&] {
+        gridDim = {blocks, 1, 1};
+        blockDim = {threads, 1, 1};
+        for (unsigned b = next.fetch_add(1); b < blocks; b = next.fetch_add(1)) {
+            blockIdx = {b, 0, 0};
+            for (unsigned t = 0; t < threads; ++t) {
+                threadIdx = {t, 0, 0};
+                body();
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (unsigned w = 1; w < workers; ++w) pool.emplace_back(run);
+    run();
+    for (auto &th : pool) th.join();
+}
+
+template <typename T>
+void pack_field(const T *u, const T *v, T *field, const int64_t *geom, int64_t rb, int64_t re, int64_t nfields)
+{
+    const PassGeom g = geometry_from(geom);
+    if (re <= rb || nfields <= 0) return;
+    auto *f = reinterpret_cast<rlic::PackedField<T> *>(field);
+    launch(stream_blocks((re - rb + 2) * g.pitch * nfields), 256,
+           [&] { rlic::pack_field_kernel<T>(u, v, f, g, (int)rb, (int)re, (long long)nfields); });
+}
+
+template <typename T>
+void pad_texture(const T *dense, T *padded, const int64_t *geom, int64_t rb, int64_t re, int64_t nfields,
+                 int *negative)
+{
+    const PassGeom g = geometry_from(geom);
+    if (re <= rb || nfields <= 0) return;
+    launch(stream_blocks((re - rb + 2) * g.pitch * nfields), 256,
+           [&] { rlic::pad_texture_kernel<T>(dense, padded, g, (int)rb, (int)re, (long long)nfields, negative); });
+}
+
+template <typename T>
+void unpad_texture(const T *padded, T *dense, const int64_t *geom, int64_t rb, int64_t re, int64_t nfields)
+{
+    const PassGeom g = geometry_from(geom);
+    if (re <= rb || nfields <= 0) return;
+    launch(stream_blocks((re - rb) * g.nx * nfields), 256,
+           [&] { rlic::unpad_texture_kernel<T>(padded, dense, g, (int)rb, (int)re, (long long)nfields); });
+}
+
+constexpr int kDefault = -1;
+
+// One pass, as launch_pass() issues it.  flavor / admit: kDefault selects the library's
+// per-type tuning (rlic::Tune), other values pick a formulation explicitly.
+template <typename T, bool POL, typename Taps, typename Idx, int FLAVOR, int ADMIT>
+void run_pass(const T *tex, const T *field, T *out, const PassGeom &g, const Taps &taps, int ntaps,
+              unsigned blocks)
+{
+    using Tn = rlic::Tune<T, POL>;
+    auto *f = reinterpret_cast<const rlic::PackedField<T> *>(field);
+    launch(blocks, rlic::kThreads, [&] {
+        rlic::lic_pass_kernel<T, POL, Taps, Idx, rlic::kTileW, rlic::kTileH, Tn::unroll, Tn::min_blocks,
+                              FLAVOR, ADMIT>(tex, f, out, g, taps, ntaps);
+    });
+}
+
+// An explicitly chosen formulation (32-bit indices, taps in the parameter block only).
+template <typename T, bool POL, typename Taps>
+int pick_formulation(const T *tex, const T *field, T *out, const PassGeom &g, const Taps &taps, int ntaps,
+                     unsigned blocks, int flavor, int admit)
+{
+#define RLIC_CASE(F, A) \
+    if (flavor == F && admit == A) { run_pass<T, POL, Taps, int, F, A>(tex, field, out, g, taps, ntaps, blocks); return 0; }
+    RLIC_CASE(0, 0) RLIC_CASE(0, 1) RLIC_CASE(0, 2) RLIC_CASE(0, 3)
+    RLIC_CASE(1, 0) RLIC_CASE(1, 1) RLIC_CASE(1, 2) RLIC_CASE(1, 3)
+#undef RLIC_CASE
+    return 1;
+}
+
+// The library's own choice (rlic::Tune), as launch_pass() dispatches it.
+template <typename T, bool POL, typename Taps>
+int tuned(const T *tex, const T *field, T *out, const PassGeom &g, const Taps &taps, int ntaps, unsigned blocks,
+          int wide)
+{
+    using Tn = rlic::Tune<T, POL>;
+    if (wide) run_pass<T, POL, Taps, long long, Tn::flavor, Tn::admit>(tex, field, out, g, taps, ntaps, blocks);
+    else run_pass<T, POL, Taps, int, Tn::flavor, Tn::admit>(tex, field, out, g, taps, ntaps, blocks);
+    return 0;
+}
+
+template <typename T>
+int pass(const T *tex, const T *field, T *out, const int64_t *geom, int64_t nfields, int64_t first_row,
+         int64_t out_rows, int uv_mode, const T *host_taps, int64_t klen, int wide, int flavor, int admit)
+{
+    PassGeom g = geometry_from(geom);
+    if (out_rows <= 0 || g.nx <= 0 || nfields <= 0) return 0;
+    g.first_row = (int)first_row;
+    g.out_rows = (int)out_rows;
+    g.tiles_x = (g.nx + rlic::kTileW - 1) / rlic::kTileW;
+    const int64_t tiles_y = (out_rows + rlic::kTileH - 1) / rlic::kTileH;
+    const int64_t per_field = tiles_y * g.tiles_x;
+    g.tiles_per_field = (int)per_field;
+    const unsigned blocks = (unsigned)(per_field * nfields);
+    const bool pol = uv_mode == 1;
+    const bool chosen = flavor != kDefault || admit != kDefault;
+
+    constexpr int kMaxParam = rlic::kParamTapBytes / (int)sizeof(T);
+    using PT = rlic::ParamTaps<T, kMaxParam>;
+    using GT = rlic::GlobalTaps<T>;
+    const int ntaps = (int)klen;
+    if (klen <= kMaxParam) {
+        PT pt;
+        std::memset(pt.w, 0, sizeof pt.w);
+        std::memcpy(pt.w, host_taps, sizeof(T) * (size_t)klen);
+        if (chosen) {
+            if (wide) return 1;
+            return pol ? pick_formulation<T, true, PT>(tex, field, out, g, pt, ntaps, blocks, flavor, admit)
+                       : pick_formulation<T, false, PT>(tex, field, out, g, pt, ntaps, blocks, flavor, admit);
+        }
+        return pol ? tuned<T, true, PT>(tex, field, out, g, pt, ntaps, blocks, wide)
+                   : tuned<T, false, PT>(tex, field, out, g, pt, ntaps, blocks, wide);
+    }
+    if (chosen) return 1;
+    const GT gt{host_taps};
+    return pol ? tuned<T, true, GT>(tex, field, out, g, gt, ntaps, blocks, wide)
+               : tuned<T, false, GT>(tex, field, out, g, gt, ntaps, blocks, wide);
+}
+
+}  // namespace
+
+#define EMU_DEFINE(SFX, T)                                                                                  \
+    extern "C" void emu_pack_field_##SFX(const T *u, const T *v, T *field, const int64_t *geom, int64_t rb,  \
+                                         int64_t re, int64_t nfields)                                        \
+    { pack_field<T>(u, v, field, geom, rb, re, nfields); }                                                   \
+    extern "C" void emu_pad_texture_##SFX(const T *dense, T *padded, const int64_t *geom, int64_t rb,        \
+                                          int64_t re, int64_t nfields, int *negative)                        \
+    { pad_texture<T>(dense, padded, geom, rb, re, nfields, negative); }                                      \
+    extern "C" void emu_unpad_texture_##SFX(const T *padded, T *dense, const int64_t *geom, int64_t rb,      \
+                                            int64_t re, int64_t nfields)                                     \
+    { unpad_texture<T>(padded, dense, geom, rb, re, nfields); }                                              \
+    extern "C" int emu_pass_##SFX(const T *tex, const T *field, T *out, const int64_t *geom, int64_t nfields, \
+                                  int64_t first_row, int64_t out_rows, int uv_mode, const T *taps,           \
+                                  int64_t klen, int wide, int flavor, int admit)                             \
+    { return pass<T>(tex, field, out, geom, nfields, first_row, out_rows, uv_mode, taps, klen, wide, flavor, admit); }
+
+EMU_DEFINE(f32, float)
+EMU_DEFINE(f64, double)
