@@ -30,7 +30,8 @@
  *
  * Arithmetic contract: the kernels evaluate the reference's default feature
  * set (fma + branchless, Cargo.toml:28) operation by operation in the input
- * dtype, so results are bit-identical to that build on the same inputs.
+ * dtype, so results are bit-identical to that build on the same inputs;
+ * rlic_b200_set_arithmetic() selects the `fma`-only build instead.
  */
 #ifndef RLIC_B200_H
 #define RLIC_B200_H
@@ -61,6 +62,21 @@ const char *rlic_b200_last_error(void);
 
 /* Number of visible CUDA devices (0 when there is no driver/GPU; never fails). */
 int rlic_b200_device_count(void);
+
+/* Which build of the reference the kernels reproduce bit for bit.  The crate's features
+ * (Cargo.toml:27-30) change one function, the time to the next pixel edge
+ * (lib.rs:157-180), and the builds in circulation differ in them:
+ *   RLIC_B200_ARITH_FMA_BRANCHLESS  `fma` + `branchless`: the crate default, i.e. a build
+ *                                   from source / the sdist, and the aarch64 wheels
+ *                                   (.github/workflows/cd.yml:93,143,210).  Default here.
+ *   RLIC_B200_ARITH_FMA             `fma` alone: the x86-64 wheels (cd.yml:89,139,210).
+ * The two agree on almost every pixel (a last-bit difference in an edge time matters only
+ * where it flips a `tx < ty` decision).  Process-wide; takes effect for calls that start
+ * after it returns, so set it before computing rather than concurrently with calls. */
+#define RLIC_B200_ARITH_FMA_BRANCHLESS 0
+#define RLIC_B200_ARITH_FMA 1
+int rlic_b200_set_arithmetic(int which);
+int rlic_b200_get_arithmetic(void);
 
 /* Number of kernel launches issued by this library since it was loaded
  * (all threads, all devices).  bench.py reads it around the timed region. */

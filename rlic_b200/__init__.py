@@ -12,6 +12,9 @@ Anne Archibald) are the behavioural reference only; see NOTICE.
 __all__ = [
     "convolve",
     "convolve_batch",
+    "get_arithmetic",
+    "set_arithmetic",
 ]
 
+from rlic_b200._core import get_arithmetic, set_arithmetic
 from rlic_b200._lib import convolve, convolve_batch

@@ -31,6 +31,7 @@ _LIB_PATH = Path(__file__).resolve().parent / "librlic_b200.so"
 
 OK, EINVAL, ENODEVICE, ECUDA, ESHARD = range(5)
 ABI_VERSION = 2
+ARITHMETICS = {"fma+branchless": 0, "fma": 1}   # RLIC_B200_ARITH_* in include/rlic_b200.h
 
 _MODE_CODE = {"velocity": 0, "polarization": 1}
 _WALL_CODE = {"closed": 0, "periodic": 1}
@@ -86,6 +87,14 @@ def _load() -> ctypes.CDLL:
     cdll.rlic_b200_result_free.restype = None
     cdll.rlic_b200_set_device.argtypes = [_int]
     cdll.rlic_b200_set_device.restype = _int
+    cdll.rlic_b200_set_arithmetic.argtypes = [_int]
+    cdll.rlic_b200_set_arithmetic.restype = _int
+    cdll.rlic_b200_get_arithmetic.restype = _int
+    requested = os.environ.get("RLIC_B200_ARITHMETIC")
+    if requested:
+        if requested not in ARITHMETICS:
+            raise ImportError(f"RLIC_B200_ARITHMETIC={requested!r}: expected one of {sorted(ARITHMETICS)}")
+        cdll.rlic_b200_set_arithmetic(ARITHMETICS[requested])
     for sfx, real in (("f32", ctypes.c_float), ("f64", ctypes.c_double)):
         for name, argtypes in _signatures(real).items():
             fn = getattr(cdll, f"rlic_b200_{name}_{sfx}")
@@ -106,6 +115,23 @@ class _LazyLib:
 
 
 lib = _LazyLib()
+
+
+def set_arithmetic(name: str) -> None:
+    """Choose which build of the reference the kernels reproduce bit for bit
+    (include/rlic_b200.h): ``"fma+branchless"`` -- the crate default, i.e. source
+    builds and the aarch64 wheels, the default here -- or ``"fma"``, the x86-64
+    wheels.  Process-wide; also settable with ``RLIC_B200_ARITHMETIC``."""
+    try:
+        code = ARITHMETICS[name]
+    except KeyError:
+        raise ValueError(f"unknown arithmetic {name!r}: expected one of {sorted(ARITHMETICS)}") from None
+    check(lib.rlic_b200_set_arithmetic(code))
+
+
+def get_arithmetic() -> str:
+    code = int(lib.rlic_b200_get_arithmetic())
+    return next(name for name, c in ARITHMETICS.items() if c == code)
 
 
 def device_count() -> int:

@@ -29,6 +29,7 @@ thread_local std::string tls_error;
 thread_local int tls_device = 0;
 std::atomic<int64_t> g_launches{0};
 std::atomic<int> g_force_wide{0};   // testing hook: use 64-bit element indices for any size
+std::atomic<int> g_arithmetic{RLIC_B200_ARITH_FMA_BRANCHLESS};   // which reference build to reproduce
 
 int fail(int code, const char *fmt, ...)
 {
@@ -241,10 +242,16 @@ template <typename T> struct TapSet {
 
 template <typename T, bool POL, typename Taps, typename Idx>
 cudaError_t launch_one(const T *tex, const Field<T> *field, T *out, const PassGeom &g,
-                       const Taps &taps, int ntaps, unsigned blocks, cudaStream_t stream)
+                       const Taps &taps, int ntaps, unsigned blocks, bool branchless, cudaStream_t stream)
 {
-    rlic::lic_pass_kernel<T, POL, Taps, Idx>
-        <<<blocks, rlic::kThreads, 0, stream>>>(tex, field, out, g, taps, ntaps);
+    using Tn = rlic::Tune<T, POL>;
+    if (branchless)
+        rlic::lic_pass_kernel<T, POL, Taps, Idx>
+            <<<blocks, rlic::kThreads, 0, stream>>>(tex, field, out, g, taps, ntaps);
+    else
+        rlic::lic_pass_kernel<T, POL, Taps, Idx, rlic::kTileW, rlic::kTileH, Tn::unroll, Tn::min_blocks,
+                              Tn::flavor, Tn::admit, false>
+            <<<blocks, rlic::kThreads, 0, stream>>>(tex, field, out, g, taps, ntaps);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }
@@ -271,10 +278,11 @@ int launch_pass(const T *tex, const Field<T> *field, T *out, PassGeom g, int64_t
     const bool wide = g.field_stride >= (int64_t)INT_MAX ||
                       g_force_wide.load(std::memory_order_relaxed) != 0;
     const bool pol = uv_mode == RLIC_B200_POLARIZATION;
+    const bool branchless = g_arithmetic.load(std::memory_order_relaxed) == RLIC_B200_ARITH_FMA_BRANCHLESS;
 
     cudaError_t e;
 #define RLIC_LAUNCH(POL, TAPS, TAPV, IDX) \
-    e = launch_one<T, POL, TAPS, IDX>(tex, field, out, g, TAPV, taps.ntaps, (unsigned)blocks, stream)
+    e = launch_one<T, POL, TAPS, IDX>(tex, field, out, g, TAPV, taps.ntaps, (unsigned)blocks, branchless, stream)
     using PT = rlic::ParamTaps<T, TapSet<T>::kMaxParam>;
     using GT = rlic::GlobalTaps<T>;
     const GT gt{static_cast<const T *>(taps.global.p)};
@@ -767,6 +775,17 @@ int rlic_b200_debug_wall_cell(int64_t ny, int64_t nx, int64_t row0, int64_t nrow
     out[4] = s.shift;
     return RLIC_B200_OK;
 }
+
+int rlic_b200_set_arithmetic(int which)
+{
+    tls_error.clear();
+    if (which != RLIC_B200_ARITH_FMA_BRANCHLESS && which != RLIC_B200_ARITH_FMA)
+        return fail(RLIC_B200_EINVAL, "unknown arithmetic %d", which);
+    g_arithmetic.store(which, std::memory_order_relaxed);
+    return RLIC_B200_OK;
+}
+
+int rlic_b200_get_arithmetic(void) { return g_arithmetic.load(std::memory_order_relaxed); }
 
 int rlic_b200_debug_geometry(int64_t ny, int64_t nx, int64_t row0, int64_t nrows, int64_t halo_lo,
                              int64_t halo_hi, int x_left, int x_right, int y_left, int y_right,

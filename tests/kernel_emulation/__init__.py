@@ -51,7 +51,7 @@ def lib() -> ctypes.CDLL:
             getattr(cdll, f"emu_unpad_texture_{sfx}").argtypes = [p, p, g, _i64, _i64, _i64]
             getattr(cdll, f"emu_unpad_texture_{sfx}").restype = None
             getattr(cdll, f"emu_pass_{sfx}").argtypes = [p, p, p, g, _i64, _i64, _i64, _int, p, _i64,
-                                                        _int, _int, _int]
+                                                        _int, _int, _int, _int]
             getattr(cdll, f"emu_pass_{sfx}").restype = _int
         _lib = cdll
     return _lib
@@ -110,18 +110,18 @@ class Buffers:
                                                         self._g, rb, re, self.nfields)
         return dense[0] if self.nfields == 1 else dense
 
-    def run_pass(self, src, dst, taps, uv_mode, rows=None, wide=False, flavor=-1, admit=-1):
+    def run_pass(self, src, dst, taps, uv_mode, rows=None, wide=False, flavor=-1, admit=-1, branchless=True):
         first, count = rows or (self.slab[2], self.slab[1])
         taps = np.ascontiguousarray(taps, dtype=self.dtype)
         rc = getattr(lib(), f"emu_pass_{self.sfx}")(
             _ptr(self.tex[src], self.real), _ptr(self.field, self.real), _ptr(self.tex[dst], self.real),
             self._g, self.nfields, first, count, _core.mode_code(uv_mode), _ptr(taps, self.real), taps.size,
-            int(wide), flavor, admit)
+            int(wide), flavor, admit, int(branchless))
         assert rc == 0, "no such formulation"
 
 
 def convolve(texture, u, v, *, kernel, uv_mode="velocity", boundaries=(("closed", "closed"),) * 2,
-             iterations=1, wide=False, flavor=-1, admit=-1) -> np.ndarray:
+             iterations=1, wide=False, flavor=-1, admit=-1, branchless=True) -> np.ndarray:
     """The whole-image flow of ``run_device`` in lic_api.cu: pack, pad, passes, un-pad."""
     ny, nx = texture.shape
     b = Buffers(texture.dtype, ny, nx, _core.wall_codes(boundaries), len(kernel))
@@ -129,6 +129,6 @@ def convolve(texture, u, v, *, kernel, uv_mode="velocity", boundaries=(("closed"
     b.pad_texture(texture, 0)
     src = 0
     for _ in range(iterations):
-        b.run_pass(src, 1 - src, kernel, uv_mode, wide=wide, flavor=flavor, admit=admit)
+        b.run_pass(src, 1 - src, kernel, uv_mode, wide=wide, flavor=flavor, admit=admit, branchless=branchless)
         src = 1 - src
     return b.unpad_texture(src)

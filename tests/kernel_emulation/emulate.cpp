@@ -99,7 +99,7 @@ constexpr int kDefault = -1;
 
 // One pass, as launch_pass() issues it.  flavor / admit: kDefault selects the library's
 // per-type tuning (rlic::Tune), other values pick a formulation explicitly.
-template <typename T, bool POL, typename Taps, typename Idx, int FLAVOR, int ADMIT>
+template <typename T, bool POL, typename Taps, typename Idx, int FLAVOR, int ADMIT, bool BRANCHLESS = true>
 void run_pass(const T *tex, const T *field, T *out, const PassGeom &g, const Taps &taps, int ntaps,
               unsigned blocks)
 {
@@ -107,7 +107,7 @@ void run_pass(const T *tex, const T *field, T *out, const PassGeom &g, const Tap
     auto *f = reinterpret_cast<const rlic::PackedField<T> *>(field);
     launch(blocks, rlic::kThreads, [&] {
         rlic::lic_pass_kernel<T, POL, Taps, Idx, rlic::kTileW, rlic::kTileH, Tn::unroll, Tn::min_blocks,
-                              FLAVOR, ADMIT>(tex, f, out, g, taps, ntaps);
+                              FLAVOR, ADMIT, BRANCHLESS>(tex, f, out, g, taps, ntaps);
     });
 }
 
@@ -127,17 +127,23 @@ int pick_formulation(const T *tex, const T *field, T *out, const PassGeom &g, co
 // The library's own choice (rlic::Tune), as launch_pass() dispatches it.
 template <typename T, bool POL, typename Taps>
 int tuned(const T *tex, const T *field, T *out, const PassGeom &g, const Taps &taps, int ntaps, unsigned blocks,
-          int wide)
+          int wide, int branchless)
 {
     using Tn = rlic::Tune<T, POL>;
-    if (wide) run_pass<T, POL, Taps, long long, Tn::flavor, Tn::admit>(tex, field, out, g, taps, ntaps, blocks);
-    else run_pass<T, POL, Taps, int, Tn::flavor, Tn::admit>(tex, field, out, g, taps, ntaps, blocks);
+    if (branchless) {
+        if (wide) run_pass<T, POL, Taps, long long, Tn::flavor, Tn::admit>(tex, field, out, g, taps, ntaps, blocks);
+        else run_pass<T, POL, Taps, int, Tn::flavor, Tn::admit>(tex, field, out, g, taps, ntaps, blocks);
+    } else {
+        if (wide) run_pass<T, POL, Taps, long long, Tn::flavor, Tn::admit, false>(tex, field, out, g, taps, ntaps, blocks);
+        else run_pass<T, POL, Taps, int, Tn::flavor, Tn::admit, false>(tex, field, out, g, taps, ntaps, blocks);
+    }
     return 0;
 }
 
 template <typename T>
 int pass(const T *tex, const T *field, T *out, const int64_t *geom, int64_t nfields, int64_t first_row,
-         int64_t out_rows, int uv_mode, const T *host_taps, int64_t klen, int wide, int flavor, int admit)
+         int64_t out_rows, int uv_mode, const T *host_taps, int64_t klen, int wide, int flavor, int admit,
+         int branchless)
 {
     PassGeom g = geometry_from(geom);
     if (out_rows <= 0 || g.nx <= 0 || nfields <= 0) return 0;
@@ -160,17 +166,17 @@ int pass(const T *tex, const T *field, T *out, const int64_t *geom, int64_t nfie
         std::memset(pt.w, 0, sizeof pt.w);
         std::memcpy(pt.w, host_taps, sizeof(T) * (size_t)klen);
         if (chosen) {
-            if (wide) return 1;
+            if (wide || !branchless) return 1;
             return pol ? pick_formulation<T, true, PT>(tex, field, out, g, pt, ntaps, blocks, flavor, admit)
                        : pick_formulation<T, false, PT>(tex, field, out, g, pt, ntaps, blocks, flavor, admit);
         }
-        return pol ? tuned<T, true, PT>(tex, field, out, g, pt, ntaps, blocks, wide)
-                   : tuned<T, false, PT>(tex, field, out, g, pt, ntaps, blocks, wide);
+        return pol ? tuned<T, true, PT>(tex, field, out, g, pt, ntaps, blocks, wide, branchless)
+                   : tuned<T, false, PT>(tex, field, out, g, pt, ntaps, blocks, wide, branchless);
     }
     if (chosen) return 1;
     const GT gt{host_taps};
-    return pol ? tuned<T, true, GT>(tex, field, out, g, gt, ntaps, blocks, wide)
-               : tuned<T, false, GT>(tex, field, out, g, gt, ntaps, blocks, wide);
+    return pol ? tuned<T, true, GT>(tex, field, out, g, gt, ntaps, blocks, wide, branchless)
+               : tuned<T, false, GT>(tex, field, out, g, gt, ntaps, blocks, wide, branchless);
 }
 
 }  // namespace
@@ -187,8 +193,9 @@ int pass(const T *tex, const T *field, T *out, const int64_t *geom, int64_t nfie
     { unpad_texture<T>(padded, dense, geom, rb, re, nfields); }                                              \
     extern "C" int emu_pass_##SFX(const T *tex, const T *field, T *out, const int64_t *geom, int64_t nfields, \
                                   int64_t first_row, int64_t out_rows, int uv_mode, const T *taps,           \
-                                  int64_t klen, int wide, int flavor, int admit)                             \
-    { return pass<T>(tex, field, out, geom, nfields, first_row, out_rows, uv_mode, taps, klen, wide, flavor, admit); }
+                                  int64_t klen, int wide, int flavor, int admit, int branchless)             \
+    { return pass<T>(tex, field, out, geom, nfields, first_row, out_rows, uv_mode, taps, klen, wide, flavor, admit, \
+                     branchless); }
 
 EMU_DEFINE(f32, float)
 EMU_DEFINE(f64, double)

@@ -133,3 +133,33 @@ def test_product_never_imports_the_oracle():
         text = path.read_text()
         assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), path
         assert "liblic_oracle" not in text, path
+
+
+def test_arithmetic_selection_round_trips_and_rejects_unknown_builds():
+    import os
+    import subprocess
+    import sys
+
+    import rlic_b200
+
+    for name, code in _core.ARITHMETICS.items():
+        m = re.search(rf"#define RLIC_B200_ARITH_{name.upper().replace('+', '_')} (\d+)", HEADER)
+        assert int(m.group(1)) == code
+    assert rlic_b200.get_arithmetic() == "fma+branchless"          # the crate default
+    try:
+        rlic_b200.set_arithmetic("fma")
+        assert rlic_b200.get_arithmetic() == "fma"
+        with pytest.raises(ValueError, match="unknown arithmetic"):
+            rlic_b200.set_arithmetic("branchless")
+        assert _core.lib.rlic_b200_set_arithmetic(7) == _core.EINVAL
+        assert rlic_b200.get_arithmetic() == "fma"
+    finally:
+        rlic_b200.set_arithmetic("fma+branchless")
+    # the environment variable is read when the library is first loaded
+    code = "import rlic_b200; print(rlic_b200.get_arithmetic())"
+    env = dict(os.environ, RLIC_B200_ARITHMETIC="fma", PYTHONPATH=str(ROOT))
+    assert subprocess.run([sys.executable, "-c", code], env=env, capture_output=True,
+                          text=True).stdout.strip() == "fma"
+    env["RLIC_B200_ARITHMETIC"] = "nonsense"
+    bad = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
+    assert bad.returncode != 0 and "RLIC_B200_ARITHMETIC" in bad.stderr

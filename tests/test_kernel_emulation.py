@@ -45,8 +45,10 @@ def random_case(shape, dtype, klen, seed, specials=True):
 def check(tex, u, v, kernel, mode="velocity", walls="closed", iterations=1, **how):
     bnd = WALLS[walls]
     got = ke.convolve(tex, u, v, kernel=kernel, uv_mode=mode, boundaries=bnd, iterations=iterations, **how)
+    # oracle variants mirror the crate's features: 3 = fma + branchless (default), 1 = fma alone
+    variant = 3 if how.get("branchless", True) else 1
     want = oracle.convolve(np.ascontiguousarray(tex), np.ascontiguousarray(u), np.ascontiguousarray(v),
-                           kernel=kernel, uv_mode=mode, boundaries=bnd, iterations=iterations)
+                           kernel=kernel, uv_mode=mode, boundaries=bnd, iterations=iterations, variant=variant)
     assert got.dtype == tex.dtype and got.shape == tex.shape
     assert_array_equal(got, want)
     return got
@@ -236,6 +238,53 @@ def test_padding_reports_negative_texture_values_but_not_nan():
     assert b.pad_texture(tex, 0) is True
     tex[11, 8] = -0.0
     assert b.pad_texture(tex, 0) is False
+
+
+# ---- the `fma`-only arithmetic (rlic_b200.set_arithmetic("fma"): the x86-64 wheels' build) ----
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_fma_only_golden_vectors(name):
+    mode, bnd, its = GOLDEN_CASES[name]
+    tex, u, v, kernel = load(name)
+    got = ke.convolve(tex, u, v, kernel=kernel, uv_mode=mode, boundaries=bnd, iterations=its, branchless=False)
+    assert_array_equal(got, expected(name, 1))
+
+
+@pytest.mark.parametrize("seed", range(48))
+def test_fma_only_randomised_configurations(seed):
+    tex, u, v, kernel, mode, walls, its = fuzz_case(seed)
+    with np.errstate(all="ignore"):
+        check(tex, u, v, kernel, mode=mode, walls=walls, iterations=its, branchless=False)
+
+
+@pytest.mark.parametrize("walls", WALLS)
+@pytest.mark.parametrize("mode", ["velocity", "polarization"])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_fma_only_special_pixels(dtype, mode, walls):
+    check(*random_case((45, 70), dtype, 23, seed=11), mode=mode, walls=walls, iterations=2, branchless=False)
+
+
+def test_fma_only_axis_aligned_zero_and_signed_zero_fields():
+    rng = np.random.default_rng(3)
+    tex = rng.random((40, 50))
+    one, zero = np.ones_like(tex), np.zeros_like(tex)
+    k = np.linspace(0.1, 1, 15)
+    for u, v in ((one, zero), (zero, one), (-one, zero), (zero, -one), (one, -zero), (-zero, -one),
+                 (zero, zero), (-zero, zero), (one, -one)):
+        for walls in WALLS:
+            check(tex, u, v, k, walls=walls, branchless=False)
+            check(tex, u, v, k, mode="polarization", walls=walls, branchless=False)
+
+
+def test_fma_only_workloads_and_the_builds_really_differ():
+    w = workloads.readme_example()
+    check(w.texture, w.u, w.v, w.kernel, walls="periodic", iterations=5, branchless=False)
+    w = workloads.vortex_noise(512, iterations=2)
+    default = check(w.texture, w.u, w.v, w.kernel, iterations=2)
+    fma_only = check(w.texture, w.u, w.v, w.kernel, iterations=2, branchless=False, wide=True)
+    differing = np.mean(default != fma_only)
+    # a last-bit difference in an edge time matters where it flips a `tx < ty` decision:
+    # after two passes ~8 % of the pixels of this run differ between the two builds
+    assert 0 < differing < 0.5, differing
 
 
 # ---- row slabs: what rlic_b200.sharded and rlic_b200_pass_slab_* rely on ------------------

@@ -11,6 +11,8 @@ from pathlib import Path
 import numpy as np
 import pytest
 
+from _status import first_gpu_run
+
 ROOT = Path(__file__).resolve().parents[1]
 LIBDIR = ROOT / "rlic_b200"
 N, TAPS = 256, 65
@@ -78,6 +80,7 @@ def test_python_regenerates_the_c_inputs_exactly(client):
     assert first == f"inputs {inputs_checksum():016x}"
 
 
+@first_gpu_run
 @pytest.mark.gpu
 def test_c_client_matches_the_oracle(client):
     import oracle
