@@ -73,6 +73,48 @@ def geometry(ny, nx, slab, walls, klen) -> np.ndarray:
     return out
 
 
+class SlabOps:
+    """The ``ops`` interface of ``rlic_b200.sharded.ShardedConvolver`` (what ``CudaSlabOps``
+    does through the C ABI's slab entry points), on CPU tensors through the emulated kernels."""
+
+    @staticmethod
+    def _np(t):
+        return t.numpy()
+
+    @staticmethod
+    def _geom(plan, walls, klen=1):
+        return geometry(plan.ny, plan.nx, (plan.row0, plan.nrows, plan.halo_lo, plan.halo_hi), walls, klen)
+
+    def pack_field(self, u, v, field, plan, walls):
+        sfx, real = _kind(self._np(u).dtype)
+        g = self._geom(plan, walls)
+        getattr(lib(), f"emu_pack_field_{sfx}")(
+            _ptr(self._np(u), real), _ptr(self._np(v), real), _ptr(self._np(field), real), _ptr(g, _i64),
+            plan.halo_lo, plan.halo_lo + plan.nrows, 1)
+
+    def pad_texture(self, texture, padded, plan, walls):
+        sfx, real = _kind(self._np(texture).dtype)
+        g = self._geom(plan, walls)
+        getattr(lib(), f"emu_pad_texture_{sfx}")(
+            _ptr(self._np(texture), real), _ptr(self._np(padded), real), _ptr(g, _i64),
+            plan.halo_lo, plan.halo_lo + plan.nrows, 1, None)
+
+    def unpad_texture(self, padded, texture, plan, walls):
+        sfx, real = _kind(self._np(texture).dtype)
+        g = self._geom(plan, walls)
+        getattr(lib(), f"emu_unpad_texture_{sfx}")(
+            _ptr(self._np(padded), real), _ptr(self._np(texture), real), _ptr(g, _i64),
+            plan.halo_lo, plan.halo_lo + plan.nrows, 1)
+
+    def pass_rows(self, src, field, dst, plan, a, b, taps, mode, walls):
+        sfx, real = _kind(self._np(src).dtype)
+        g = self._geom(plan, walls, taps.size)
+        rc = getattr(lib(), f"emu_pass_{sfx}")(
+            _ptr(self._np(src), real), _ptr(self._np(field), real), _ptr(self._np(dst), real), _ptr(g, _i64), 1,
+            plan.halo_lo + a, b - a, mode, _ptr(taps, real), taps.size, 0, -1, -1, 1)
+        assert rc == 0
+
+
 class Buffers:
     """Padded device-style buffers of one slab (or a batch of whole images), on the host."""
 

@@ -240,6 +240,30 @@ def test_padding_reports_negative_texture_values_but_not_nan():
     assert b.pad_texture(tex, 0) is False
 
 
+@pytest.mark.parametrize("walls", WALLS)
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_band_by_band_upload_builds_the_same_buffers(dtype, walls):
+    """The host path uploads an image in row bands (convolve_host in lic_api.cu): packing and
+    padding band by band, in any order, must leave exactly the buffers of a single call --
+    including the guard rows, whose content comes from the first / last image row."""
+    tex, u, v, kernel = random_case((37, 29), dtype, 9, seed=3)
+    codes = _core.wall_codes(WALLS[walls])
+    whole = ke.Buffers(dtype, 37, 29, codes, kernel.size)
+    whole.pack_field(u, v)
+    whole.pad_texture(tex, 0)
+    banded = ke.Buffers(dtype, 37, 29, codes, kernel.size)
+    for rb, re in ((20, 31), (0, 7), (31, 37), (7, 20)):
+        banded.pack_field(u[rb:re], v[rb:re], rows=(rb, re))
+        banded.pad_texture(tex[rb:re], 0, rows=(rb, re))
+    assert_array_equal(banded.field.view(np.uint8), whole.field.view(np.uint8))
+    # texture cells no walker can reach (corners, pad columns of guard rows) are never written
+    reach_w, reach_b = ~np.isnan(whole.tex[0]), ~np.isnan(banded.tex[0])
+    tex_nan = np.isnan(tex)
+    if not tex_nan.any():
+        assert_array_equal(reach_w, reach_b)
+    assert_array_equal(banded.tex[0].view(np.uint8), whole.tex[0].view(np.uint8))
+
+
 # ---- the `fma`-only arithmetic (rlic_b200.set_arithmetic("fma"): the x86-64 wheels' build) ----
 @pytest.mark.parametrize("name", GOLDEN_CASES)
 def test_fma_only_golden_vectors(name):

@@ -2,10 +2,11 @@
 
 The halo plan, the message ordering, the padded-buffer row ranges and the
 strip/interior decomposition of ``rlic_b200.sharded`` run for real; only the
-per-slab compute steps are replaced by the CPU oracle (injected through ``ops`` —
-test-only use of the oracle; the product default is the CUDA slab API).  Buffers
-are poisoned outside the rows a rank legitimately holds, so a missing or
-misplaced halo shows up as a mismatch.
+per-slab compute steps are replaced (injected through ``ops``; the product
+default is the CUDA slab API), in two ways: by the CPU oracle on poisoned
+buffers, so that a missing or misplaced halo shows up as a mismatch; and by the
+library's own kernels compiled for the CPU (tests/kernel_emulation), so that the
+real packed records, sentinels and wall cells are what travels.
 The sharded result must equal the unsharded oracle bit for bit.
 """
 
@@ -140,7 +141,18 @@ class OracleSlabOps:
                          {plan.halo_lo + a + k: band[k] for k in range(b - a)})
 
 
-def _worker(rank, world, port, case, queue):
+def _make_ops(kind):
+    if kind == "oracle stand-in":
+        return OracleSlabOps()
+    # the library's own kernels, compiled for the CPU (tests/kernel_emulation): real packed
+    # records, sentinels and wall cells travel through the exchange
+    sys.path.insert(0, str(ROOT / "tests"))
+    import kernel_emulation
+
+    return kernel_emulation.SlabOps()
+
+
+def _worker(rank, world, port, case, queue, ops_kind="oracle stand-in"):
     try:
         os.environ["MASTER_ADDR"] = "127.0.0.1"
         os.environ["MASTER_PORT"] = str(port)
@@ -158,7 +170,7 @@ def _worker(rank, world, port, case, queue):
         kernel = (rng.random(klen) + 0.1).astype(dtype)
 
         sc = ShardedConvolver(ny, nx, kernel=kernel, uv_mode=mode, boundaries=boundaries,
-                              ops=OracleSlabOps())
+                              ops=_make_ops(ops_kind))
         p = sc.plan
         assert (p.row0, p.row1) == (ny * rank // world, ny * (rank + 1) // world)
         mine = slice(p.row0, p.row1)
@@ -195,13 +207,14 @@ CASES = {
 }
 
 
+@pytest.mark.parametrize("ops_kind", ["oracle stand-in", "emulated kernels"])
 @pytest.mark.parametrize("name", CASES)
-def test_sharded_equals_unsharded(name):
+def test_sharded_equals_unsharded(name, ops_kind):
     world, case = CASES[name]
     ctx = mp.get_context("spawn")
     queue = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, case, queue)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, case, queue, ops_kind)) for r in range(world)]
     for pr in procs:
         pr.start()
     try:
