@@ -53,8 +53,20 @@ def lib() -> ctypes.CDLL:
             getattr(cdll, f"emu_pass_{sfx}").argtypes = [p, p, p, g, _i64, _i64, _i64, _int, p, _i64,
                                                         _int, _int, _int, _int]
             getattr(cdll, f"emu_pass_{sfx}").restype = _int
+        cdll.emu_step_counts.argtypes = [ctypes.POINTER(ctypes.c_ulonglong), _int]
+        cdll.emu_step_counts.restype = None
         _lib = cdll
     return _lib
+
+
+def step_counts(reset: bool = True) -> dict:
+    """How the steps of the passes run so far were decided: ``step`` all of them, ``declined``
+    the ones the fast path handed over, of which ``wall`` crossed a wall (sentinel cell) and
+    ``generic`` took the generic step (a wall crossing usually continues on the fast path's
+    behalf through the generic step too)."""
+    out = (ctypes.c_ulonglong * 4)()
+    lib().emu_step_counts(out, int(reset))
+    return dict(zip(("step", "declined", "wall", "generic"), (int(x) for x in out)))
 
 
 def _kind(dtype):

@@ -68,6 +68,13 @@ template <typename T> static inline T __ldg(const T *p) { return *p; }
 static inline unsigned max(unsigned a, unsigned b) { return a > b ? a : b; }
 
 namespace emulated {
+// How the steps of a pass were decided (see lic_walk.cuh: half_walk): every step, the ones
+// the fast path declined, of those the wall crossings (sentinel cells) and the ones that
+// went through the generic step (the rest stopped on a NaN).
+struct StepCounts { unsigned long long step, declined, wall, generic; };
+extern thread_local StepCounts step_counts;
+#define RLIC_EMU_EVENT(which) (++emulated::step_counts.which)
+
 static inline float rcp_approx(float b) { return (float)(1.0 / (double)b); }
 static inline double rcp_approx(double b) { return __hiloint2double(__double2hiint(1.0 / b), 0); }
 }  // namespace emulated

@@ -15,6 +15,7 @@
 #include <vector>
 
 thread_local Dim3 threadIdx, blockIdx, blockDim, gridDim;
+thread_local emulated::StepCounts emulated::step_counts;
 
 namespace {
 
@@ -45,6 +46,8 @@ unsigned stream_blocks(long long items)
 // Runs `body()` once per (block, thread) of a 1-D launch, blocks spread over host threads.
 // The kernels involved never synchronise within a block, so threads run to completion
 // one after another.
+std::atomic<unsigned long long> g_counts[4];
+
 template <typename Body> void launch(unsigned blocks, unsigned threads, Body body)
 {
     const unsigned workers = std::max(1u, std::min(blocks, std::thread::hardware_concurrency()));
@@ -52,6 +55,7 @@ template <typename Body> void launch(unsigned blocks, unsigned threads, Body bod
     auto run = [&] {
         gridDim = {blocks, 1, 1};
         blockDim = {threads, 1, 1};
+        emulated::step_counts = {};
         for (unsigned b = next.fetch_add(1); b < blocks; b = next.fetch_add(1)) {
             blockIdx = {b, 0, 0};
             for (unsigned t = 0; t < threads; ++t) {
@@ -59,6 +63,10 @@ template <typename Body> void launch(unsigned blocks, unsigned threads, Body bod
                 body();
             }
         }
+        g_counts[0] += emulated::step_counts.step;
+        g_counts[1] += emulated::step_counts.declined;
+        g_counts[2] += emulated::step_counts.wall;
+        g_counts[3] += emulated::step_counts.generic;
     };
     std::vector<std::thread> pool;
     for (unsigned w = 1; w < workers; ++w) pool.emplace_back(run);
@@ -180,6 +188,15 @@ int pass(const T *tex, const T *field, T *out, const int64_t *geom, int64_t nfie
 }
 
 }  // namespace
+
+// Step counters accumulated over every pass since the last reset.
+extern "C" void emu_step_counts(unsigned long long *out, int reset)
+{
+    for (int i = 0; i < 4; ++i) {
+        out[i] = g_counts[i].load();
+        if (reset) g_counts[i].store(0);
+    }
+}
 
 #define EMU_DEFINE(SFX, T)                                                                                  \
     extern "C" void emu_pack_field_##SFX(const T *u, const T *v, T *field, const int64_t *geom, int64_t rb,  \

@@ -240,6 +240,28 @@ def test_padding_reports_negative_texture_values_but_not_nan():
     assert b.pad_texture(tex, 0) is False
 
 
+def test_step_counters_tell_how_steps_were_decided():
+    ke.step_counts()                                     # reset
+    tex = np.random.default_rng(0).random((32, 48))
+    ones, zeros = np.ones_like(tex), np.zeros_like(tex)
+    k = np.ones(9)
+    # uniform flow to the right, periodic: every step is a fast-path step except the wall crossings
+    ke.convolve(tex, ones, zeros, kernel=k, boundaries=WALLS["periodic"])
+    c = ke.step_counts()
+    assert c["step"] == 32 * 48 * 8
+    # a crossing is resolved at the start of the step after the one that left the image: the
+    # forward walkers from columns 45..47 and the backward ones from 0..2 have such a step left
+    assert c["wall"] == 32 * (3 + 3) and c["declined"] == c["wall"] == c["generic"]
+    # a field of NaN stops every walker at its first step; nothing reaches the generic step
+    ke.convolve(tex, ones * np.nan, zeros, kernel=k)
+    c = ke.step_counts()
+    assert c["step"] == c["declined"] == 32 * 48 * 2 and c["generic"] == 0 and c["wall"] == 0
+    # zero field: every step is declined (flagged pixel) and the generic step stays put
+    ke.convolve(tex, zeros, zeros, kernel=k)
+    c = ke.step_counts()
+    assert c["step"] == c["declined"] == c["generic"] == 32 * 48 * 8 and c["wall"] == 0
+
+
 @pytest.mark.parametrize("walls", WALLS)
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 def test_band_by_band_upload_builds_the_same_buffers(dtype, walls):
