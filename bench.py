@@ -416,7 +416,8 @@ def run_ours(args) -> dict:
     e2e = {"value": e2e_val, "unit": METRIC, "h2d_bytes_per_step": h2d * world,
            "d2h_bytes_per_step": d2h * world, "ms_per_step": e2e_ms,
            "api": "rlic_b200.convolve(numpy arrays in pinned host memory)" if world == 1
-                  else "per rank: pinned host slab -> ShardedConvolver -> pinned host slab"}
+                  else "per rank: pinned host slab -> ShardedConvolver -> pinned host slab",
+           "schedule": rlic_b200.get_schedule(), "arithmetic": rlic_b200.get_arithmetic()}
 
     line = {
         "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps,

@@ -78,6 +78,29 @@ int rlic_b200_device_count(void);
 int rlic_b200_set_arithmetic(int which);
 int rlic_b200_get_arithmetic(void);
 
+/* How the host entry points (rlic_b200_convolve_*, _convolve_checked_*) order their work
+ * for a single large image.  Both upload, compute and download in row bands and give the
+ * same bits; they differ in how much of the transfers hides behind the passes.
+ *   RLIC_B200_SCHEDULE_TRAILING   pass 1 follows the uploads band by band, the middle
+ *                                 passes run over the whole image, the last pass releases
+ *                                 bands to the download.  Default.
+ *   RLIC_B200_SCHEDULE_WAVEFRONT  every pass follows the uploads band by band (pass p of
+ *                                 band b runs once pass p-1 of bands b-1..b+1 is done), so
+ *                                 early bands finish, and leave, while late bands are still
+ *                                 arriving.  Used when y is not periodic and iterations >= 2;
+ *                                 otherwise the call falls back to the trailing order.
+ * Process-wide, like rlic_b200_set_arithmetic. */
+#define RLIC_B200_SCHEDULE_TRAILING 0
+#define RLIC_B200_SCHEDULE_WAVEFRONT 1
+int rlic_b200_set_schedule(int which);
+int rlic_b200_get_schedule(void);
+
+/* Testing hook (host code only): the (pass, band) launch order of the wavefront schedule
+ * for `nbands` bands and `iterations` passes, as pairs pass_band[2k] = pass (1-based),
+ * pass_band[2k+1] = band; returns the number of pairs (at most `capacity` are written). */
+int64_t rlic_b200_debug_wavefront_order(int64_t nbands, int64_t iterations, int32_t *pass_band,
+                                        int64_t capacity);
+
 /* Number of kernel launches issued by this library since it was loaded
  * (all threads, all devices).  bench.py reads it around the timed region. */
 int64_t rlic_b200_launch_count(void);

@@ -13,8 +13,10 @@ __all__ = [
     "convolve",
     "convolve_batch",
     "get_arithmetic",
+    "get_schedule",
     "set_arithmetic",
+    "set_schedule",
 ]
 
-from rlic_b200._core import get_arithmetic, set_arithmetic
+from rlic_b200._core import get_arithmetic, get_schedule, set_arithmetic, set_schedule
 from rlic_b200._lib import convolve, convolve_batch

@@ -32,6 +32,7 @@ _LIB_PATH = Path(__file__).resolve().parent / "librlic_b200.so"
 OK, EINVAL, ENODEVICE, ECUDA, ESHARD = range(5)
 ABI_VERSION = 2
 ARITHMETICS = {"fma+branchless": 0, "fma": 1}   # RLIC_B200_ARITH_* in include/rlic_b200.h
+SCHEDULES = {"trailing": 0, "wavefront": 1}      # RLIC_B200_SCHEDULE_*
 
 _MODE_CODE = {"velocity": 0, "polarization": 1}
 _WALL_CODE = {"closed": 0, "periodic": 1}
@@ -90,6 +91,16 @@ def _load() -> ctypes.CDLL:
     cdll.rlic_b200_set_arithmetic.argtypes = [_int]
     cdll.rlic_b200_set_arithmetic.restype = _int
     cdll.rlic_b200_get_arithmetic.restype = _int
+    cdll.rlic_b200_set_schedule.argtypes = [_int]
+    cdll.rlic_b200_set_schedule.restype = _int
+    cdll.rlic_b200_get_schedule.restype = _int
+    cdll.rlic_b200_debug_wavefront_order.argtypes = [_i64, _i64, ctypes.POINTER(ctypes.c_int32), _i64]
+    cdll.rlic_b200_debug_wavefront_order.restype = _i64
+    wanted = os.environ.get("RLIC_B200_SCHEDULE")
+    if wanted:
+        if wanted not in SCHEDULES:
+            raise ImportError(f"RLIC_B200_SCHEDULE={wanted!r}: expected one of {sorted(SCHEDULES)}")
+        cdll.rlic_b200_set_schedule(SCHEDULES[wanted])
     requested = os.environ.get("RLIC_B200_ARITHMETIC")
     if requested:
         if requested not in ARITHMETICS:
@@ -132,6 +143,22 @@ def set_arithmetic(name: str) -> None:
 def get_arithmetic() -> str:
     code = int(lib.rlic_b200_get_arithmetic())
     return next(name for name, c in ARITHMETICS.items() if c == code)
+
+
+def set_schedule(name: str) -> None:
+    """How the host path orders uploads, passes and downloads of one large image
+    (include/rlic_b200.h): ``"trailing"`` (default) or ``"wavefront"``.  Same results
+    either way.  Process-wide; also settable with ``RLIC_B200_SCHEDULE``."""
+    try:
+        code = SCHEDULES[name]
+    except KeyError:
+        raise ValueError(f"unknown schedule {name!r}: expected one of {sorted(SCHEDULES)}") from None
+    check(lib.rlic_b200_set_schedule(code))
+
+
+def get_schedule() -> str:
+    code = int(lib.rlic_b200_get_schedule())
+    return next(name for name, c in SCHEDULES.items() if c == code)
 
 
 def device_count() -> int:

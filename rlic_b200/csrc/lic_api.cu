@@ -314,6 +314,30 @@ struct Events {
     }
 };
 
+// Order in which the (pass, band) launches of the wavefront schedule are issued on the one
+// compute stream.  Pass p of band b reads pass p-1 of bands b-1, b, b+1 (a band is at
+// least two kernel half-widths tall) and overwrites what pass p-1 of those same bands
+// read (two ping-pong buffers), so it may run once those three are done: launches are
+// grouped in slots b + 2 (p - 1), a slot's members are independent of each other, and
+// within a slot the pass-1 launch -- the only one that waits for an upload -- goes last.
+struct BandPass { int pass, band; };   // pass is 1-based
+
+std::vector<BandPass> wavefront_order(int64_t nbands, int64_t iterations)
+{
+    std::vector<BandPass> order;
+    order.reserve((size_t)(nbands * iterations));
+    const int64_t slots = (nbands - 1) + 2 * (iterations - 1) + 1;
+    for (int64_t slot = 0; slot < slots; ++slot)
+        for (int64_t p = iterations; p >= 1; --p) {
+            const int64_t b = slot - 2 * (p - 1);
+            if (b >= 0 && b < nbands)
+                order.push_back({(int)p, (int)b});
+        }
+    return order;
+}
+
+std::atomic<int> g_schedule{RLIC_B200_SCHEDULE_TRAILING};
+
 // Host entry: upload -> passes -> download, pipelined over row bands.
 //   stream `io`  : uploads (band by band: u, v -> packed field; texture -> padded
 //                  buffer) and downloads (padded -> dense -> host)
@@ -405,6 +429,78 @@ int convolve_host(const T *tex, const T *u, const T *v, int64_t nfields, int64_t
             CUDA_TRY(cudaEventRecord(done.ev[(size_t)b], run.s));
         return RLIC_B200_OK;
     };
+
+    // ---- wavefront schedule (opt-in): every pass trails the uploads, band by band ----
+    // Early bands run through all their passes while later bands are still on the bus,
+    // and their results go back while later bands still compute.  Needs a top and a
+    // bottom that do not depend on each other (no wrap in y) and something to skew.
+    if (g_schedule.load(std::memory_order_relaxed) == RLIC_B200_SCHEDULE_WAVEFRONT && !periodic_y &&
+        iterations >= 2 && nbands >= 2) {
+        const std::vector<BandPass> order = wavefront_order(nbands, iterations);
+        auto upload_needed = [&](int64_t b) {   // last band a pass-1 walker of band b can reach
+            const int64_t last_row = std::min(ny - 1, band_begin(b + 1) - 1 + reach);
+            return std::min(nbands - 1, last_row / band_rows);
+        };
+        auto band_pass = [&](const BandPass &bp) -> int {
+            const int64_t b = bp.band;
+            // pass p reads what pass p-1 wrote (pass 1: the uploaded texture) and writes bufs[(p-1) % 2]
+            const T *from = bp.pass == 1 ? t_tex : bufs[(bp.pass - 2) & 1];
+            if (bp.pass == 1)
+                CUDA_TRY(cudaStreamWaitEvent(run.s, uploaded.ev[(size_t)upload_needed(b)], 0));
+            if (int rc = launch_pass<T>(from, t_field, bufs[(bp.pass - 1) & 1], g, nfields, band_begin(b),
+                                        band_begin(b + 1) - band_begin(b), uv_mode, taps, run.s))
+                return rc;
+            if (bp.pass == iterations)
+                CUDA_TRY(cudaEventRecord(done.ev[(size_t)b], run.s));
+            return RLIC_B200_OK;
+        };
+        size_t next = 0;
+        for (int64_t b = 0; b < nbands; ++b) {
+            const int64_t rb = band_begin(b), re = band_begin(b + 1);
+            const size_t off = (size_t)rb * (size_t)nx;
+            const size_t n = (size_t)(re - rb) * (size_t)nx;
+            const HostToDevice uv_jobs[2] = {{s_u + off, u + off, n * sizeof(T)},
+                                             {s_v + off, v + off, n * sizeof(T)}};
+            CUDA_TRY(upload(uv_jobs, 2, io.s));
+            CUDA_TRY(launch_pack<T>(s_u + off, s_v + off, t_field, g, rb, re, 1, io.s));
+            const HostToDevice tex_job{s_t + off, tex + off, n * sizeof(T)};
+            CUDA_TRY(upload(&tex_job, 1, io.s));
+            CUDA_TRY(launch_pad<T>(s_t + off, t_tex, g, rb, re, 1, flag, io.s));
+            CUDA_TRY(cudaEventRecord(uploaded.ev[(size_t)b], io.s));
+            // issue everything that no longer waits for a band still to be enqueued
+            for (; next < order.size(); ++next) {
+                if (order[next].pass == 1 && upload_needed(order[next].band) > b)
+                    break;
+                if (int rc = band_pass(order[next]))
+                    return rc;
+            }
+        }
+        for (; next < order.size(); ++next)
+            if (int rc = band_pass(order[next]))
+                return rc;
+        T *const result = bufs[(iterations - 1) & 1];
+        if (is_pageable(out))
+            prefault_for_write(out, bytes);
+        // results leave on their own stream: the bus is full duplex, and `io` may still be uploading
+        Stream back;
+        CUDA_TRY(cudaStreamCreateWithFlags(&back.s, cudaStreamNonBlocking));
+        for (int64_t b = 0; b < nbands; ++b) {
+            const int64_t rb = band_begin(b), re = band_begin(b + 1);
+            const size_t off = (size_t)rb * (size_t)nx;
+            const size_t n = (size_t)(re - rb) * (size_t)nx;
+            CUDA_TRY(cudaStreamWaitEvent(back.s, done.ev[(size_t)b], 0));
+            // the texture's staging band was consumed by the padding that `uploaded` covers
+            CUDA_TRY(cudaStreamWaitEvent(back.s, uploaded.ev[(size_t)b], 0));
+            CUDA_TRY(launch_unpad<T>(result, s_t + off, g, rb, re, 1, back.s));
+            CUDA_TRY(cudaMemcpyAsync(out + off, s_t + off, n * sizeof(T), cudaMemcpyDeviceToHost, back.s));
+        }
+        CUDA_TRY(cudaStreamSynchronize(back.s));
+        if (texture_has_negative)
+            CUDA_TRY(cudaMemcpyAsync(texture_has_negative, flag, sizeof(int), cudaMemcpyDeviceToHost, io.s));
+        CUDA_TRY(cudaStreamSynchronize(io.s));
+        CUDA_TRY(cudaStreamSynchronize(run.s));
+        return RLIC_B200_OK;
+    }
 
     // ---- uploads, with pass 1 trailing behind them ----
     int64_t next_band = 0;   // next band of pass 1 to launch
@@ -786,6 +882,30 @@ int rlic_b200_set_arithmetic(int which)
 }
 
 int rlic_b200_get_arithmetic(void) { return g_arithmetic.load(std::memory_order_relaxed); }
+
+int rlic_b200_set_schedule(int which)
+{
+    tls_error.clear();
+    if (which != RLIC_B200_SCHEDULE_TRAILING && which != RLIC_B200_SCHEDULE_WAVEFRONT)
+        return fail(RLIC_B200_EINVAL, "unknown schedule %d", which);
+    g_schedule.store(which, std::memory_order_relaxed);
+    return RLIC_B200_OK;
+}
+
+int rlic_b200_get_schedule(void) { return g_schedule.load(std::memory_order_relaxed); }
+
+int64_t rlic_b200_debug_wavefront_order(int64_t nbands, int64_t iterations, int32_t *pass_band,
+                                        int64_t capacity)
+{
+    if (nbands <= 0 || iterations <= 0 || nbands * iterations > (int64_t)1 << 24)
+        return 0;
+    const std::vector<BandPass> order = wavefront_order(nbands, iterations);
+    for (size_t k = 0; k < order.size() && (int64_t)k < capacity && pass_band; ++k) {
+        pass_band[2 * k] = order[k].pass;
+        pass_band[2 * k + 1] = order[k].band;
+    }
+    return (int64_t)order.size();
+}
 
 int rlic_b200_debug_geometry(int64_t ny, int64_t nx, int64_t row0, int64_t nrows, int64_t halo_lo,
                              int64_t halo_hi, int x_left, int x_right, int y_left, int y_right,

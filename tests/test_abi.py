@@ -163,3 +163,20 @@ def test_arithmetic_selection_round_trips_and_rejects_unknown_builds():
     env["RLIC_B200_ARITHMETIC"] = "nonsense"
     bad = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
     assert bad.returncode != 0 and "RLIC_B200_ARITHMETIC" in bad.stderr
+
+
+def test_schedule_selection_round_trips():
+    import rlic_b200
+
+    for name, code in _core.SCHEDULES.items():
+        m = re.search(rf"#define RLIC_B200_SCHEDULE_{name.upper()} (\d+)", HEADER)
+        assert int(m.group(1)) == code
+    assert rlic_b200.get_schedule() == "trailing"
+    try:
+        rlic_b200.set_schedule("wavefront")
+        assert rlic_b200.get_schedule() == "wavefront"
+        with pytest.raises(ValueError, match="unknown schedule"):
+            rlic_b200.set_schedule("diagonal")
+        assert _core.lib.rlic_b200_set_schedule(9) == _core.EINVAL
+    finally:
+        rlic_b200.set_schedule("trailing")

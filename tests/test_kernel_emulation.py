@@ -407,3 +407,77 @@ def test_stitched_slabs_equal_the_whole_image(name):
     got = slab_pass_all(tex, u, v, kernel, WALLS[walls], mode, cuts)
     want = oracle.convolve(tex, u, v, kernel=kernel, uv_mode=mode, boundaries=WALLS[walls])
     assert_array_equal(got, want)
+
+
+# ---- the wavefront schedule of the host path (rlic_b200_set_schedule) ----------------------
+def wavefront_order(nbands, iterations):
+    import ctypes
+
+    out = np.zeros(2 * nbands * iterations, dtype=np.int32)
+    n = _core.lib.rlic_b200_debug_wavefront_order(nbands, iterations,
+                                                  out.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                                                  nbands * iterations)
+    assert n == nbands * iterations
+    return [tuple(int(x) for x in pair) for pair in out.reshape(-1, 2)]
+
+
+def run_in_order(order, tex, u, v, kernel, walls, mode, band_rows, iterations):
+    """convolve_host's buffers and roles, its launches issued one after another in `order`:
+    exactly what an in-order stream does.  tex[0] is the uploaded texture and doubles as
+    the second work buffer; pass p writes work buffer (p - 1) % 2 of {tex[1], tex[0]}."""
+    ny, nx = tex.shape
+    b = ke.Buffers(tex.dtype, ny, nx, _core.wall_codes(WALLS[walls]), kernel.size)
+    b.pack_field(u, v)
+    b.pad_texture(tex, 0)
+    b.tex[1][:] = np.nan
+    work = (1, 0)
+    for p, band in order:
+        src = 0 if p == 1 else work[(p - 2) & 1]
+        r0, r1 = band * band_rows, min(ny, (band + 1) * band_rows)
+        b.run_pass(src, work[(p - 1) & 1], kernel, mode, rows=(r0, r1 - r0))
+    return b.unpad_texture(work[(iterations - 1) & 1])
+
+
+@pytest.mark.parametrize("nbands,iterations", [(2, 2), (5, 2), (5, 5), (3, 7), (8, 5), (7, 1)])
+def test_wavefront_order_respects_every_dependency(nbands, iterations):
+    order = wavefront_order(nbands, iterations)
+    assert sorted(order) == [(p, b) for p in range(1, iterations + 1) for b in range(nbands)]
+    at = {pb: k for k, pb in enumerate(order)}
+    for (p, b), k in at.items():
+        if p > 1:   # reads, and overwrites what was read by, pass p-1 of the neighbouring bands
+            for nb in (b - 1, b, b + 1):
+                if 0 <= nb < nbands:
+                    assert at[(p - 1, nb)] < k
+    # within a group of mutually independent launches the one that waits for an upload is last
+    for k in range(1, len(order)):
+        (p0, b0), (p1, b1) = order[k - 1], order[k]
+        if b0 + 2 * (p0 - 1) == b1 + 2 * (p1 - 1):
+            assert p0 > p1
+
+
+@pytest.mark.parametrize("dtype,mode,walls,iterations", [
+    (np.float32, "velocity", "closed", 5),
+    (np.float64, "polarization", "x-periodic", 4),
+    (np.float32, "polarization", "closed", 2),
+    (np.float64, "velocity", "closed", 3),
+])
+def test_wavefront_schedule_computes_the_same_image(dtype, mode, walls, iterations):
+    ny, band_rows = 150, 32                       # five bands, the last one short
+    tex, u, v, kernel = random_case((ny, 41), dtype, 33, seed=21)     # reach 16 = half a band
+    nbands = -(-ny // band_rows)
+    got = run_in_order(wavefront_order(nbands, iterations), tex, u, v, kernel, walls, mode, band_rows, iterations)
+    want = oracle.convolve(tex, u, v, kernel=kernel, uv_mode=mode, boundaries=WALLS[walls], iterations=iterations)
+    assert_array_equal(got, want)
+
+
+def test_an_order_that_breaks_a_dependency_is_caught():
+    """The previous test has teeth: issue pass 2 of band 0 before pass 1 of band 1."""
+    ny, band_rows, iterations = 150, 32, 3
+    tex, u, v, kernel = random_case((ny, 41), np.float32, 33, seed=21)
+    order = wavefront_order(5, iterations)
+    i, j = order.index((2, 0)), order.index((1, 1))
+    assert j < i
+    order[i], order[j] = order[j], order[i]
+    got = run_in_order(order, tex, u, v, kernel, "closed", "velocity", band_rows, iterations)
+    want = oracle.convolve(tex, u, v, kernel=kernel, boundaries=WALLS["closed"], iterations=iterations)
+    assert not np.array_equal(got, want, equal_nan=True)
