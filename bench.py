@@ -417,7 +417,8 @@ def run_ours(args) -> dict:
            "d2h_bytes_per_step": d2h * world, "ms_per_step": e2e_ms,
            "api": "rlic_b200.convolve(numpy arrays in pinned host memory)" if world == 1
                   else "per rank: pinned host slab -> ShardedConvolver -> pinned host slab",
-           "schedule": rlic_b200.get_schedule(), "arithmetic": rlic_b200.get_arithmetic()}
+           "schedule": rlic_b200.get_schedule(), "arithmetic": rlic_b200.get_arithmetic(),
+           "walk": rlic_b200.get_walk()}
 
     line = {
         "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps,

@@ -95,6 +95,19 @@ int rlic_b200_get_arithmetic(void);
 int rlic_b200_set_schedule(int which);
 int rlic_b200_get_schedule(void);
 
+/* How the pass kernels are written.  Same results bit for bit; a process-wide choice like the
+ * two above.
+ *   RLIC_B200_WALK_PER_STEP  the kernels every measurement of round 1 was made with (default)
+ *   RLIC_B200_WALK_GROUPED   the loop-exit test once per group of steps, no negation of the
+ *                            record in the backward pass: 6 (f32) / 1-2 (f64) fewer
+ *                            instructions per step in the sm_100a SASS; reproduces the oracle on
+ *                            the CPU emulation of the kernel source, not yet run or timed on a GPU.
+ *                            Applies to the default arithmetic only. */
+#define RLIC_B200_WALK_PER_STEP 0
+#define RLIC_B200_WALK_GROUPED 1
+int rlic_b200_set_walk(int which);
+int rlic_b200_get_walk(void);
+
 /* Testing hook (host code only): the (pass, band) launch order of the wavefront schedule
  * for `nbands` bands and `iterations` passes, as pairs pass_band[2k] = pass (1-based),
  * pass_band[2k+1] = band; returns the number of pairs (at most `capacity` are written). */

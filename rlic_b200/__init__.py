@@ -14,9 +14,12 @@ __all__ = [
     "convolve_batch",
     "get_arithmetic",
     "get_schedule",
+    "get_walk",
     "set_arithmetic",
     "set_schedule",
+    "set_walk",
 ]
 
-from rlic_b200._core import get_arithmetic, get_schedule, set_arithmetic, set_schedule
+from rlic_b200._core import (get_arithmetic, get_schedule, get_walk, set_arithmetic, set_schedule,
+                             set_walk)
 from rlic_b200._lib import convolve, convolve_batch

@@ -33,6 +33,7 @@ OK, EINVAL, ENODEVICE, ECUDA, ESHARD = range(5)
 ABI_VERSION = 2
 ARITHMETICS = {"fma+branchless": 0, "fma": 1}   # RLIC_B200_ARITH_* in include/rlic_b200.h
 SCHEDULES = {"trailing": 0, "wavefront": 1}      # RLIC_B200_SCHEDULE_*
+WALKS = {"per-step": 0, "grouped": 1}            # RLIC_B200_WALK_*
 
 _MODE_CODE = {"velocity": 0, "polarization": 1}
 _WALL_CODE = {"closed": 0, "periodic": 1}
@@ -96,6 +97,14 @@ def _load() -> ctypes.CDLL:
     cdll.rlic_b200_get_schedule.restype = _int
     cdll.rlic_b200_debug_wavefront_order.argtypes = [_i64, _i64, ctypes.POINTER(ctypes.c_int32), _i64]
     cdll.rlic_b200_debug_wavefront_order.restype = _i64
+    cdll.rlic_b200_set_walk.argtypes = [_int]
+    cdll.rlic_b200_set_walk.restype = _int
+    cdll.rlic_b200_get_walk.restype = _int
+    walk = os.environ.get("RLIC_B200_WALK")
+    if walk:
+        if walk not in WALKS:
+            raise ImportError(f"RLIC_B200_WALK={walk!r}: expected one of {sorted(WALKS)}")
+        cdll.rlic_b200_set_walk(WALKS[walk])
     wanted = os.environ.get("RLIC_B200_SCHEDULE")
     if wanted:
         if wanted not in SCHEDULES:
@@ -159,6 +168,22 @@ def set_schedule(name: str) -> None:
 def get_schedule() -> str:
     code = int(lib.rlic_b200_get_schedule())
     return next(name for name, c in SCHEDULES.items() if c == code)
+
+
+def set_walk(name: str) -> None:
+    """Which formulation of the pass kernels runs (include/rlic_b200.h): ``"per-step"``
+    (default: what every published measurement used) or ``"grouped"`` (fewer instructions
+    per step, same bits).  Process-wide; also settable with ``RLIC_B200_WALK``."""
+    try:
+        code = WALKS[name]
+    except KeyError:
+        raise ValueError(f"unknown walk {name!r}: expected one of {sorted(WALKS)}") from None
+    check(lib.rlic_b200_set_walk(code))
+
+
+def get_walk() -> str:
+    code = int(lib.rlic_b200_get_walk())
+    return next(name for name, c in WALKS.items() if c == code)
 
 
 def device_count() -> int:

@@ -30,6 +30,7 @@ thread_local int tls_device = 0;
 std::atomic<int64_t> g_launches{0};
 std::atomic<int> g_force_wide{0};   // testing hook: use 64-bit element indices for any size
 std::atomic<int> g_arithmetic{RLIC_B200_ARITH_FMA_BRANCHLESS};   // which reference build to reproduce
+std::atomic<int> g_walk{RLIC_B200_WALK_PER_STEP};                // which formulation of the pass kernels
 
 int fail(int code, const char *fmt, ...)
 {
@@ -242,10 +243,15 @@ template <typename T> struct TapSet {
 
 template <typename T, bool POL, typename Taps, typename Idx>
 cudaError_t launch_one(const T *tex, const Field<T> *field, T *out, const PassGeom &g,
-                       const Taps &taps, int ntaps, unsigned blocks, bool branchless, cudaStream_t stream)
+                       const Taps &taps, int ntaps, unsigned blocks, bool branchless, bool grouped,
+                       cudaStream_t stream)
 {
     using Tn = rlic::Tune<T, POL>;
-    if (branchless)
+    if (branchless && grouped)
+        rlic::lic_pass_kernel<T, POL, Taps, Idx, rlic::kTileW, rlic::kTileH, Tn::unroll, Tn::min_blocks,
+                              Tn::walk_flavor, Tn::admit, true, Tn::walk>
+            <<<blocks, rlic::kThreads, 0, stream>>>(tex, field, out, g, taps, ntaps);
+    else if (branchless)
         rlic::lic_pass_kernel<T, POL, Taps, Idx>
             <<<blocks, rlic::kThreads, 0, stream>>>(tex, field, out, g, taps, ntaps);
     else
@@ -279,10 +285,11 @@ int launch_pass(const T *tex, const Field<T> *field, T *out, PassGeom g, int64_t
                       g_force_wide.load(std::memory_order_relaxed) != 0;
     const bool pol = uv_mode == RLIC_B200_POLARIZATION;
     const bool branchless = g_arithmetic.load(std::memory_order_relaxed) == RLIC_B200_ARITH_FMA_BRANCHLESS;
+    const bool grouped = g_walk.load(std::memory_order_relaxed) == RLIC_B200_WALK_GROUPED;
 
     cudaError_t e;
 #define RLIC_LAUNCH(POL, TAPS, TAPV, IDX) \
-    e = launch_one<T, POL, TAPS, IDX>(tex, field, out, g, TAPV, taps.ntaps, (unsigned)blocks, branchless, stream)
+    e = launch_one<T, POL, TAPS, IDX>(tex, field, out, g, TAPV, taps.ntaps, (unsigned)blocks, branchless, grouped, stream)
     using PT = rlic::ParamTaps<T, TapSet<T>::kMaxParam>;
     using GT = rlic::GlobalTaps<T>;
     const GT gt{static_cast<const T *>(taps.global.p)};
@@ -882,6 +889,17 @@ int rlic_b200_set_arithmetic(int which)
 }
 
 int rlic_b200_get_arithmetic(void) { return g_arithmetic.load(std::memory_order_relaxed); }
+
+int rlic_b200_set_walk(int which)
+{
+    tls_error.clear();
+    if (which != RLIC_B200_WALK_PER_STEP && which != RLIC_B200_WALK_GROUPED)
+        return fail(RLIC_B200_EINVAL, "unknown walk %d", which);
+    g_walk.store(which, std::memory_order_relaxed);
+    return RLIC_B200_OK;
+}
+
+int rlic_b200_get_walk(void) { return g_walk.load(std::memory_order_relaxed); }
 
 int rlic_b200_set_schedule(int which)
 {

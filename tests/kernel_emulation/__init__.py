@@ -51,7 +51,7 @@ def lib() -> ctypes.CDLL:
             getattr(cdll, f"emu_unpad_texture_{sfx}").argtypes = [p, p, g, _i64, _i64, _i64]
             getattr(cdll, f"emu_unpad_texture_{sfx}").restype = None
             getattr(cdll, f"emu_pass_{sfx}").argtypes = [p, p, p, g, _i64, _i64, _i64, _int, p, _i64,
-                                                        _int, _int, _int, _int]
+                                                        _int, _int, _int, _int, _int]
             getattr(cdll, f"emu_pass_{sfx}").restype = _int
         cdll.emu_step_counts.argtypes = [ctypes.POINTER(ctypes.c_ulonglong), _int]
         cdll.emu_step_counts.restype = None
@@ -123,7 +123,7 @@ class SlabOps:
         g = self._geom(plan, walls, taps.size)
         rc = getattr(lib(), f"emu_pass_{sfx}")(
             _ptr(self._np(src), real), _ptr(self._np(field), real), _ptr(self._np(dst), real), _ptr(g, _i64), 1,
-            plan.halo_lo + a, b - a, mode, _ptr(taps, real), taps.size, 0, -1, -1, 1)
+            plan.halo_lo + a, b - a, mode, _ptr(taps, real), taps.size, 0, -1, -1, 1, 0)
         assert rc == 0
 
 
@@ -164,18 +164,19 @@ class Buffers:
                                                         self._g, rb, re, self.nfields)
         return dense[0] if self.nfields == 1 else dense
 
-    def run_pass(self, src, dst, taps, uv_mode, rows=None, wide=False, flavor=-1, admit=-1, branchless=True):
+    def run_pass(self, src, dst, taps, uv_mode, rows=None, wide=False, flavor=-1, admit=-1, branchless=True,
+                 walk=0):
         first, count = rows or (self.slab[2], self.slab[1])
         taps = np.ascontiguousarray(taps, dtype=self.dtype)
         rc = getattr(lib(), f"emu_pass_{self.sfx}")(
             _ptr(self.tex[src], self.real), _ptr(self.field, self.real), _ptr(self.tex[dst], self.real),
             self._g, self.nfields, first, count, _core.mode_code(uv_mode), _ptr(taps, self.real), taps.size,
-            int(wide), flavor, admit, int(branchless))
+            int(wide), flavor, admit, int(branchless), int(walk))
         assert rc == 0, "no such formulation"
 
 
 def convolve(texture, u, v, *, kernel, uv_mode="velocity", boundaries=(("closed", "closed"),) * 2,
-             iterations=1, wide=False, flavor=-1, admit=-1, branchless=True) -> np.ndarray:
+             iterations=1, wide=False, flavor=-1, admit=-1, branchless=True, walk=0) -> np.ndarray:
     """The whole-image flow of ``run_device`` in lic_api.cu: pack, pad, passes, un-pad."""
     ny, nx = texture.shape
     b = Buffers(texture.dtype, ny, nx, _core.wall_codes(boundaries), len(kernel))
@@ -183,6 +184,7 @@ def convolve(texture, u, v, *, kernel, uv_mode="velocity", boundaries=(("closed"
     b.pad_texture(texture, 0)
     src = 0
     for _ in range(iterations):
-        b.run_pass(src, 1 - src, kernel, uv_mode, wide=wide, flavor=flavor, admit=admit, branchless=branchless)
+        b.run_pass(src, 1 - src, kernel, uv_mode, wide=wide, flavor=flavor, admit=admit, branchless=branchless,
+                   walk=walk)
         src = 1 - src
     return b.unpad_texture(src)

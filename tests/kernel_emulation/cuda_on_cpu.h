@@ -57,6 +57,7 @@ static inline int __float_as_int(float x) { return bits_as<int>(x); }
 static inline unsigned __float_as_uint(float x) { return bits_as<unsigned>(x); }
 static inline float __int_as_float(int x) { return bits_as<float>(x); }
 static inline int __double2hiint(double x) { return (int)(bits_as<uint64_t>(x) >> 32); }
+static inline int __double2loint(double x) { return (int)(uint32_t)bits_as<uint64_t>(x); }
 static inline double __hiloint2double(int hi, int lo)
 {
     return bits_as<double>(((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo);

@@ -107,7 +107,8 @@ constexpr int kDefault = -1;
 
 // One pass, as launch_pass() issues it.  flavor / admit: kDefault selects the library's
 // per-type tuning (rlic::Tune), other values pick a formulation explicitly.
-template <typename T, bool POL, typename Taps, typename Idx, int FLAVOR, int ADMIT, bool BRANCHLESS = true>
+template <typename T, bool POL, typename Taps, typename Idx, int FLAVOR, int ADMIT, bool BRANCHLESS = true,
+          int WALK = 0>
 void run_pass(const T *tex, const T *field, T *out, const PassGeom &g, const Taps &taps, int ntaps,
               unsigned blocks)
 {
@@ -115,30 +116,44 @@ void run_pass(const T *tex, const T *field, T *out, const PassGeom &g, const Tap
     auto *f = reinterpret_cast<const rlic::PackedField<T> *>(field);
     launch(blocks, rlic::kThreads, [&] {
         rlic::lic_pass_kernel<T, POL, Taps, Idx, rlic::kTileW, rlic::kTileH, Tn::unroll, Tn::min_blocks,
-                              FLAVOR, ADMIT, BRANCHLESS>(tex, f, out, g, taps, ntaps);
+                              FLAVOR, ADMIT, BRANCHLESS, WALK>(tex, f, out, g, taps, ntaps);
     });
 }
 
 // An explicitly chosen formulation (32-bit indices, taps in the parameter block only).
+// walk: 0 the per-step loop (flavours 0, 1), 1 the grouped walk, 9 the grouped walk with
+// its loop control on the byte offset (flavours 0-3); the register-pinning bits of WALK
+// mean nothing on a CPU.
 template <typename T, bool POL, typename Taps>
 int pick_formulation(const T *tex, const T *field, T *out, const PassGeom &g, const Taps &taps, int ntaps,
-                     unsigned blocks, int flavor, int admit)
+                     unsigned blocks, int flavor, int admit, int walk)
 {
 #define RLIC_CASE(F, A) \
-    if (flavor == F && admit == A) { run_pass<T, POL, Taps, int, F, A>(tex, field, out, g, taps, ntaps, blocks); return 0; }
+    if (flavor == F && admit == A) { \
+        if (walk == 1) run_pass<T, POL, Taps, int, F, A, true, 1>(tex, field, out, g, taps, ntaps, blocks); \
+        else if (walk == 9) run_pass<T, POL, Taps, int, F, A, true, 9>(tex, field, out, g, taps, ntaps, blocks); \
+        else if (walk == 0 && F < 2) run_pass<T, POL, Taps, int, (F < 2 ? F : 0), A>(tex, field, out, g, taps, ntaps, blocks); \
+        else return 1; \
+        return 0; }
     RLIC_CASE(0, 0) RLIC_CASE(0, 1) RLIC_CASE(0, 2) RLIC_CASE(0, 3)
     RLIC_CASE(1, 0) RLIC_CASE(1, 1) RLIC_CASE(1, 2) RLIC_CASE(1, 3)
+    RLIC_CASE(2, 0) RLIC_CASE(2, 1) RLIC_CASE(2, 2) RLIC_CASE(2, 3)
+    RLIC_CASE(3, 0) RLIC_CASE(3, 1) RLIC_CASE(3, 2) RLIC_CASE(3, 3)
 #undef RLIC_CASE
     return 1;
 }
 
-// The library's own choice (rlic::Tune), as launch_pass() dispatches it.
+// The library's own choice (rlic::Tune), as launch_one() dispatches it: walk != 0 is
+// rlic_b200_set_walk(RLIC_B200_WALK_GROUPED).
 template <typename T, bool POL, typename Taps>
 int tuned(const T *tex, const T *field, T *out, const PassGeom &g, const Taps &taps, int ntaps, unsigned blocks,
-          int wide, int branchless)
+          int wide, int branchless, int walk)
 {
     using Tn = rlic::Tune<T, POL>;
-    if (branchless) {
+    if (branchless && walk) {
+        if (wide) run_pass<T, POL, Taps, long long, Tn::walk_flavor, Tn::admit, true, Tn::walk>(tex, field, out, g, taps, ntaps, blocks);
+        else run_pass<T, POL, Taps, int, Tn::walk_flavor, Tn::admit, true, Tn::walk>(tex, field, out, g, taps, ntaps, blocks);
+    } else if (branchless) {
         if (wide) run_pass<T, POL, Taps, long long, Tn::flavor, Tn::admit>(tex, field, out, g, taps, ntaps, blocks);
         else run_pass<T, POL, Taps, int, Tn::flavor, Tn::admit>(tex, field, out, g, taps, ntaps, blocks);
     } else {
@@ -151,7 +166,7 @@ int tuned(const T *tex, const T *field, T *out, const PassGeom &g, const Taps &t
 template <typename T>
 int pass(const T *tex, const T *field, T *out, const int64_t *geom, int64_t nfields, int64_t first_row,
          int64_t out_rows, int uv_mode, const T *host_taps, int64_t klen, int wide, int flavor, int admit,
-         int branchless)
+         int branchless, int walk)
 {
     PassGeom g = geometry_from(geom);
     if (out_rows <= 0 || g.nx <= 0 || nfields <= 0) return 0;
@@ -175,16 +190,16 @@ int pass(const T *tex, const T *field, T *out, const int64_t *geom, int64_t nfie
         std::memcpy(pt.w, host_taps, sizeof(T) * (size_t)klen);
         if (chosen) {
             if (wide || !branchless) return 1;
-            return pol ? pick_formulation<T, true, PT>(tex, field, out, g, pt, ntaps, blocks, flavor, admit)
-                       : pick_formulation<T, false, PT>(tex, field, out, g, pt, ntaps, blocks, flavor, admit);
+            return pol ? pick_formulation<T, true, PT>(tex, field, out, g, pt, ntaps, blocks, flavor, admit, walk)
+                       : pick_formulation<T, false, PT>(tex, field, out, g, pt, ntaps, blocks, flavor, admit, walk);
         }
-        return pol ? tuned<T, true, PT>(tex, field, out, g, pt, ntaps, blocks, wide, branchless)
-                   : tuned<T, false, PT>(tex, field, out, g, pt, ntaps, blocks, wide, branchless);
+        return pol ? tuned<T, true, PT>(tex, field, out, g, pt, ntaps, blocks, wide, branchless, walk)
+                   : tuned<T, false, PT>(tex, field, out, g, pt, ntaps, blocks, wide, branchless, walk);
     }
     if (chosen) return 1;
     const GT gt{host_taps};
-    return pol ? tuned<T, true, GT>(tex, field, out, g, gt, ntaps, blocks, wide, branchless)
-               : tuned<T, false, GT>(tex, field, out, g, gt, ntaps, blocks, wide, branchless);
+    return pol ? tuned<T, true, GT>(tex, field, out, g, gt, ntaps, blocks, wide, branchless, walk)
+               : tuned<T, false, GT>(tex, field, out, g, gt, ntaps, blocks, wide, branchless, walk);
 }
 
 }  // namespace
@@ -210,9 +225,10 @@ extern "C" void emu_step_counts(unsigned long long *out, int reset)
     { unpad_texture<T>(padded, dense, geom, rb, re, nfields); }                                              \
     extern "C" int emu_pass_##SFX(const T *tex, const T *field, T *out, const int64_t *geom, int64_t nfields, \
                                   int64_t first_row, int64_t out_rows, int uv_mode, const T *taps,           \
-                                  int64_t klen, int wide, int flavor, int admit, int branchless)             \
+                                  int64_t klen, int wide, int flavor, int admit, int branchless,   \
+                                  int walk)                                                                  \
     { return pass<T>(tex, field, out, geom, nfields, first_row, out_rows, uv_mode, taps, klen, wide, flavor, admit, \
-                     branchless); }
+                     branchless, walk); }
 
 EMU_DEFINE(f32, float)
 EMU_DEFINE(f64, double)

@@ -180,3 +180,32 @@ def test_schedule_selection_round_trips():
         assert _core.lib.rlic_b200_set_schedule(9) == _core.EINVAL
     finally:
         rlic_b200.set_schedule("trailing")
+
+
+def test_walk_selection_round_trips_and_reads_the_environment():
+    import os
+    import subprocess
+    import sys
+
+    import rlic_b200
+
+    for name, code in _core.WALKS.items():
+        m = re.search(rf"#define RLIC_B200_WALK_{name.upper().replace('-', '_')} (\d+)", HEADER)
+        assert int(m.group(1)) == code
+    assert rlic_b200.get_walk() == "per-step"      # the kernels every published number was measured with
+    try:
+        rlic_b200.set_walk("grouped")
+        assert rlic_b200.get_walk() == "grouped"
+        with pytest.raises(ValueError, match="unknown walk"):
+            rlic_b200.set_walk("sideways")
+        assert _core.lib.rlic_b200_set_walk(5) == _core.EINVAL
+        assert rlic_b200.get_walk() == "grouped"
+    finally:
+        rlic_b200.set_walk("per-step")
+    code = "import rlic_b200; print(rlic_b200.get_walk())"
+    env = dict(os.environ, RLIC_B200_WALK="grouped", PYTHONPATH=str(ROOT))
+    assert subprocess.run([sys.executable, "-c", code], env=env, capture_output=True,
+                          text=True).stdout.strip() == "grouped"
+    env["RLIC_B200_WALK"] = "nonsense"
+    bad = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
+    assert bad.returncode != 0 and "RLIC_B200_WALK" in bad.stderr

@@ -286,6 +286,133 @@ def test_band_by_band_upload_builds_the_same_buffers(dtype, walls):
     assert_array_equal(banded.tex[0].view(np.uint8), whole.tex[0].view(np.uint8))
 
 
+# ---------------------------------------------------------------------------
+# The grouped walk (rlic_b200.set_walk("grouped"), WALK template bits in lic_walk.cuh): the
+# loop-exit test once per group of steps, a tail loop for the remainder, and the backward
+# pass / polarization flip applied to the travel direction instead of the record.  It must
+# produce the same bits as the per-step walk, i.e. the oracle's; `walk=1` dispatches as the
+# library does (rlic::Tune), explicit (flavor, admit, walk) triples cover the formulations
+# the lab sweeps.
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_grouped_walk_golden_vectors(name):
+    mode, bnd, its = GOLDEN_CASES[name]
+    tex, u, v, kernel = load(name)
+    got = ke.convolve(tex, u, v, kernel=kernel, uv_mode=mode, boundaries=bnd, iterations=its, walk=1)
+    assert_array_equal(got, expected(name, 3))
+
+
+@pytest.mark.parametrize("seed", range(48))
+def test_grouped_walk_randomised_configurations(seed):
+    tex, u, v, kernel, mode, walls, its = fuzz_case(seed)
+    with np.errstate(all="ignore"):
+        check(tex, u, v, kernel, mode=mode, walls=walls, iterations=its, walk=1)
+
+
+@pytest.mark.parametrize("walls", WALLS)
+@pytest.mark.parametrize("mode", ["velocity", "polarization"])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_grouped_walk_special_pixels(dtype, mode, walls):
+    check(*random_case((45, 70), dtype, 23, seed=11), mode=mode, walls=walls, iterations=2, walk=1)
+
+
+@pytest.mark.parametrize("klen", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 33, 64, 200])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_grouped_walk_every_remainder_of_the_group_size(dtype, klen):
+    """Groups are 4 steps (f32) or 2 (f64); the forward and backward halves of an odd and of
+    an even kernel leave every possible remainder to the tail loop."""
+    check(*random_case((19, 21), dtype, klen, seed=klen), mode="polarization", walls="x-periodic", walk=1)
+    check(*random_case((19, 21), dtype, klen, seed=klen + 1), walls="periodic", iterations=2, walk=1)
+
+
+@pytest.mark.parametrize("walk", [1, 9])
+@pytest.mark.parametrize("flavor", [0, 1, 2, 3])
+def test_grouped_walk_every_formulation(flavor, walk):
+    for admit, seed in ((0, 2), (1, 5), (2, 6), (3, 9)):
+        tex, u, v, kernel, mode, walls, its = fuzz_case(seed)
+        with np.errstate(all="ignore"):
+            check(tex, u, v, kernel, mode=mode, walls=walls, iterations=its, flavor=flavor, admit=admit,
+                  walk=walk)
+    check(*random_case((45, 70), np.float32, 23, seed=11), mode="polarization", walls="periodic",
+          flavor=flavor, admit=3, walk=walk)
+    check(*random_case((45, 70), np.float64, 22, seed=12), walls="x-periodic", flavor=flavor, admit=2,
+          walk=walk)
+    check(*random_case((45, 70), np.float64, 23, seed=13), mode="polarization", walls="y-periodic",
+          flavor=flavor, admit=2, walk=walk)
+
+
+def test_grouped_walk_axis_aligned_zero_and_signed_zero_fields():
+    rng = np.random.default_rng(3)
+    tex = rng.random((40, 50))
+    one, zero = np.ones_like(tex), np.zeros_like(tex)
+    k = np.linspace(0.1, 1, 15)
+    for u, v in ((one, zero), (zero, one), (-one, zero), (zero, -one), (one, one), (-one, one),
+                 (zero, zero), (-zero, zero), (one, -zero), (-one, -zero)):
+        for walls in WALLS:
+            check(tex, u, v, k, walls=walls, walk=1)
+            check(tex, u, v, k, mode="polarization", walls=walls, walk=1)
+            check(tex.astype(np.float32), u.astype(np.float32), v.astype(np.float32), k.astype(np.float32),
+                  walls=walls, walk=1)
+
+
+def test_grouped_walk_infinite_huge_and_denormal_velocities():
+    tex, u, v, k = random_case((24, 24), np.float32, 13, seed=8)
+    u[7, 7] = np.inf
+    v[8, 8] = -np.inf
+    u[9, 9] = 3e38
+    v[9, 9] = -3e38
+    u[10, 10] = 1e-45
+    v[11, 11] = -1e-42
+    check(tex, u, v, k, walls="periodic", iterations=2, walk=1)
+    check(tex, u, v, k, mode="polarization", walk=1)
+
+
+def test_grouped_walk_workloads():
+    w = workloads.readme_example()                                     # C1 in full
+    check(w.texture, w.u, w.v, w.kernel, walls="periodic", walk=1)
+    w = workloads.vortex_noise(512, iterations=3)                      # C2, reduced
+    got = ke.convolve(w.texture, w.u, w.v, kernel=w.kernel, iterations=3, walk=1)
+    want = oracle.convolve(w.texture, w.u, w.v, kernel=w.kernel, iterations=3, threads=oracle.max_threads())
+    assert_array_equal(got, want)
+    w = workloads.polarization_split(256, taps=129)                    # C3, reduced
+    check(w.texture, w.u, w.v, w.kernel, mode="polarization", walls="x-periodic", walk=1)
+
+
+def test_grouped_walk_wide_indices_global_taps_and_batches():
+    check(*random_case((70, 45), np.float32, 19, seed=77), mode="polarization", walls="x-periodic",
+          iterations=2, wide=True, walk=1)
+    check(*random_case((70, 45), np.float64, 19, seed=78), walls="y-periodic", iterations=2, wide=True, walk=1)
+    check(*random_case((9, 12), np.float32, 1001, seed=5), walls="periodic", walk=1)
+    check(*random_case((9, 12), np.float64, 500, seed=6), mode="polarization", walls="closed", walk=1)
+    rng = np.random.default_rng(14)
+    nf, ny, nx = 4, 33, 65
+    tex = rng.random((nf, ny, nx), dtype=np.float32)
+    u = (rng.random((nf, ny, nx), dtype=np.float32) - 0.5)
+    v = (rng.random((nf, ny, nx), dtype=np.float32) - 0.5)
+    kernel = np.linspace(0.2, 1.0, 18, dtype=np.float32)
+    bnd = WALLS["y-periodic"]
+    b = ke.Buffers(np.float32, ny, nx, _core.wall_codes(bnd), kernel.size, nfields=nf)
+    b.pack_field(u, v)
+    b.pad_texture(tex, 0)
+    b.run_pass(0, 1, kernel, "velocity", walk=1)
+    b.run_pass(1, 0, kernel, "velocity", walk=1)
+    got = b.unpad_texture(0)
+    for f in range(nf):
+        assert_array_equal(got[f], oracle.convolve(tex[f], u[f], v[f], kernel=kernel, boundaries=bnd, iterations=2))
+
+
+def test_grouped_walk_decides_steps_like_the_per_step_walk():
+    """Same admissions, same wall crossings, same generic steps: the counters agree."""
+    w = workloads.vortex_noise(128, iterations=1)
+    counts = []
+    for walk in (0, 1):
+        ke.step_counts()
+        ke.convolve(w.texture, w.u, w.v, kernel=w.kernel, walk=walk)
+        counts.append(ke.step_counts())
+    assert counts[0] == counts[1] and counts[0]["step"] == 128 * 128 * 64
+
+
+
 # ---- the `fma`-only arithmetic (rlic_b200.set_arithmetic("fma"): the x86-64 wheels' build) ----
 @pytest.mark.parametrize("name", GOLDEN_CASES)
 def test_fma_only_golden_vectors(name):

@@ -8,8 +8,9 @@
 # Steps (each independent; a failure is logged and the script goes on):
 #   1  the -m gpu suite (includes the first_gpu_run tests: XPASS = good)
 #   2  smoke() of __graft_entry__
-#   3  bench.py as the driver runs it, then with the wavefront schedule, then with the
-#      fma-only arithmetic (the JSON line's e2e.schedule / e2e.arithmetic say which)
+#   3  bench.py as the driver runs it, then with the grouped walk, the wavefront schedule and
+#      the fma-only arithmetic (the JSON line's e2e.walk / e2e.schedule / e2e.arithmetic say
+#      which), and the kernel lab's sweep of the grouped-walk formulations (tools/kernel_lab)
 #   4  every BASELINE configuration (tools/bench_configs.py), default and wavefront
 #   5  ncu launch list of one bench step, and a full capture of the f64 pass kernel
 set -u
@@ -32,9 +33,16 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks_throttle_reasons.acti
 step 900 pytest_gpu python -m pytest tests -q -m gpu -rxX
 step 120 smoke python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')"
 step 240 bench_default python bench.py --steps 10 --warmup 3
+step 240 bench_grouped env RLIC_B200_WALK=grouped python bench.py --steps 10 --warmup 3 --no-cpu-baseline
+if [ -x tools/kernel_lab ]; then
+    step 300 lab_grouped_f32_f64 tools/kernel_lab 4096 65 grouped
+    step 120 lab_shipped tools/kernel_lab 4096 65 shipped
+    step 300 lab_grouped_c3_field tools/kernel_lab 4096 65 grouped 1
+fi
 step 240 bench_wavefront env RLIC_B200_SCHEDULE=wavefront python bench.py --steps 10 --warmup 3 --no-cpu-baseline
 step 240 bench_fma env RLIC_B200_ARITHMETIC=fma python bench.py --steps 10 --warmup 3 --no-cpu-baseline
 step 300 configs_default python tools/bench_configs.py --configs c1,c2,c3,c4
+step 300 configs_grouped env RLIC_B200_WALK=grouped python tools/bench_configs.py --configs c1,c2,c3,c4
 step 300 configs_wavefront env RLIC_B200_SCHEDULE=wavefront python tools/bench_configs.py --configs c2,c4
 if command -v ncu >/dev/null; then
     step 300 ncu_launches ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv \

@@ -10,6 +10,8 @@
 //   lab3  precomputed refined reciprocals in the packed field  -> adopted
 //   lab5-10  launch bounds, sign arithmetic, zero components, admission tests, tap addressing
 //   lab11 wall sentinels in padded buffers (no column counter, no wall compares)  -> adopted
+//   lab18 (written without a GPU, to be run first thing in round 2) the grouped walk: WALK
+//         bits x sign flavours 0-3; static SASS counts in profiles/r1_sass_steps_grouped_walk.txt
 #include "../rlic_b200/csrc/lic_walk.cuh"
 
 #include <cstdio>
@@ -156,7 +158,8 @@ struct Result { std::string name; float ms; bool same; int regs; };
 template <typename T>
 void run_type(const char *tname, int n, int L, const char *only)
 {
-    const int reps = only ? 1 : 5;
+    // LAB_REPS=1 for a run under ncu
+    const int reps = getenv("LAB_REPS") ? atoi(getenv("LAB_REPS")) : 5;
     const size_t count = (size_t)n * n;
     PassGeom g{};
     g.nx = n; g.pitch = n + 2; g.rows = n; g.field_stride = rlic::padded_cells(n, n);
@@ -198,7 +201,7 @@ void run_type(const char *tname, int n, int L, const char *only)
         }
         CK(cudaGetLastError());
         cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, k));
-        if (!only || strstr("shipped", only)) results.push_back({"shipped", best, true, fa.numRegs});
+        results.push_back({"shipped", best, true, fa.numRegs});   // always listed: the yardstick of the run
         CK(cudaMemcpy(h_ref.data(), ref, cells * sizeof(T), cudaMemcpyDeviceToHost));
     }
 #define CAND(NAME, TW, TH, UNROLL, MINB, FLAVOR, ADMIT) do { \
@@ -276,6 +279,69 @@ void run_type(const char *tname, int n, int L, const char *only)
             CANDPERS("persist b6 6x1", 6, 2, 0, 2, 6, 1);
         }
         CK(cudaFree(counters));
+    }
+    // grouped walk (lic_walk.cuh: walk_step / half_walk_grouped).  WALK bits: 1 grouped,
+    // 2 pitch pinned in a uniform register, 4 the constant 1.0 pinned, 8 loop control on the
+    // byte offset.  "tuned" is what rlic_b200_set_walk(RLIC_B200_WALK_GROUPED) launches.
+#define CANDW(NAME, POL, UNROLL, MINB, FLAVOR, ADMIT, WALK) do { \
+        if (only && !strstr(NAME, only)) break; \
+        auto kref = rlic::lic_pass_kernel<T, POL, PT, int>; \
+        auto k = rlic::lic_pass_kernel<T, POL, PT, int, 16, 16, UNROLL, MINB, FLAVOR, ADMIT, true, WALK>; \
+        CK(cudaMemset(ref, 0, cells * sizeof(T))); \
+        kref<<<g.tiles_per_field, 256>>>(ptex, field, ref, g, taps, L); \
+        CK(cudaMemcpy(h_ref.data(), ref, cells * sizeof(T), cudaMemcpyDeviceToHost)); \
+        float best = 1e9; \
+        CK(cudaMemset(out, 0, cells * sizeof(T))); \
+        for (int r = 0; r < reps + 1; ++r) { \
+            CK(cudaEventRecord(e0)); \
+            k<<<g.tiles_per_field, 256>>>(ptex, field, out, g, taps, L); \
+            CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); \
+            float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); if (r) best = fminf(best, ms); \
+        } \
+        CK(cudaGetLastError()); \
+        CK(cudaMemcpy(h_out.data(), out, cells * sizeof(T), cudaMemcpyDeviceToHost)); \
+        bool same = memcmp(h_out.data(), h_ref.data(), cells * sizeof(T)) == 0; \
+        cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, k)); \
+        results.push_back({NAME, best, same, fa.numRegs}); \
+    } while (0)
+    {
+        using TV = rlic::Tune<T, false>;
+        using TP = rlic::Tune<T, true>;
+        CANDW("grouped tuned vel", false, TV::unroll, TV::min_blocks, TV::walk_flavor, TV::admit, TV::walk);
+        CANDW("grouped tuned pol", true, TP::unroll, TP::min_blocks, TP::walk_flavor, TP::admit, TP::walk);
+        if (sizeof(T) == 4) {
+            CANDW("grouped vel w1 f1", false, 4, 8, 1, 3, 1);
+            CANDW("grouped vel w1 f2", false, 4, 8, 2, 3, 1);
+            CANDW("grouped vel w3 f2", false, 4, 8, 2, 3, 3);
+            CANDW("grouped vel w5 f2", false, 4, 8, 2, 3, 5);
+            CANDW("grouped vel w7 f2", false, 4, 8, 2, 3, 7);
+            CANDW("grouped vel w15 f2", false, 4, 8, 2, 3, 15);
+            CANDW("grouped vel w7 f2 u2", false, 2, 8, 2, 3, 7);
+            CANDW("grouped vel w7 f2 u8", false, 8, 8, 2, 3, 7);
+            CANDW("grouped vel w7 f3", false, 4, 8, 3, 3, 7);
+            CANDW("grouped vel w1 f0", false, 4, 8, 0, 3, 1);
+            CANDW("grouped vel w7 f2 a2", false, 4, 8, 2, 2, 7);
+            CANDW("grouped pol w1 f0", true, 4, 8, 0, 3, 1);
+            CANDW("grouped pol w9 f0", true, 4, 8, 0, 3, 9);
+            CANDW("grouped pol w1 f2", true, 4, 8, 2, 3, 1);
+            CANDW("grouped pol w7 f2", true, 4, 8, 2, 3, 7);
+        } else {
+            CANDW("grouped vel w1 f0", false, 2, 6, 0, 2, 1);
+            CANDW("grouped vel w9 f0", false, 2, 6, 0, 2, 9);
+            CANDW("grouped vel w11 f0", false, 2, 6, 0, 2, 11);
+            CANDW("grouped vel w1 f2", false, 2, 6, 2, 2, 1);
+            CANDW("grouped vel w5 f2", false, 2, 6, 2, 2, 5);
+            CANDW("grouped vel w11 f0 u4", false, 4, 6, 0, 2, 11);
+            CANDW("grouped pol w1 f0", true, 2, 5, 0, 2, 1);
+            CANDW("grouped pol w9 f0", true, 2, 5, 0, 2, 9);
+            CANDW("grouped pol w11 f0", true, 2, 5, 0, 2, 11);
+            CANDW("grouped pol w1 f2", true, 2, 5, 2, 2, 1);
+            CANDW("grouped pol w9 f0 b4", true, 2, 4, 0, 2, 9);
+        }
+        // the later CAND()s compare with the velocity result of the shipped kernel
+        auto kref = rlic::lic_pass_kernel<T, false, PT, int>;
+        kref<<<g.tiles_per_field, 256>>>(ptex, field, ref, g, taps, L);
+        CK(cudaMemcpy(h_ref.data(), ref, cells * sizeof(T), cudaMemcpyDeviceToHost));
     }
     //    name              TW  TH  unroll minblocks flavor admit
     CAND("u2 b8 f1 a3", 16, 16, 2, 8, 1, 3);

@@ -1,0 +1,37 @@
+// Instantiates the pass-kernel formulations that tools/sass_steps.py counts (developer tool;
+// nothing here is linked into librlic_b200.so).  Compiled to a cubin only, never run.
+#include "../rlic_b200/csrc/lic_walk.cuh"
+using namespace rlic;
+using PT32 = ParamTaps<float, kParamTapBytes / 4>;
+using PT64 = ParamTaps<double, kParamTapBytes / 8>;
+
+template <typename T, bool POL, typename PT, int WALK, int FLAVOR> const void *variant()
+{
+    using Tn = Tune<T, POL>;
+    return (const void *)&lic_pass_kernel<T, POL, PT, int, kTileW, kTileH, Tn::unroll, Tn::min_blocks, FLAVOR,
+                                          Tn::admit, true, WALK>;
+}
+template <typename T, bool POL, typename PT> const void *shipped()
+{
+    return (const void *)&lic_pass_kernel<T, POL, PT, int>;
+}
+template <typename T, bool POL, typename PT> const void *tuned_grouped()
+{
+    using Tn = Tune<T, POL>;
+    return variant<T, POL, PT, Tn::walk, Tn::walk_flavor>();
+}
+
+#define SWEEP(T, POL, PT, FLAVOR) \
+    variant<T, POL, PT, 1, FLAVOR>(), variant<T, POL, PT, 3, FLAVOR>(), variant<T, POL, PT, 5, FLAVOR>(), \
+    variant<T, POL, PT, 7, FLAVOR>(), variant<T, POL, PT, 9, FLAVOR>(), variant<T, POL, PT, 11, FLAVOR>()
+
+const void *table[] = {
+    shipped<float, false, PT32>(), shipped<float, true, PT32>(),
+    shipped<double, false, PT64>(), shipped<double, true, PT64>(),
+    tuned_grouped<float, false, PT32>(), tuned_grouped<float, true, PT32>(),
+    tuned_grouped<double, false, PT64>(), tuned_grouped<double, true, PT64>(),
+    SWEEP(float, false, PT32, 1), SWEEP(float, false, PT32, 2), SWEEP(float, false, PT32, 0),
+    SWEEP(float, true, PT32, 0), SWEEP(float, true, PT32, 2),
+    SWEEP(double, false, PT64, 0), SWEEP(double, false, PT64, 2),
+    SWEEP(double, true, PT64, 0), SWEEP(double, true, PT64, 2),
+};
