@@ -37,6 +37,7 @@ step 240 bench_grouped env RLIC_B200_WALK=grouped python bench.py --steps 10 --w
 if [ -x tools/kernel_lab ]; then
     step 300 lab_grouped_f32_f64 tools/kernel_lab 4096 65 grouped
     step 120 lab_shipped tools/kernel_lab 4096 65 shipped
+    step 120 lab_gather_ceiling tools/kernel_lab 4096 65 ceiling
     step 300 lab_grouped_c3_field tools/kernel_lab 4096 65 grouped 1
 fi
 step 240 bench_wavefront env RLIC_B200_SCHEDULE=wavefront python bench.py --steps 10 --warmup 3 --no-cpu-baseline
