@@ -4,7 +4,11 @@ limits 2^-40 / 2^40 and their neighbours, denormals, the largest finite values, 
 60 decades of dynamic range -- over both dtypes, both modes, every wall combination, both
 arithmetic builds and both index widths.  Bitwise comparison, NaN payloads included.
 
-    python tools/emulation_campaign.py <first seed> <seconds>
+    python tools/emulation_campaign.py <first seed> <seconds> [walk]
+
+`walk` (default 0) selects the formulation of the pass kernels: 0 per-step, 1 the grouped walk
+as the library dispatches it (rlic::Tune), "mix" picks per case among the per-step walk, the
+tuned grouped walk and explicit (flavor, walk) pairs of the grouped walk.
 
 Round 1: seeds 100000..233822 (133 823 cases, 300 s on 8 cores): 0 mismatches.
 """
@@ -27,7 +31,7 @@ def nasty(rng, shape, dtype):
         else: a=(rng.random(shape)-0.5)
         return a.astype(dtype)
 t0=time.time(); n=0; bad=0
-seed0=int(sys.argv[1]); budget=float(sys.argv[2])
+seed0=int(sys.argv[1]); budget=float(sys.argv[2]); walk_arg=sys.argv[3] if len(sys.argv)>3 else "0"
 seed=seed0
 while time.time()-t0<budget:
     rng=np.random.default_rng(seed); seed+=1
@@ -37,13 +41,22 @@ while time.time()-t0<budget:
     k=(rng.random(klen)-0.3).astype(dtype)
     mode=["velocity","polarization"][rng.integers(2)]; walls=WALLS[rng.integers(4)]; its=int(rng.integers(1,4))
     branchless=bool(rng.integers(2)); wide=bool(rng.integers(2))
+    how={}
+    if walk_arg=="mix":
+        pick=int(rng.integers(4))
+        if pick==1: how=dict(walk=1)
+        elif pick>=2: how=dict(walk=[1,9][int(rng.integers(2))],flavor=int(rng.integers(4)),admit=int(rng.integers(4)))
+    elif walk_arg!="0": how=dict(walk=int(walk_arg))
+    if how: branchless=True                      # the grouped walk exists for the default arithmetic
+    if "flavor" in how: wide=False; klen=min(klen,60)   # explicit formulations: 32-bit indices only
+    k=k[:klen]
     with np.errstate(all="ignore"):
-        got=ke.convolve(tex,u,v,kernel=k,uv_mode=mode,boundaries=walls,iterations=its,branchless=branchless,wide=wide)
+        got=ke.convolve(tex,u,v,kernel=k,uv_mode=mode,boundaries=walls,iterations=its,branchless=branchless,wide=wide,**how)
         want=oracle.convolve(tex,u,v,kernel=k,uv_mode=mode,boundaries=walls,iterations=its,variant=3 if branchless else 1)
     n+=1
     if not np.array_equal(got.view(np.uint8),want.view(np.uint8)):
         # allow NaN payload differences? report both
         same_val=np.array_equal(got,want,equal_nan=True)
-        bad+=1; print("MISMATCH seed",seed-1,dtype.__name__,(ny,nx),klen,mode,walls,its,"branchless",branchless,"values equal:",same_val, "ndiff",(got!=want).sum(), flush=True)
+        bad+=1; print("MISMATCH seed",seed-1,dtype.__name__,(ny,nx),klen,mode,walls,its,"branchless",branchless,how,"values equal:",same_val, "ndiff",(got!=want).sum(), flush=True)
         if bad>10: break
 print("cases",n,"bad",bad,"seeds",seed0,"..",seed-1)
