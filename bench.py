@@ -188,6 +188,21 @@ def parity_of_sample(one_pass: np.ndarray, r0: int, band: np.ndarray) -> dict:
     }
 
 
+def path_divergence(rlic_b200, u: np.ndarray, v: np.ndarray, r0: int, rows: int) -> dict:
+    """Fraction of the sample's pixels whose walker visits different pixels on the GPU than
+    in the CPU oracle: both run one pass over an exact path-signature texture
+    (workloads.path_probe), so any difference is a different path, never rounding."""
+    import oracle
+    from rlic_b200 import workloads
+
+    probe, ones = workloads.path_probe((N_SIDE, N_SIDE), np.float32, TAPS)
+    mine = rlic_b200.convolve(probe, u, v, kernel=ones, boundaries="closed", iterations=1)
+    want = oracle.pass_rows(probe, u, v, kernel=ones, rows=(r0, r0 + rows), threads=oracle.max_threads())
+    return {"path_divergence_fraction": float(np.mean(mine[r0:r0 + rows] != want)),
+            "path_probe": "one pass over random integers < 2^17 with a kernel of ones: exact sums, "
+                          "equal iff the same pixels were visited"}
+
+
 def run_reference(args) -> dict:
     """--impl reference: the CPU implementation of the path on the host cores."""
     rank = int(os.environ.get("RANK", "0"))
@@ -457,6 +472,7 @@ def run_ours(args) -> dict:
         try:   # a reporting extra: never allowed to take the bench line down with it
             one_pass = rlic_b200.convolve(h_tex, h_u, h_v, kernel=kernel, boundaries="closed", iterations=1)
             line["parity"] = parity_of_sample(one_pass, r0, band)
+            line["parity"].update(path_divergence(rlic_b200, h_u, h_v, r0, band.shape[0]))
         except Exception as exc:  # noqa: BLE001
             line["parity"] = {"error": f"{type(exc).__name__}: {exc}"}
         single = cpu_baseline(1, 4.0)

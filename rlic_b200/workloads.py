@@ -56,6 +56,21 @@ def triangle_kernel(length: int, dtype) -> np.ndarray:
     return (1 - np.abs(np.linspace(-1, 1, length))).astype(dtype)
 
 
+def path_probe(shape, dtype, taps: int, seed: int = 0):
+    """Inputs that turn one convolution pass into an exact signature of the pixels each
+    walker visited (the path-divergence fraction): a texture of random
+    integers below 2^17 and a kernel of ones.  A pixel's result is then the plain sum of at
+    most ``taps`` such integers -- below 2^24, so it is exact in f32 and f64 whatever the
+    order or fusing of the additions -- and two implementations return the same number iff
+    their walkers visited the same pixels the same number of times (up to a 2^-17 chance of
+    a collision).  Comparing two such images counts diverging *paths*, not rounding."""
+    if taps * (1 << 17) > (1 << 24):
+        raise ValueError("too many taps for an exact f32 sum")
+    rng = np.random.default_rng(seed)
+    texture = rng.integers(0, 1 << 17, size=shape).astype(dtype)
+    return texture, np.ones(taps, dtype=dtype)
+
+
 def vortex(ny: int, nx: int, dtype, drift: float = 0.0):
     """Solid-body rotation about the image centre; even sizes have no exact zeros."""
     y = np.linspace(-1, 1, ny, dtype=np.float64)

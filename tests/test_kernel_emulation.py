@@ -608,3 +608,28 @@ def test_an_order_that_breaks_a_dependency_is_caught():
     got = run_in_order(order, tex, u, v, kernel, "closed", "velocity", band_rows, iterations)
     want = oracle.convolve(tex, u, v, kernel=kernel, boundaries=WALLS["closed"], iterations=iterations)
     assert not np.array_equal(got, want, equal_nan=True)
+
+
+# ---------------------------------------------------------------------------
+# Path signatures (workloads.path_probe): an exact measure of path divergence.
+
+def test_path_probe_counts_diverging_paths_not_rounding():
+    """On the probe inputs a pass returns exact integer sums.  The kernel source (either walk)
+    visits exactly the oracle's pixels; the reference's other build (`fma` alone) takes a
+    different path for a small fraction of the walkers, and the probe counts those."""
+    w = workloads.vortex_noise(256, iterations=1)
+    probe, ones = workloads.path_probe(w.texture.shape, np.float32, w.kernel.size)
+    want = oracle.convolve(probe, w.u, w.v, kernel=ones)
+    assert_array_equal(want, np.round(want))                      # integer sums: nothing was rounded
+    assert want.max() < 2 ** 24
+    for walk in (0, 1):
+        assert_array_equal(ke.convolve(probe, w.u, w.v, kernel=ones, walk=walk), want)
+    other = oracle.convolve(probe, w.u, w.v, kernel=ones, variant=1)
+    diverged = float(np.mean(other != want))
+    assert 0.0 < diverged < 0.02
+    # the value-based comparison on a noise texture sees (at least) the same walkers
+    noisy = oracle.convolve(w.texture, w.u, w.v, kernel=w.kernel)
+    noisy_other = oracle.convolve(w.texture, w.u, w.v, kernel=w.kernel, variant=1)
+    assert float(np.mean(noisy != noisy_other)) >= diverged * 0.9
+    with pytest.raises(ValueError):
+        workloads.path_probe((4, 4), np.float32, 200)

@@ -15,6 +15,7 @@ import pytest
 from numpy.testing import assert_array_equal
 
 import oracle
+from _status import first_gpu_run
 import rlic_b200 as rlic
 from rlic_b200 import _core, workloads
 
@@ -246,6 +247,27 @@ def test_mismatch_fraction_against_the_pypi_x86_64_variant(capsys):
               f"max {err.max():.3e}")
     assert diverged < 5e-3
     assert bit_equal > 0.5
+
+
+@first_gpu_run
+def test_path_divergence_is_zero_against_the_oracle_and_small_against_the_other_build(capsys):
+    """north_star: "the fraction of pixels whose traced path diverges is reported".  On the
+    path-signature inputs (workloads.path_probe) a pass returns exact integer sums, so the
+    comparison counts different *paths*: none against the oracle of the default build, a
+    small minority against the `fma`-only build (whose edge times differ in the last bit)."""
+    for n, dtype in ((1024, np.float32), (512, np.float64)):
+        w = workloads.vortex_noise(n, dtype=dtype, iterations=1)
+        probe, ones = workloads.path_probe(w.texture.shape, dtype, w.kernel.size)
+        got = rlic.convolve(probe, w.u, w.v, kernel=ones)
+        want = oracle.convolve(probe, w.u, w.v, kernel=ones, threads=oracle.max_threads())
+        assert_array_equal(got, want)
+        other = oracle.convolve(probe, w.u, w.v, kernel=ones, variant=oracle.VARIANT_FMA,
+                                threads=oracle.max_threads())
+        diverged = float(np.mean(got != other))
+        with capsys.disabled():
+            print(f"\n[path divergence, {np.dtype(dtype).name} {n}x{n}] vs default build 0, "
+                  f"vs fma-only build {diverged:.4%}")
+        assert diverged < 0.02
 
 
 def test_concurrent_calls_are_independent():
