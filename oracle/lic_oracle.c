@@ -20,6 +20,10 @@
  *     oracle reproduces to within rounding of the 8-bit colours
  *     (tests/test_reference_images.py; about 1/256 of the dynamic range per
  *     pixel, so an algorithmic pin, not a bit-level one)
+ *   - the eight inputs of the reference's regression test (its tests/
+ *     test_regressions.py, held there to vectorplot's LIC at rtol 1.5e-7), against
+ *     an exact rational-arithmetic tracer at the same tolerances
+ *     (tests/test_regressions.py; vectorplot itself is not installable here)
  * It is NOT pinned against output ARRAYS produced by the reference itself:
  * at the bit level the status is "parity unpinned" (DESIGN.md section 3 says
  * the same).
