@@ -16,7 +16,7 @@
  *     cases, default-argument equalities)
  *   - a second, independent pure-Python restatement (oracle/pyoracle.py)
  *   - the only outputs of the real rLIC available offline: the five LIC
- *     panels of its README figures (static/*.png, seeded inputs), which this
+ *     panels of its README figures (the PNG files under static/, seeded inputs), which this
  *     oracle reproduces to within rounding of the 8-bit colours
  *     (tests/test_reference_images.py; about 1/256 of the dynamic range per
  *     pixel, so an algorithmic pin, not a bit-level one)
