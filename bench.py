@@ -327,7 +327,10 @@ def run_ours(args) -> dict:
     else:
         from rlic_b200.sharded import ShardedConvolver
 
-        sc = ShardedConvolver(N_SIDE * world, N_SIDE, kernel=kernel, boundaries="closed")
+        # RLIC_B200_EXCHANGE=peer: the halo exchange fused into the edge-strip kernels (peer
+        # stores over NVLink) instead of NCCL messages; opt-in until it has run on hardware
+        sc = ShardedConvolver(N_SIDE * world, N_SIDE, kernel=kernel, boundaries="closed",
+                              exchange=os.environ.get("RLIC_B200_EXCHANGE", "nccl"))
         sc.set_field(d_u, d_v)
 
         def step(events=None):
@@ -457,6 +460,8 @@ def run_ours(args) -> dict:
                   else "per rank: pinned host slab -> ShardedConvolver -> pinned host slab",
            "schedule": rlic_b200.get_schedule(), "arithmetic": rlic_b200.get_arithmetic(),
            "walk": rlic_b200.get_walk()}
+    if world > 1:
+        e2e["exchange"] = sc.exchange
 
     line = {
         "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps,

@@ -361,6 +361,55 @@ int rlic_b200_pass_slab_f64(const double *d_texture, const double *d_field, doub
                             void *stream);
 
 /*
+ * FUSED HALO EXCHANGE (row-slab sharding, one process per GPU; rlic_b200/sharded.py with
+ * exchange="peer").  Not yet run on hardware: the NCCL exchange is the default.
+ *
+ *   pass_slab_peer   rlic_b200_pass_slab_* that also stores every result of the rows it
+ *                    computes -- the pixels and the two wall cells that travel with each
+ *                    row -- into a neighbour's padded buffer `d_peer_out` (mapped with
+ *                    rlic_b200_peer_open), `peer_row_delta` buffer rows away from where
+ *                    they land locally: the pass over an edge strip and the shipping of
+ *                    that strip into the neighbour's halo are one kernel, the transfer
+ *                    going over NVLink as the tiles finish.  Default arithmetic only.
+ *   peer_alloc       device memory that other processes can map (cudaMalloc + an IPC
+ *                    handle of RLIC_B200_PEER_HANDLE_BYTES bytes), zero-filled
+ *   peer_open/close  map / unmap another process's allocation from its handle
+ *   peer_signal      after everything enqueued so far on `stream`: raise the 32-bit counter
+ *                    `d_flag` (normally in a neighbour's memory) to `value`, with
+ *                    system-scope fences around the store
+ *   peer_wait        hold `stream` until the counter `d_flag` (in local memory) has reached
+ *                    `value` (signed distance, so counters may wrap); after `timeout_ms`
+ *                    the wait gives up and sets *d_timed_out (device memory, may be NULL)
+ *                    instead of wedging the device
+ */
+#define RLIC_B200_PEER_HANDLE_BYTES 64
+int rlic_b200_pass_slab_peer_f32(const float *d_texture, const float *d_field, float *d_out,
+                                 int64_t ny, int64_t nx,
+                                 int64_t row0, int64_t nrows, int64_t halo_lo, int64_t halo_hi,
+                                 int64_t sub_row0, int64_t sub_nrows,
+                                 const float *kernel, int64_t klen,
+                                 int uv_mode,
+                                 int x_left, int x_right, int y_left, int y_right,
+                                 float *d_peer_out, int64_t peer_row_delta,
+                                 void *stream);
+int rlic_b200_pass_slab_peer_f64(const double *d_texture, const double *d_field, double *d_out,
+                                 int64_t ny, int64_t nx,
+                                 int64_t row0, int64_t nrows, int64_t halo_lo, int64_t halo_hi,
+                                 int64_t sub_row0, int64_t sub_nrows,
+                                 const double *kernel, int64_t klen,
+                                 int uv_mode,
+                                 int x_left, int x_right, int y_left, int y_right,
+                                 double *d_peer_out, int64_t peer_row_delta,
+                                 void *stream);
+int rlic_b200_peer_alloc(int64_t bytes, void **ptr, unsigned char *handle);
+int rlic_b200_peer_open(const unsigned char *handle, void **ptr);
+int rlic_b200_peer_close(void *ptr);
+int rlic_b200_peer_free(void *ptr);
+int rlic_b200_peer_signal(uint32_t *d_flag, uint32_t value, void *stream);
+int rlic_b200_peer_wait(const uint32_t *d_flag, uint32_t value, int64_t timeout_ms, int *d_timed_out,
+                        void *stream);
+
+/*
  * BATCH of independent fields on the host (BASELINE config 5): `nfields`
  * images of ny x nx stored back to back in each of texture/u/v/out, split
  * whole-image over the listed devices (one host thread + stream pair per

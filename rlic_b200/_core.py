@@ -61,6 +61,7 @@ def _signatures(real) -> dict[str, list]:
         "slab_pad_texture": [_vp, *slab, *walls, _vp, _vp],
         "slab_unpad_texture": [_vp, *slab, *walls, _vp, _vp],
         "pass_slab": [_vp, _vp, _vp, *slab, _i64, _i64, p, _i64, _int, *walls, _vp],
+        "pass_slab_peer": [_vp, _vp, _vp, *slab, _i64, _i64, p, _i64, _int, *walls, _vp, _i64, _vp],
     }
 
 
@@ -97,6 +98,16 @@ def _load() -> ctypes.CDLL:
     cdll.rlic_b200_get_schedule.restype = _int
     cdll.rlic_b200_debug_wavefront_order.argtypes = [_i64, _i64, ctypes.POINTER(ctypes.c_int32), _i64]
     cdll.rlic_b200_debug_wavefront_order.restype = _i64
+    # peer memory and flags of the fused halo exchange (rlic_b200/sharded.py)
+    handle = ctypes.POINTER(ctypes.c_ubyte)
+    cdll.rlic_b200_peer_alloc.argtypes = [_i64, ctypes.POINTER(_vp), handle]
+    cdll.rlic_b200_peer_open.argtypes = [handle, ctypes.POINTER(_vp)]
+    cdll.rlic_b200_peer_close.argtypes = [_vp]
+    cdll.rlic_b200_peer_free.argtypes = [_vp]
+    cdll.rlic_b200_peer_signal.argtypes = [_vp, ctypes.c_uint32, _vp]
+    cdll.rlic_b200_peer_wait.argtypes = [_vp, ctypes.c_uint32, _i64, _vp, _vp]
+    for name in ("alloc", "open", "close", "free", "signal", "wait"):
+        getattr(cdll, f"rlic_b200_peer_{name}").restype = _int
     cdll.rlic_b200_set_walk.argtypes = [_int]
     cdll.rlic_b200_set_walk.restype = _int
     cdll.rlic_b200_get_walk.restype = _int

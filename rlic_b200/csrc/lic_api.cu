@@ -241,13 +241,29 @@ template <typename T> struct TapSet {
     }
 };
 
+// Where the results of a pass over an edge strip also go when the halo exchange is fused
+// into it (rlic_b200_pass_slab_peer_*): the neighbour's padded buffer and the cell offset
+// between a row here and the same row there.
+template <typename T> struct PeerTarget {
+    T *out = nullptr;
+    long long delta = 0;
+};
+
 template <typename T, bool POL, typename Taps, typename Idx>
 cudaError_t launch_one(const T *tex, const Field<T> *field, T *out, const PassGeom &g,
                        const Taps &taps, int ntaps, unsigned blocks, bool branchless, bool grouped,
-                       cudaStream_t stream)
+                       const PeerTarget<T> &peer, cudaStream_t stream)
 {
     using Tn = rlic::Tune<T, POL>;
-    if (branchless && grouped)
+    if (peer.out) {   // the default arithmetic only (checked by the caller)
+        if (grouped)
+            rlic::lic_pass_peer_kernel<T, POL, Taps, Idx, rlic::kTileW, rlic::kTileH, Tn::unroll,
+                                       Tn::min_blocks, Tn::walk_flavor, Tn::admit, true, Tn::walk>
+                <<<blocks, rlic::kThreads, 0, stream>>>(tex, field, out, g, taps, ntaps, peer.out, peer.delta);
+        else
+            rlic::lic_pass_peer_kernel<T, POL, Taps, Idx>
+                <<<blocks, rlic::kThreads, 0, stream>>>(tex, field, out, g, taps, ntaps, peer.out, peer.delta);
+    } else if (branchless && grouped)
         rlic::lic_pass_kernel<T, POL, Taps, Idx, rlic::kTileW, rlic::kTileH, Tn::unroll, Tn::min_blocks,
                               Tn::walk_flavor, Tn::admit, true, Tn::walk>
             <<<blocks, rlic::kThreads, 0, stream>>>(tex, field, out, g, taps, ntaps);
@@ -267,7 +283,7 @@ cudaError_t launch_one(const T *tex, const Field<T> *field, T *out, const PassGe
 template <typename T>
 int launch_pass(const T *tex, const Field<T> *field, T *out, PassGeom g, int64_t nfields,
                 int64_t first_row, int64_t out_rows, int uv_mode, const TapSet<T> &taps,
-                cudaStream_t stream)
+                cudaStream_t stream, const PeerTarget<T> &peer = PeerTarget<T>{})
 {
     if (out_rows <= 0 || g.nx <= 0 || nfields <= 0)
         return RLIC_B200_OK;
@@ -286,10 +302,12 @@ int launch_pass(const T *tex, const Field<T> *field, T *out, PassGeom g, int64_t
     const bool pol = uv_mode == RLIC_B200_POLARIZATION;
     const bool branchless = g_arithmetic.load(std::memory_order_relaxed) == RLIC_B200_ARITH_FMA_BRANCHLESS;
     const bool grouped = g_walk.load(std::memory_order_relaxed) == RLIC_B200_WALK_GROUPED;
+    if (peer.out && (!branchless || nfields != 1))
+        return fail(RLIC_B200_EINVAL, "the fused halo exchange needs the default arithmetic and one field");
 
     cudaError_t e;
 #define RLIC_LAUNCH(POL, TAPS, TAPV, IDX) \
-    e = launch_one<T, POL, TAPS, IDX>(tex, field, out, g, TAPV, taps.ntaps, (unsigned)blocks, branchless, grouped, stream)
+    e = launch_one<T, POL, TAPS, IDX>(tex, field, out, g, TAPV, taps.ntaps, (unsigned)blocks, branchless, grouped, peer, stream)
     using PT = rlic::ParamTaps<T, TapSet<T>::kMaxParam>;
     using GT = rlic::GlobalTaps<T>;
     const GT gt{static_cast<const T *>(taps.global.p)};
@@ -740,7 +758,7 @@ int slab_unpad_texture(const T *d_padded, int64_t ny, int64_t nx, const Slab &sl
 template <typename T>
 int pass_slab(const T *d_tex, const T *d_field, T *d_out, int64_t ny, int64_t nx, const Slab &sl,
               int64_t sub0, int64_t subn, const T *kernel, int64_t klen, int uv_mode,
-              const Walls &w, void *stream)
+              const Walls &w, void *stream, T *peer_out = nullptr, int64_t peer_row_delta = 0)
 {
     if (int rc = check_common(ny, nx, klen, uv_mode, w))
         return rc;
@@ -757,8 +775,11 @@ int pass_slab(const T *d_tex, const T *d_field, T *d_out, int64_t ny, int64_t nx
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     TapSet<T> taps;
     CUDA_TRY(taps.prepare(kernel, klen, s));
+    PeerTarget<T> peer;
+    peer.out = peer_out;
+    peer.delta = (long long)peer_row_delta * g.pitch;
     return launch_pass<T>(d_tex, reinterpret_cast<const Field<T> *>(d_field), d_out, g, 1,
-                          sl.halo_lo + sub0, subn, uv_mode, taps, s);
+                          sl.halo_lo + sub0, subn, uv_mode, taps, s, peer);
 }
 
 // Whole fields split over devices.  Two host threads per device take chunks
@@ -1082,5 +1103,98 @@ int rlic_b200_set_device(int device)
 
 RLIC_DEFINE(float, f32)
 RLIC_DEFINE(double, f64)
+
+#define RLIC_DEFINE_PEER(T, sfx)                                                                 \
+    int rlic_b200_pass_slab_peer_##sfx(const T *d_texture, const T *d_field, T *d_out,           \
+                                       int64_t ny, int64_t nx, int64_t row0, int64_t nrows,      \
+                                       int64_t halo_lo, int64_t halo_hi, int64_t sub_row0,       \
+                                       int64_t sub_nrows, const T *kernel, int64_t klen,         \
+                                       int uv_mode, int x_left, int x_right, int y_left,         \
+                                       int y_right, T *d_peer_out, int64_t peer_row_delta,       \
+                                       void *stream)                                             \
+    {                                                                                            \
+        tls_error.clear();                                                                       \
+        if (!d_peer_out)                                                                         \
+            return fail(RLIC_B200_EINVAL, "null peer buffer");                                   \
+        return pass_slab<T>(d_texture, d_field, d_out, ny, nx,                                   \
+                            Slab{row0, nrows, halo_lo, halo_hi}, sub_row0, sub_nrows, kernel,    \
+                            klen, uv_mode, Walls{x_left, x_right, y_left, y_right}, stream,      \
+                            d_peer_out, peer_row_delta);                                         \
+    }
+RLIC_DEFINE_PEER(float, f32)
+RLIC_DEFINE_PEER(double, f64)
+
+// ---- peer memory and flags of the fused halo exchange (one process per GPU) ----
+int rlic_b200_peer_alloc(int64_t bytes, void **ptr, unsigned char *handle)
+{
+    tls_error.clear();
+    if (bytes <= 0 || !ptr || !handle)
+        return fail(RLIC_B200_EINVAL, "bad argument to peer_alloc");
+    static_assert(sizeof(cudaIpcMemHandle_t) == RLIC_B200_PEER_HANDLE_BYTES, "handle size");
+    void *p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, (size_t)bytes));          // not the stream-ordered pool: IPC needs a plain allocation
+    cudaError_t e = cudaMemset(p, 0, (size_t)bytes);
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess)
+        e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        CUDA_TRY(e);
+    }
+    std::memcpy(handle, &h, sizeof h);
+    *ptr = p;
+    return RLIC_B200_OK;
+}
+
+int rlic_b200_peer_open(const unsigned char *handle, void **ptr)
+{
+    tls_error.clear();
+    if (!handle || !ptr)
+        return fail(RLIC_B200_EINVAL, "bad argument to peer_open");
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof h);
+    CUDA_TRY(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return RLIC_B200_OK;
+}
+
+int rlic_b200_peer_close(void *ptr)
+{
+    tls_error.clear();
+    if (ptr)
+        CUDA_TRY(cudaIpcCloseMemHandle(ptr));
+    return RLIC_B200_OK;
+}
+
+int rlic_b200_peer_free(void *ptr)
+{
+    tls_error.clear();
+    if (ptr)
+        CUDA_TRY(cudaFree(ptr));
+    return RLIC_B200_OK;
+}
+
+int rlic_b200_peer_signal(uint32_t *d_flag, uint32_t value, void *stream)
+{
+    tls_error.clear();
+    if (!d_flag)
+        return fail(RLIC_B200_EINVAL, "null flag");
+    rlic::peer_signal_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(d_flag, value);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    return RLIC_B200_OK;
+}
+
+int rlic_b200_peer_wait(const uint32_t *d_flag, uint32_t value, int64_t timeout_ms, int *d_timed_out,
+                        void *stream)
+{
+    tls_error.clear();
+    if (!d_flag || timeout_ms <= 0)
+        return fail(RLIC_B200_EINVAL, "bad argument to peer_wait");
+    rlic::peer_wait_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(
+        d_flag, value, (long long)timeout_ms * 1000000ll, d_timed_out);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    return RLIC_B200_OK;
+}
 
 }  // extern "C"

@@ -18,14 +18,26 @@ with its two wall cells is the contiguous cell range
 The per-pixel arithmetic is the single-GPU kernel's, in global row numbers, so
 the gathered result is bit-identical to an unsharded run.
 
-The compute steps are injectable (``ops``) so the exchange logic can be
-exercised without a GPU; the default is the CUDA slab API of the C ABI.  There
-is no CPU compute path in this package.
+``exchange="peer"`` (opt-in; written after round 1's GPU time was spent, so the NCCL
+exchange stays the default until it has run on hardware) fuses the per-iteration
+texture exchange into the passes over the edge strips: the pass kernel stores every
+row it computes there into the neighbour's halo as well, through that neighbour's
+buffer mapped into this process (CUDA IPC; the stores travel over NVLink while the
+strip is still being computed), and two pairs of counters per neighbour -- raised by
+one-thread kernels after the launches they announce, awaited by one-thread kernels on
+the consumer's stream -- order the iterations: ``halo`` ("the rows for your pass n + 1
+are in your buffer") and ``free`` ("my pass n is done, its input buffer may be
+overwritten").  No separate exchange step, no host synchronisation, nothing on a side
+stream.
+
+The compute steps are injectable (``ops``), and so is the peer memory (``peers``), so the
+exchange logic can be exercised without a GPU; the defaults are the CUDA slab API and the
+CUDA IPC entry points of the C ABI.  There is no CPU compute path in this package.
 """
 
 from __future__ import annotations
 
-__all__ = ["SlabPlan", "ShardedConvolver", "CudaSlabOps"]
+__all__ = ["SlabPlan", "ShardedConvolver", "CudaSlabOps", "CudaPeerMemory"]
 
 import ctypes
 from dataclasses import dataclass
@@ -167,6 +179,129 @@ class CudaSlabOps:
             taps.ctypes.data_as(ctypes.POINTER(real)), taps.size, mode, *walls, self._stream()))
 
 
+    def pass_rows_peer(self, src, field, dst, plan, a, b, taps, mode, walls, peer, peer_row_delta):
+        """The pass over owned rows [a, b) that also stores them into ``peer`` (a neighbour's
+        padded buffer mapped into this process), ``peer_row_delta`` buffer rows away."""
+        from rlic_b200 import _core
+
+        sfx, real = self._kind(src)
+        _core.check(getattr(_core.lib, f"rlic_b200_pass_slab_peer_{sfx}")(
+            src.data_ptr(), field.data_ptr(), dst.data_ptr(), *plan.slab_args, a, b - a,
+            taps.ctypes.data_as(ctypes.POINTER(real)), taps.size, mode, *walls,
+            peer.data_ptr(), peer_row_delta, self._stream()))
+
+    def signal(self, flags, index, value):
+        """After everything enqueued so far: raise counter ``index`` of ``flags`` (int32
+        tensor, usually a neighbour's) to ``value``."""
+        from rlic_b200 import _core
+
+        _core.check(_core.lib.rlic_b200_peer_signal(flags.data_ptr() + 4 * index, value & 0xFFFFFFFF,
+                                                    self._stream()))
+
+    def wait(self, flags, index, value, timeout_ms, timed_out_index):
+        """Hold the stream until counter ``index`` of the local ``flags`` has reached ``value``;
+        past ``timeout_ms`` give up and set ``flags[timed_out_index]``."""
+        from rlic_b200 import _core
+
+        _core.check(_core.lib.rlic_b200_peer_wait(flags.data_ptr() + 4 * index, value & 0xFFFFFFFF, timeout_ms,
+                                                  flags.data_ptr() + 4 * timed_out_index, self._stream()))
+
+
+class _DevicePointer:
+    """A raw device allocation as a ``__cuda_array_interface__`` producer (zero-copy into torch)."""
+
+    def __init__(self, ptr: int, count: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": typestr, "data": (ptr, False),
+                                         "strides": None, "version": 3}
+
+
+class CudaPeerMemory:
+    """Device memory other ranks can map: the CUDA IPC entry points of the C ABI."""
+
+    _TYPESTR = {torch.float32: "<f4", torch.float64: "<f8", torch.int32: "<i4"}
+
+    def alloc(self, nbytes: int) -> tuple[int, bytes]:
+        from rlic_b200 import _core
+
+        ptr = ctypes.c_void_p()
+        handle = (ctypes.c_ubyte * 64)()
+        _core.check(_core.lib.rlic_b200_peer_alloc(nbytes, ctypes.byref(ptr), handle))
+        return int(ptr.value), bytes(handle)
+
+    def open(self, handle: bytes) -> int:
+        from rlic_b200 import _core
+
+        ptr = ctypes.c_void_p()
+        raw = (ctypes.c_ubyte * 64).from_buffer_copy(handle)
+        _core.check(_core.lib.rlic_b200_peer_open(raw, ctypes.byref(ptr)))
+        return int(ptr.value)
+
+    def close(self, ptr: int) -> None:
+        from rlic_b200 import _core
+
+        _core.check(_core.lib.rlic_b200_peer_close(ctypes.c_void_p(ptr)))
+
+    def free(self, ptr: int) -> None:
+        from rlic_b200 import _core
+
+        _core.check(_core.lib.rlic_b200_peer_free(ctypes.c_void_p(ptr)))
+
+    def view(self, ptr: int, count: int, dtype, device) -> torch.Tensor:
+        return torch.as_tensor(_DevicePointer(ptr, count, self._TYPESTR[dtype]), device=device)
+
+
+# counters in a rank's flag block, raised by its neighbours (int32 each)
+_HALO_FROM_UP, _HALO_FROM_DOWN, _FREE_FROM_UP, _FREE_FROM_DOWN, _TIMED_OUT, _NFLAGS = 0, 1, 2, 3, 4, 8
+
+
+class _PeerExchange:
+    """One rank's side of the fused halo exchange: its two padded texture buffers and its flag
+    block in memory the neighbours can map, and the neighbours' mapped into this process."""
+
+    def __init__(self, plan: SlabPlan, group, peers, dtype, device):
+        self.plan, self.peers = plan, peers
+        itemsize = torch.empty((), dtype=dtype).element_size()
+        self._own = []                                   # (ptr, handle) of this rank's allocations
+        for nbytes in (plan.cells * itemsize, plan.cells * itemsize, 4 * _NFLAGS):
+            self._own.append(peers.alloc(nbytes))
+        self.bufs = [peers.view(self._own[i][0], plan.cells, dtype, device) for i in (0, 1)]
+        self.flags = peers.view(self._own[2][0], _NFLAGS, torch.int32, device)
+        handles = [None] * plan.world
+        dist.all_gather_object(handles, [h for _, h in self._own], group=group)
+        self._opened = {}                                # rank -> [ptr, ptr, ptr]
+        self.remote = {}                                 # rank -> (bufs, flags, that rank's plan)
+        for rank in {plan.up, plan.down} - {None}:
+            ptrs = [peers.open(h) for h in handles[rank]]
+            self._opened[rank] = ptrs
+            theirs = SlabPlan(ny=plan.ny, nx=plan.nx, world=plan.world, rank=rank, reach=plan.reach,
+                              periodic_y=plan.periodic_y)
+            self.remote[rank] = ([peers.view(ptrs[i], theirs.cells, dtype, device) for i in (0, 1)],
+                                 peers.view(ptrs[2], _NFLAGS, torch.int32, device), theirs)
+        # where my edge strips land: my top rows in the upper neighbour's high halo, my
+        # bottom rows in the lower neighbour's low halo (buffer rows, theirs minus mine)
+        self.delta_up = self.delta_down = 0
+        if plan.up is not None:
+            theirs = self.remote[plan.up][2]
+            self.delta_up = theirs.halo_lo + theirs.nrows - plan.halo_lo
+        if plan.down is not None:
+            self.delta_down = -(plan.halo_lo + plan.nrows - plan.reach)
+        self.tick = 0                                    # passes announced so far (all ranks alike)
+        dist.barrier(group=group)                        # every flag block exists and is zero
+
+    def close(self, group) -> None:
+        dist.barrier(group=group)                        # nobody still writes into a neighbour
+        self.remote = {}
+        for ptrs in self._opened.values():
+            for ptr in ptrs:
+                self.peers.close(ptr)
+        self._opened = {}
+        dist.barrier(group=group)                        # every mapping is gone before memory is freed
+        self.bufs, self.flags = [], None
+        for ptr, _ in self._own:
+            self.peers.free(ptr)
+        self._own = []
+
+
 class ShardedConvolver:
     """Holds one rank's slab of a sharded image and runs ``convolve`` on it.
 
@@ -174,8 +309,10 @@ class ShardedConvolver:
     no halos), tensors on the rank's device.
     """
 
+    PEER_TIMEOUT_MS = 20_000      # a wait for a neighbour gives up after this long (and says so)
+
     def __init__(self, ny: int, nx: int, *, kernel, uv_mode: str = "velocity",
-                 boundaries="closed", group=None, ops=None):
+                 boundaries="closed", group=None, ops=None, exchange: str = "nccl", peers=None):
         from rlic_b200 import _core   # enum tables only; no computation
 
         self.group = group
@@ -196,6 +333,17 @@ class ShardedConvolver:
         self.ops = ops or CudaSlabOps()
         self.field = None
         self.comm_stream = None
+        if exchange not in ("nccl", "peer"):
+            raise ValueError(f"unknown exchange {exchange!r}: expected 'nccl' or 'peer'")
+        if exchange == "peer" and self.world > 1:
+            smallest = min(ny * (r + 1) // self.world - ny * r // self.world for r in range(self.world))
+            if smallest < 4 * max(self.plan.reach, 1):
+                raise ValueError(
+                    f"exchange='peer' needs slabs of at least four kernel half-widths "
+                    f"({4 * max(self.plan.reach, 1)} rows); the smallest here has {smallest}")
+        self.exchange = exchange if self.world > 1 else "nccl"
+        self._peer_memory = peers
+        self._peer = None            # _PeerExchange, built on the first convolve (needs dtype and device)
 
     # -- halo plumbing ------------------------------------------------------
     @staticmethod
@@ -265,6 +413,8 @@ class ShardedConvolver:
             raise ValueError(f"expected this rank's slab of shape {(p.nrows, p.nx)}")
         if iterations <= 0:
             return texture.clone()
+        if self.exchange == "peer":
+            return self._convolve_peer(texture, iterations)
         src = self._alloc(texture)
         dst = self._alloc(texture)
         self.ops.pad_texture(texture.contiguous(), src, p, self.walls)
@@ -306,3 +456,78 @@ class ShardedConvolver:
         out = torch.empty_like(texture)
         self.ops.unpad_texture(src, out, p, self.walls)
         return out
+
+    # -- fused halo exchange --------------------------------------------------
+    def _convolve_peer(self, texture: torch.Tensor, iterations: int) -> torch.Tensor:
+        """``convolve`` with ``exchange="peer"``: see the module docstring.  Per pass n (tick t):
+
+            wait   free >= t - 1 from both neighbours      (their pass n - 1 is over: the buffer
+                                                             my strips are about to land in is idle)
+            strips pass over the two edge strips, stored here AND in the neighbours' halos
+            signal halo = t to both neighbours
+            pass   over the interior
+            signal free = t to both neighbours              (my pass n is over)
+            wait   halo >= t from both neighbours           (their strips are in my halos)
+
+        all on the current stream, none of it involving the host.  The first input's halos
+        travel by the ordinary exchange, which also tells each rank that its neighbours have
+        finished the previous call."""
+        p, h = self.plan, self.plan.reach
+        if self._peer is None:
+            self._peer = _PeerExchange(p, self.group, self._peer_memory or CudaPeerMemory(),
+                                       texture.dtype, texture.device)
+        px = self._peer
+        if px.bufs[0].dtype != texture.dtype:
+            raise TypeError("the peer buffers of this convolver hold another dtype")
+        bufs, flags = px.bufs, px.flags
+        up = px.remote.get(p.up) if p.up is not None else None
+        down = px.remote.get(p.down) if p.down is not None else None
+        self.ops.pad_texture(texture.contiguous(), bufs[0], p, self.walls)
+        self._exchange(bufs[0])
+        base, limit = px.tick, self.PEER_TIMEOUT_MS
+        for it in range(iterations):
+            t = base + it + 1
+            src, dst = bufs[it % 2], bufs[(it + 1) % 2]
+            if it == iterations - 1:
+                self._pass_rows(src, dst, 0, p.nrows)
+                break
+            if it > 0:
+                if up is not None:
+                    self.ops.wait(flags, _FREE_FROM_UP, t - 1, limit, _TIMED_OUT)
+                if down is not None:
+                    self.ops.wait(flags, _FREE_FROM_DOWN, t - 1, limit, _TIMED_OUT)
+            if up is not None:
+                self.ops.pass_rows_peer(src, self.field, dst, p, 0, h, self.taps, self.mode, self.walls,
+                                        up[0][(it + 1) % 2], px.delta_up)
+            else:
+                self._pass_rows(src, dst, 0, h)
+            if down is not None:
+                self.ops.pass_rows_peer(src, self.field, dst, p, p.nrows - h, p.nrows, self.taps, self.mode,
+                                        self.walls, down[0][(it + 1) % 2], px.delta_down)
+            else:
+                self._pass_rows(src, dst, p.nrows - h, p.nrows)
+            if up is not None:
+                self.ops.signal(up[1], _HALO_FROM_DOWN, t)
+            if down is not None:
+                self.ops.signal(down[1], _HALO_FROM_UP, t)
+            self._pass_rows(src, dst, h, p.nrows - h)
+            if up is not None:
+                self.ops.signal(up[1], _FREE_FROM_DOWN, t)
+                self.ops.wait(flags, _HALO_FROM_UP, t, limit, _TIMED_OUT)
+            if down is not None:
+                self.ops.signal(down[1], _FREE_FROM_UP, t)
+                self.ops.wait(flags, _HALO_FROM_DOWN, t, limit, _TIMED_OUT)
+        px.tick = base + iterations
+        out = torch.empty_like(texture)
+        self.ops.unpad_texture(bufs[iterations % 2], out, p, self.walls)
+        return out
+
+    def peer_timed_out(self) -> bool:
+        """Whether any wait for a neighbour gave up (synchronises with the device)."""
+        return bool(self._peer is not None and int(self._peer.flags[_TIMED_OUT].item()) != 0)
+
+    def close(self) -> None:
+        """Release the peer mappings and buffers (collective; only needed with ``exchange="peer"``)."""
+        if self._peer is not None:
+            self._peer.close(self.group)
+            self._peer = None

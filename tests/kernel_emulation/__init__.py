@@ -53,6 +53,10 @@ def lib() -> ctypes.CDLL:
             getattr(cdll, f"emu_pass_{sfx}").argtypes = [p, p, p, g, _i64, _i64, _i64, _int, p, _i64,
                                                         _int, _int, _int, _int, _int]
             getattr(cdll, f"emu_pass_{sfx}").restype = _int
+        for sfx, real in (("f32", ctypes.c_float), ("f64", ctypes.c_double)):
+            p, g = ctypes.POINTER(real), ctypes.POINTER(_i64)
+            getattr(cdll, f"emu_pass_peer_{sfx}").argtypes = [p, p, p, g, _i64, _i64, _int, p, _i64, _int, p, _i64]
+            getattr(cdll, f"emu_pass_peer_{sfx}").restype = _int
         cdll.emu_step_counts.argtypes = [ctypes.POINTER(ctypes.c_ulonglong), _int]
         cdll.emu_step_counts.restype = None
         _lib = cdll
@@ -124,6 +128,18 @@ class SlabOps:
         rc = getattr(lib(), f"emu_pass_{sfx}")(
             _ptr(self._np(src), real), _ptr(self._np(field), real), _ptr(self._np(dst), real), _ptr(g, _i64), 1,
             plan.halo_lo + a, b - a, mode, _ptr(taps, real), taps.size, 0, -1, -1, 1, 0)
+        assert rc == 0
+
+
+    def pass_rows_peer(self, src, field, dst, plan, a, b, taps, mode, walls, peer, peer_row_delta):
+        """rlic_b200_pass_slab_peer_*: the pass over owned rows [a, b) that also stores its rows
+        into `peer` (the neighbour's padded buffer), `peer_row_delta` buffer rows away."""
+        sfx, real = _kind(self._np(src).dtype)
+        g = self._geom(plan, walls, taps.size)
+        rc = getattr(lib(), f"emu_pass_peer_{sfx}")(
+            _ptr(self._np(src), real), _ptr(self._np(field), real), _ptr(self._np(dst), real), _ptr(g, _i64),
+            plan.halo_lo + a, b - a, mode, _ptr(taps, real), taps.size, int(getattr(self, "walk", 0)),
+            _ptr(self._np(peer), real), peer_row_delta)
         assert rc == 0
 
 

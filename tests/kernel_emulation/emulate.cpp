@@ -202,6 +202,57 @@ int pass(const T *tex, const T *field, T *out, const int64_t *geom, int64_t nfie
                : tuned<T, false, GT>(tex, field, out, g, gt, ntaps, blocks, wide, branchless, walk);
 }
 
+// The fused pass + halo shipment (lic_pass_peer_kernel), dispatched as launch_one() does for
+// the default arithmetic: per-step walk, or the tuned grouped walk.
+template <typename T, bool POL, typename Taps>
+void run_pass_peer(const T *tex, const T *field, T *out, const PassGeom &g, const Taps &taps, int ntaps,
+                   unsigned blocks, int walk, T *peer_out, long long peer_delta)
+{
+    using Tn = rlic::Tune<T, POL>;
+    auto *f = reinterpret_cast<const rlic::PackedField<T> *>(field);
+    if (walk)
+        launch(blocks, rlic::kThreads, [&] {
+            rlic::lic_pass_peer_kernel<T, POL, Taps, int, rlic::kTileW, rlic::kTileH, Tn::unroll, Tn::min_blocks,
+                                       Tn::walk_flavor, Tn::admit, true, Tn::walk>(tex, f, out, g, taps, ntaps,
+                                                                                    peer_out, peer_delta);
+        });
+    else
+        launch(blocks, rlic::kThreads, [&] {
+            rlic::lic_pass_peer_kernel<T, POL, Taps, int>(tex, f, out, g, taps, ntaps, peer_out, peer_delta);
+        });
+}
+
+template <typename T>
+int pass_peer(const T *tex, const T *field, T *out, const int64_t *geom, int64_t first_row, int64_t out_rows,
+              int uv_mode, const T *host_taps, int64_t klen, int walk, T *peer_out, int64_t peer_row_delta)
+{
+    PassGeom g = geometry_from(geom);
+    if (out_rows <= 0 || g.nx <= 0) return 0;
+    g.first_row = (int)first_row;
+    g.out_rows = (int)out_rows;
+    g.tiles_x = (g.nx + rlic::kTileW - 1) / rlic::kTileW;
+    g.tiles_per_field = (int)(((out_rows + rlic::kTileH - 1) / rlic::kTileH) * g.tiles_x);
+    const unsigned blocks = (unsigned)g.tiles_per_field;
+    const long long delta = (long long)peer_row_delta * g.pitch;      // as pass_slab() in lic_api.cu
+    constexpr int kMaxParam = rlic::kParamTapBytes / (int)sizeof(T);
+    using PT = rlic::ParamTaps<T, kMaxParam>;
+    using GT = rlic::GlobalTaps<T>;
+    const int ntaps = (int)klen;
+    const bool pol = uv_mode == 1;
+    if (klen <= kMaxParam) {
+        PT pt;
+        std::memset(pt.w, 0, sizeof pt.w);
+        std::memcpy(pt.w, host_taps, sizeof(T) * (size_t)klen);
+        if (pol) run_pass_peer<T, true, PT>(tex, field, out, g, pt, ntaps, blocks, walk, peer_out, delta);
+        else run_pass_peer<T, false, PT>(tex, field, out, g, pt, ntaps, blocks, walk, peer_out, delta);
+    } else {
+        const GT gt{host_taps};
+        if (pol) run_pass_peer<T, true, GT>(tex, field, out, g, gt, ntaps, blocks, walk, peer_out, delta);
+        else run_pass_peer<T, false, GT>(tex, field, out, g, gt, ntaps, blocks, walk, peer_out, delta);
+    }
+    return 0;
+}
+
 }  // namespace
 
 // Step counters accumulated over every pass since the last reset.
@@ -232,3 +283,12 @@ extern "C" void emu_step_counts(unsigned long long *out, int reset)
 
 EMU_DEFINE(f32, float)
 EMU_DEFINE(f64, double)
+
+#define EMU_DEFINE_PEER(SFX, T)                                                                              \
+    extern "C" int emu_pass_peer_##SFX(const T *tex, const T *field, T *out, const int64_t *geom,            \
+                                       int64_t first_row, int64_t out_rows, int uv_mode, const T *taps,      \
+                                       int64_t klen, int walk, T *peer_out, int64_t peer_row_delta)          \
+    { return pass_peer<T>(tex, field, out, geom, first_row, out_rows, uv_mode, taps, klen, walk, peer_out,   \
+                          peer_row_delta); }
+EMU_DEFINE_PEER(f32, float)
+EMU_DEFINE_PEER(f64, double)

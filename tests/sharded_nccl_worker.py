@@ -1,4 +1,6 @@
-"""Worker for tests/test_slab.py::test_two_gpu_sharded_run (launched by torchrun)."""
+"""Worker for tests/test_slab.py::test_two_gpu_sharded_run and ::test_two_gpu_fused_peer_exchange
+(launched by torchrun).  `--exchange peer` runs the sharded passes with the halo exchange fused
+into the edge-strip kernels (peer stores through CUDA IPC mappings) instead of NCCL messages."""
 
 import os
 import sys
@@ -12,6 +14,7 @@ sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 
 
 def main() -> None:
+    exchange = sys.argv[sys.argv.index("--exchange") + 1] if "--exchange" in sys.argv else "nccl"
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -31,7 +34,8 @@ def main() -> None:
         u = rng.random((ny, nx), dtype=np.float32) - 0.5
         v = rng.random((ny, nx), dtype=np.float32) - 0.5
         kernel = np.linspace(0.1, 1, 65, dtype=np.float32)
-        sc = ShardedConvolver(ny, nx, kernel=kernel, uv_mode=mode, boundaries=bnd)
+        sc = ShardedConvolver(ny, nx, kernel=kernel, uv_mode=mode, boundaries=bnd, exchange=exchange)
+        sc.PEER_TIMEOUT_MS = 5_000
         mine = slice(sc.plan.row0, sc.plan.row1)
         sc.set_field(torch.from_numpy(u[mine].copy()).to(dev), torch.from_numpy(v[mine].copy()).to(dev))
         for overlap in (True, False):
@@ -39,6 +43,9 @@ def main() -> None:
             want = convolve_device(*(torch.from_numpy(a).to(dev) for a in (tex, u, v)), kernel=kernel,
                                    uv_mode=mode, boundaries=bnd, iterations=4)
             ok &= bool(torch.equal(got, want[mine]))
+        if exchange == "peer":
+            ok &= not sc.peer_timed_out()
+            sc.close()
     flags = [None] * world
     dist.all_gather_object(flags, ok)
     if rank == 0:

@@ -141,18 +141,87 @@ class OracleSlabOps:
                          {plan.halo_lo + a + k: band[k] for k in range(b - a)})
 
 
+class SharedMemoryPeers:
+    """CPU stand-in for rlic_b200.sharded.CudaPeerMemory (the CUDA IPC entry points of the C
+    ABI): named shared-memory segments play the device allocations other ranks can map."""
+
+    def __init__(self):
+        self._segments = {}
+
+    def alloc(self, nbytes):
+        from multiprocessing import shared_memory
+
+        seg = shared_memory.SharedMemory(create=True, size=nbytes)
+        seg.buf[:nbytes] = bytes(nbytes)
+        self._segments[id(seg)] = seg
+        return id(seg), seg.name.encode()
+
+    def open(self, handle):
+        from multiprocessing import shared_memory
+
+        seg = shared_memory.SharedMemory(name=handle.decode())
+        self._segments[id(seg)] = seg
+        return id(seg)
+
+    def view(self, ptr, count, dtype, device):
+        return torch.frombuffer(self._segments[ptr].buf, dtype=dtype, count=count)
+
+    def close(self, ptr):
+        self._segments.pop(ptr).close()
+
+    def free(self, ptr):
+        seg = self._segments.pop(ptr)
+        seg.close()
+        seg.unlink()
+
+
+class HostFlags:
+    """signal / wait of the peer exchange on shared memory: program order is stream order."""
+
+    def signal(self, flags, index, value):
+        flags[index] = value
+
+    def wait(self, flags, index, value, timeout_ms, timed_out_index):
+        import time
+
+        deadline = time.monotonic() + min(timeout_ms, 30_000) / 1e3
+        while int(flags[index]) - value < 0:
+            if time.monotonic() > deadline:
+                flags[timed_out_index] = 1
+                return
+            time.sleep(0.0005)
+
+
+def _peer_methods(cls):
+    """Adds the peer-exchange half of the ops interface to a CPU ops class."""
+
+    class WithPeers(cls, HostFlags):
+        def pass_rows_peer(self, src, field, dst, plan, a, b, taps, mode, walls, peer, peer_row_delta):
+            if hasattr(super(), "pass_rows_peer"):      # the emulated kernels have the real thing
+                return super().pass_rows_peer(src, field, dst, plan, a, b, taps, mode, walls, peer,
+                                              peer_row_delta)
+            self.pass_rows(src, field, dst, plan, a, b, taps, mode, walls)
+            cells = plan.row_cells(plan.halo_lo + a, plan.halo_lo + b)
+            shift = peer_row_delta * plan.pitch
+            peer[cells.start + shift:cells.stop + shift] = dst[cells]
+
+    return WithPeers()
+
+
 def _make_ops(kind):
     if kind == "oracle stand-in":
-        return OracleSlabOps()
+        return _peer_methods(OracleSlabOps)
     # the library's own kernels, compiled for the CPU (tests/kernel_emulation): real packed
     # records, sentinels and wall cells travel through the exchange
     sys.path.insert(0, str(ROOT / "tests"))
     import kernel_emulation
 
-    return kernel_emulation.SlabOps()
+    ops = _peer_methods(kernel_emulation.SlabOps)
+    ops.walk = 1 if kind.endswith("grouped walk") else 0
+    return ops
 
 
-def _worker(rank, world, port, case, queue, ops_kind="oracle stand-in"):
+def _worker(rank, world, port, case, queue, ops_kind="oracle stand-in", exchange="nccl", calls=1):
     try:
         os.environ["MASTER_ADDR"] = "127.0.0.1"
         os.environ["MASTER_PORT"] = str(port)
@@ -170,12 +239,17 @@ def _worker(rank, world, port, case, queue, ops_kind="oracle stand-in"):
         kernel = (rng.random(klen) + 0.1).astype(dtype)
 
         sc = ShardedConvolver(ny, nx, kernel=kernel, uv_mode=mode, boundaries=boundaries,
-                              ops=_make_ops(ops_kind))
+                              ops=_make_ops(ops_kind), exchange=exchange,
+                              peers=SharedMemoryPeers() if exchange == "peer" else None)
         p = sc.plan
         assert (p.row0, p.row1) == (ny * rank // world, ny * (rank + 1) // world)
         mine = slice(p.row0, p.row1)
         sc.set_field(torch.from_numpy(u[mine].copy()), torch.from_numpy(v[mine].copy()))
-        got = sc.convolve(torch.from_numpy(tex[mine].copy()), iterations=iterations).numpy()
+        for _ in range(calls):     # a convolver is reused: the counters of the peer exchange carry on
+            got = sc.convolve(torch.from_numpy(tex[mine].copy()), iterations=iterations).numpy()
+        if exchange == "peer":
+            assert not sc.peer_timed_out(), "a wait for a neighbour gave up"
+            sc.close()
 
         bs_y = boundaries["y"] if isinstance(boundaries, dict) else boundaries
         bs_x = boundaries["x"] if isinstance(boundaries, dict) else boundaries
@@ -226,6 +300,62 @@ def test_sharded_equals_unsharded(name, ops_kind):
                 pr.terminate()
     assert status == "ok", payload
     assert all(payload), f"ranks with mismatching slabs: {payload}"
+
+
+PEER_CASES = {
+    # slabs of at least four kernel half-widths, as exchange="peer" demands
+    "closed-2": (2, (40, 23, 9, "closed", "velocity", 4, np.float64)),
+    "periodic-ring-2": (2, (48, 17, 11, "periodic", "velocity", 3, np.float32)),
+    "y-periodic-pol-3": (3, (45, 20, 7, {"x": "closed", "y": "periodic"}, "polarization", 5, np.float64)),
+    "x-periodic-3-uneven": (3, (77, 19, 13, {"x": "periodic", "y": "closed"}, "velocity", 4, np.float32)),
+    "single-iteration-3": (3, (45, 20, 7, "periodic", "velocity", 1, np.float32)),
+}
+
+
+PEER_RUNS = ([(name, "oracle stand-in") for name in PEER_CASES]
+             + [(name, "emulated kernels") for name in ("closed-2", "y-periodic-pol-3", "x-periodic-3-uneven")]
+             + [(name, "emulated kernels, grouped walk") for name in ("periodic-ring-2", "y-periodic-pol-3")])
+
+
+@pytest.mark.parametrize("name,ops_kind", PEER_RUNS)
+def test_fused_peer_exchange_equals_unsharded(name, ops_kind):
+    """exchange="peer": the strips land in the neighbours' halos through mapped memory (here:
+    named shared memory) and the halo / free counters order the passes; two calls in a row,
+    so that the counters and the start-of-call handshake are exercised too."""
+    world, case = PEER_CASES[name]
+    ctx = mp.get_context("spawn")
+    queue = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, case, queue, ops_kind, "peer", 2))
+             for r in range(world)]
+    for pr in procs:
+        pr.start()
+    try:
+        status, payload = queue.get(timeout=180)
+    finally:
+        for pr in procs:
+            pr.join(timeout=60)
+            if pr.is_alive():
+                pr.terminate()
+    assert status == "ok", payload
+    assert all(payload), f"ranks with mismatching slabs: {payload}"
+
+
+def test_peer_exchange_rejects_unknown_modes_and_needs_neighbours():
+    import torch.distributed as dist
+
+    from rlic_b200.sharded import ShardedConvolver
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(_free_port())
+    dist.init_process_group("gloo", rank=0, world_size=1)
+    try:
+        with pytest.raises(ValueError, match="unknown exchange"):
+            ShardedConvolver(64, 8, kernel=np.ones(5), exchange="carrier pigeon")
+        sc = ShardedConvolver(64, 8, kernel=np.ones(5), exchange="peer")
+        assert sc.exchange == "nccl"        # nobody to exchange with
+    finally:
+        dist.destroy_process_group()
 
 
 def test_plan_geometry():

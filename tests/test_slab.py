@@ -16,6 +16,7 @@ from pathlib import Path
 
 import numpy as np
 import pytest
+from _status import first_gpu_run
 
 import oracle
 from rlic_b200 import _core
@@ -197,5 +198,21 @@ def test_two_gpu_sharded_run():
         [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
          "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), str(script)],
         capture_output=True, text=True, env=env, timeout=600)
+    assert proc.returncode == 0, proc.stdout[-3000:] + proc.stderr[-3000:]
+    assert "SHARDED_OK" in proc.stdout
+
+
+@first_gpu_run
+@pytest.mark.skipif(_core.device_count() < 2, reason="needs two GPUs")
+def test_two_gpu_fused_peer_exchange():
+    """exchange="peer": the edge-strip passes store into the neighbour's halo through CUDA IPC
+    mappings, counters order the iterations; the result equals the single-GPU one."""
+    script = ROOT / "tests" / "sharded_nccl_worker.py"
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    proc = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+         "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), str(script),
+         "--exchange", "peer"],
+        capture_output=True, text=True, env=env, timeout=300)
     assert proc.returncode == 0, proc.stdout[-3000:] + proc.stderr[-3000:]
     assert "SHARDED_OK" in proc.stdout
