@@ -1131,6 +1131,7 @@ int rlic_b200_peer_alloc(int64_t bytes, void **ptr, unsigned char *handle)
     if (bytes <= 0 || !ptr || !handle)
         return fail(RLIC_B200_EINVAL, "bad argument to peer_alloc");
     static_assert(sizeof(cudaIpcMemHandle_t) == RLIC_B200_PEER_HANDLE_BYTES, "handle size");
+    CUDA_TRY(use_current_device());                   // the caller's device, as for every device entry point
     void *p = nullptr;
     CUDA_TRY(cudaMalloc(&p, (size_t)bytes));          // not the stream-ordered pool: IPC needs a plain allocation
     cudaError_t e = cudaMemset(p, 0, (size_t)bytes);
@@ -1153,6 +1154,7 @@ int rlic_b200_peer_open(const unsigned char *handle, void **ptr)
         return fail(RLIC_B200_EINVAL, "bad argument to peer_open");
     cudaIpcMemHandle_t h;
     std::memcpy(&h, handle, sizeof h);
+    CUDA_TRY(use_current_device());
     CUDA_TRY(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
     return RLIC_B200_OK;
 }

@@ -54,7 +54,8 @@ def main() -> None:
 
     n = args.n
     kernel = workloads.triangle_kernel(args.taps, np.float32)
-    sc = ShardedConvolver(n, n, kernel=kernel, boundaries="closed")
+    sc = ShardedConvolver(n, n, kernel=kernel, boundaries="closed",
+                          exchange=os.environ.get("RLIC_B200_EXCHANGE", "nccl"))
     r0, r1 = sc.plan.row0, sc.plan.row1
     # the same global image whatever the rank count: per-row seeds
     rng = np.random.default_rng(1234)
@@ -93,7 +94,9 @@ def main() -> None:
         "G_pixel_steps_s": pix * args.iterations * (args.taps - 1) / ms / 1e6,
         "checksum": [float(sums[0]), float(sums[1])],
         "halo_bytes_per_side_per_iteration": (args.taps // 2) * (n + 2) * 4,
+        "exchange": sc.exchange,
     }
+    sc.close()
     dist.barrier()
     dist.destroy_process_group()
     os.dup2(real_stdout, 1)
