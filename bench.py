@@ -486,6 +486,7 @@ def run_ours(args) -> dict:
     elif rank == 0:
         line["cpu_baseline"] = None
     if dist is not None:
+        sc.close()           # peer mappings of the fused exchange, if any (collective)
         dist.barrier()
         dist.destroy_process_group()
     return line if rank == 0 else {}
