@@ -33,7 +33,20 @@ _lib = None
 def build(force: bool = False) -> Path:
     deps = [HERE / "emulate.cpp", HERE / "cuda_on_cpu.h", KERNEL_SOURCE]
     if force or not LIB.exists() or any(d.stat().st_mtime > LIB.stat().st_mtime for d in deps):
-        subprocess.run(["g++", *FLAGS, f"-I{HERE}", str(HERE / "emulate.cpp"), "-o", str(LIB)],
+        # one translation unit per scalar type, compiled side by side (the template
+        # instantiations are what takes the time), then linked
+        compile_flags = [f for f in FLAGS if f != "-shared"]
+        units = []
+        for unit in ("F32", "F64"):
+            obj = HERE / f"emulate_{unit.lower()}.o"
+            units.append((obj, subprocess.Popen(
+                ["g++", *compile_flags, f"-DEMU_UNIT_{unit}", f"-I{HERE}", "-c", str(HERE / "emulate.cpp"),
+                 "-o", str(obj)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        for obj, proc in units:
+            out, _ = proc.communicate()
+            if proc.returncode:
+                raise RuntimeError(f"g++ failed on {obj.name}:\n{out}")
+        subprocess.run(["g++", "-shared", "-pthread", *(str(obj) for obj, _ in units), "-o", str(LIB)],
                        check=True, capture_output=True, text=True)
     return LIB
 

@@ -14,8 +14,16 @@
 #include <thread>
 #include <vector>
 
+// Built as two translation units (-DEMU_UNIT_F32 / -DEMU_UNIT_F64, compiled in parallel: the
+// template instantiations dominate the build); the shared state lives in the f32 unit.
+#if !defined(EMU_UNIT_F32) && !defined(EMU_UNIT_F64)
+#define EMU_UNIT_F32 1
+#define EMU_UNIT_F64 1
+#endif
+#ifdef EMU_UNIT_F32
 thread_local Dim3 threadIdx, blockIdx, blockDim, gridDim;
 thread_local emulated::StepCounts emulated::step_counts;
+#endif
 
 namespace {
 
@@ -46,7 +54,14 @@ unsigned stream_blocks(long long items)
 // Runs `body()` once per (block, thread) of a 1-D launch, blocks spread over host threads.
 // The kernels involved never synchronise within a block, so threads run to completion
 // one after another.
-std::atomic<unsigned long long> g_counts[4];
+}  // namespace
+#ifdef EMU_UNIT_F32
+std::atomic<unsigned long long> emu_counts[4];
+#else
+extern std::atomic<unsigned long long> emu_counts[4];
+#endif
+namespace {
+std::atomic<unsigned long long> (&g_counts)[4] = emu_counts;
 
 template <typename Body> void launch(unsigned blocks, unsigned threads, Body body)
 {
@@ -256,6 +271,7 @@ int pass_peer(const T *tex, const T *field, T *out, const int64_t *geom, int64_t
 }  // namespace
 
 // Step counters accumulated over every pass since the last reset.
+#ifdef EMU_UNIT_F32
 extern "C" void emu_step_counts(unsigned long long *out, int reset)
 {
     for (int i = 0; i < 4; ++i) {
@@ -263,6 +279,7 @@ extern "C" void emu_step_counts(unsigned long long *out, int reset)
         if (reset) g_counts[i].store(0);
     }
 }
+#endif
 
 #define EMU_DEFINE(SFX, T)                                                                                  \
     extern "C" void emu_pack_field_##SFX(const T *u, const T *v, T *field, const int64_t *geom, int64_t rb,  \
@@ -281,8 +298,12 @@ extern "C" void emu_step_counts(unsigned long long *out, int reset)
     { return pass<T>(tex, field, out, geom, nfields, first_row, out_rows, uv_mode, taps, klen, wide, flavor, admit, \
                      branchless, walk); }
 
+#ifdef EMU_UNIT_F32
 EMU_DEFINE(f32, float)
+#endif
+#ifdef EMU_UNIT_F64
 EMU_DEFINE(f64, double)
+#endif
 
 #define EMU_DEFINE_PEER(SFX, T)                                                                              \
     extern "C" int emu_pass_peer_##SFX(const T *tex, const T *field, T *out, const int64_t *geom,            \
@@ -290,5 +311,9 @@ EMU_DEFINE(f64, double)
                                        int64_t klen, int walk, T *peer_out, int64_t peer_row_delta)          \
     { return pass_peer<T>(tex, field, out, geom, first_row, out_rows, uv_mode, taps, klen, walk, peer_out,   \
                           peer_row_delta); }
+#ifdef EMU_UNIT_F32
 EMU_DEFINE_PEER(f32, float)
+#endif
+#ifdef EMU_UNIT_F64
 EMU_DEFINE_PEER(f64, double)
+#endif
