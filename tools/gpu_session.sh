@@ -3,6 +3,7 @@
 # available gets run once, with its own time limit per step, and leaves its output under
 # gpurun_out/ (merged back by gpurun).  Nothing here changes clocks or kills by pattern.
 #
+#   python __graft_entry__.py && sh tools/build_lab.sh      # here, without a GPU: the built files travel
 #   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/gpu_session.sh'
 #
 # Steps (each independent; a failure is logged and the script goes on):
@@ -34,6 +35,7 @@ step 900 pytest_gpu python -m pytest tests -q -m gpu -rxX
 step 120 smoke python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')"
 step 240 bench_default python bench.py --steps 10 --warmup 3
 step 240 bench_grouped env RLIC_B200_WALK=grouped python bench.py --steps 10 --warmup 3 --no-cpu-baseline
+[ -x tools/kernel_lab ] || step 200 build_lab sh tools/build_lab.sh     # normally built before the call
 if [ -x tools/kernel_lab ]; then
     step 300 lab_grouped_f32_f64 tools/kernel_lab 4096 65 grouped
     step 120 lab_shipped tools/kernel_lab 4096 65 shipped
