@@ -455,6 +455,22 @@ int convolve_host(const T *tex, const T *u, const T *v, int64_t nfields, int64_t
         return RLIC_B200_OK;
     };
 
+    // One band of the inputs: u, v -> packed field, texture -> padded buffer, all on `io`.
+    auto enqueue_band_upload = [&](int64_t b) -> int {
+        const int64_t rb = band_begin(b), re = band_begin(b + 1);
+        const size_t off = (size_t)rb * (size_t)nx * (size_t)nfields;
+        const size_t n = (size_t)(re - rb) * (size_t)nx * (size_t)nfields;
+        const HostToDevice uv_jobs[2] = {{s_u + off, u + off, n * sizeof(T)},
+                                         {s_v + off, v + off, n * sizeof(T)}};
+        CUDA_TRY(upload(uv_jobs, 2, io.s));
+        CUDA_TRY(launch_pack<T>(s_u + off, s_v + off, t_field, g, rb, re, nfields, io.s));
+        const HostToDevice tex_job{s_t + off, tex + off, n * sizeof(T)};
+        CUDA_TRY(upload(&tex_job, 1, io.s));
+        CUDA_TRY(launch_pad<T>(s_t + off, t_tex, g, rb, re, nfields, flag, io.s));
+        CUDA_TRY(cudaEventRecord(uploaded.ev[(size_t)b], io.s));
+        return RLIC_B200_OK;
+    };
+
     // ---- wavefront schedule (opt-in): every pass trails the uploads, band by band ----
     // Early bands run through all their passes while later bands are still on the bus,
     // and their results go back while later bands still compute.  Needs a top and a
@@ -481,17 +497,8 @@ int convolve_host(const T *tex, const T *u, const T *v, int64_t nfields, int64_t
         };
         size_t next = 0;
         for (int64_t b = 0; b < nbands; ++b) {
-            const int64_t rb = band_begin(b), re = band_begin(b + 1);
-            const size_t off = (size_t)rb * (size_t)nx;
-            const size_t n = (size_t)(re - rb) * (size_t)nx;
-            const HostToDevice uv_jobs[2] = {{s_u + off, u + off, n * sizeof(T)},
-                                             {s_v + off, v + off, n * sizeof(T)}};
-            CUDA_TRY(upload(uv_jobs, 2, io.s));
-            CUDA_TRY(launch_pack<T>(s_u + off, s_v + off, t_field, g, rb, re, 1, io.s));
-            const HostToDevice tex_job{s_t + off, tex + off, n * sizeof(T)};
-            CUDA_TRY(upload(&tex_job, 1, io.s));
-            CUDA_TRY(launch_pad<T>(s_t + off, t_tex, g, rb, re, 1, flag, io.s));
-            CUDA_TRY(cudaEventRecord(uploaded.ev[(size_t)b], io.s));
+            if (int rc = enqueue_band_upload(b))
+                return rc;
             // issue everything that no longer waits for a band still to be enqueued
             for (; next < order.size(); ++next) {
                 if (order[next].pass == 1 && upload_needed(order[next].band) > b)
@@ -530,17 +537,8 @@ int convolve_host(const T *tex, const T *u, const T *v, int64_t nfields, int64_t
     // ---- uploads, with pass 1 trailing behind them ----
     int64_t next_band = 0;   // next band of pass 1 to launch
     for (int64_t b = 0; b < nbands; ++b) {
-        const int64_t rb = band_begin(b), re = band_begin(b + 1);
-        const size_t off = (size_t)rb * (size_t)nx * (size_t)nfields;
-        const size_t n = (size_t)(re - rb) * (size_t)nx * (size_t)nfields;
-        const HostToDevice uv_jobs[2] = {{s_u + off, u + off, n * sizeof(T)},
-                                         {s_v + off, v + off, n * sizeof(T)}};
-        CUDA_TRY(upload(uv_jobs, 2, io.s));
-        CUDA_TRY(launch_pack<T>(s_u + off, s_v + off, t_field, g, rb, re, nfields, io.s));
-        const HostToDevice tex_job{s_t + off, tex + off, n * sizeof(T)};
-        CUDA_TRY(upload(&tex_job, 1, io.s));
-        CUDA_TRY(launch_pad<T>(s_t + off, t_tex, g, rb, re, nfields, flag, io.s));
-        CUDA_TRY(cudaEventRecord(uploaded.ev[(size_t)b], io.s));
+        if (int rc = enqueue_band_upload(b))
+            return rc;
         // launch every band of pass 1 whose reach is now covered
         while (next_band < nbands && !periodic_y) {
             const int64_t last_row = std::min(ny - 1, band_begin(next_band + 1) - 1 + reach);
