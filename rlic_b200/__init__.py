@@ -12,6 +12,7 @@ Anne Archibald) are the behavioural reference only; see NOTICE.
 __all__ = [
     "convolve",
     "convolve_batch",
+    "convolve_sharded",
     "get_arithmetic",
     "get_schedule",
     "get_walk",
@@ -22,4 +23,4 @@ __all__ = [
 
 from rlic_b200._core import (get_arithmetic, get_schedule, get_walk, set_arithmetic, set_schedule,
                              set_walk)
-from rlic_b200._lib import convolve, convolve_batch
+from rlic_b200._lib import convolve, convolve_batch, convolve_sharded

@@ -245,3 +245,39 @@ def convolve_batch(
     return _core.convolve_batch(
         textures, (u, v, uv_mode), kernel, (walls.x, walls.y), iterations, devices
     )
+
+
+def convolve_sharded(
+    texture,
+    /,
+    u,
+    v,
+    *,
+    kernel,
+    uv_mode: UVMode = "velocity",
+    boundaries: BoundarySpec = "closed",
+    iterations: int = 1,
+    devices=None,
+):
+    """``convolve`` with the image split into row slabs over several GPUs of this process
+    (extension; BASELINE config 4 without ``torchrun``).
+
+    Same arguments, validation, messages and result as :func:`convolve` -- bit for bit: the
+    walkers run in global row numbers -- plus ``devices`` (default: all visible GPUs, fewer
+    when the image is too short for that many slabs).  Each pass computes the edge strips of
+    every slab first, copies them into the neighbours' halos device to device and computes
+    the interiors meanwhile (``rlic_b200/multi.py``).  Not yet run on GPUs.
+    """
+    problems, walls, _ = _check_inputs(texture, u, v, kernel, uv_mode, boundaries, iterations)
+    if len(problems) == 1:
+        raise problems[0]
+    if problems:
+        raise ExceptionGroup("Invalid inputs were received.", problems)
+    if iterations == 0:
+        return texture.copy()
+    from rlic_b200.multi import MultiDeviceConvolver   # torch is needed only here
+
+    mc = MultiDeviceConvolver(*texture.shape, kernel=kernel, uv_mode=uv_mode, boundaries=boundaries,
+                              devices=devices)
+    mc.set_field(u, v)
+    return mc.convolve(texture, iterations)
