@@ -72,6 +72,18 @@ def describe(label: str) -> str:
             f"flavor {flavor} admit {admit} walk {walk:>2}")
 
 
+def pipe_of(op: str) -> str:
+    if op in ("FFMA", "FADD", "FMUL", "IMAD", "HFMA2", "HADD2", "HMUL2"):
+        return "fma"
+    if op[0] == "D":
+        return "fp64"
+    if op in ("LDG", "STG", "LDC", "LDCU", "LDL", "STL", "LDS", "STS"):
+        return "mem"
+    if op in ("BRA", "BSSY", "BSYNC", "BREAK", "CALL", "RET", "EXIT", "WARPSYNC"):
+        return "ctl"
+    return "alu"
+
+
 def loops_of(body):
     found = []
     for addr, ins in body:
@@ -101,21 +113,26 @@ def main() -> None:
         steps_per_group = int([a.strip() for a in label.split(",")][-6])   # UNROLL
         loops = sorted(loops_of(body), key=lambda lh: lh[0] - lh[1])[:2]    # the two main loops
         per_step, fp64, local = [], [], 0
+        mix = collections.Counter()
         for lo, hi in loops:
             fast = fast_path(body, lo, hi)
             ops = collections.Counter(re.sub(r"^@!?U?P\d\s+", "", i).split()[0].split(".")[0] for _, i in fast)
             per_step.append(len(fast) / steps_per_group)
             fp64.append(sum(n for op, n in ops.items() if op[0] == "D") / steps_per_group)
             local += ops.get("LDL", 0) + ops.get("STL", 0)
+            for op, n in ops.items():
+                mix[pipe_of(op)] += n / steps_per_group / len(loops)
         u = usage.get(name, {})
         rows.append((describe(label), sum(per_step) / len(per_step), per_step, sum(fp64) / len(fp64),
-                     u.get("regs"), u.get("spill", 0), local, len(body)))
+                     u.get("regs"), u.get("spill", 0), local, len(body), mix))
     print("fast-path instructions per step in the walk's two main loops (forward, backward), sm_100a SASS")
-    print(f"{'kernel':62s} {'instr/step':>10s} {'fwd':>6s} {'bwd':>6s} {'FP64/step':>9s} {'regs':>4s} "
-          f"{'spill B':>7s} {'LDL+STL in loops':>16s} {'SASS total':>10s}")
-    for d, mean, per, f64, regs, spill, local, total in sorted(rows):
-        print(f"{d:62s} {mean:10.2f} {per[0]:6.2f} {per[-1]:6.2f} {f64:9.2f} {regs!s:>4s} {spill:7d} "
-              f"{local:16d} {total:10d}")
+    print("pipes: fma = FFMA/FADD/FMUL/IMAD/HFMA2, alu = integer, logic, compare, select, min/max, move, "
+          "fp64 = D*, mem = loads/stores, ctl = branches and reconvergence")
+    print(f"{'kernel':62s} {'instr/step':>10s} {'fwd':>6s} {'bwd':>6s} {'fma':>6s} {'alu':>6s} {'fp64':>6s} "
+          f"{'mem':>5s} {'ctl':>5s} {'regs':>4s} {'spill B':>7s} {'LDL+STL in loops':>16s} {'SASS total':>10s}")
+    for d, mean, per, f64, regs, spill, local, total, mix in sorted(rows, key=lambda r: r[:2]):
+        print(f"{d:62s} {mean:10.2f} {per[0]:6.2f} {per[-1]:6.2f} {mix['fma']:6.2f} {mix['alu']:6.2f} "
+              f"{mix['fp64']:6.2f} {mix['mem']:5.2f} {mix['ctl']:5.2f} {regs!s:>4s} {spill:7d} {local:16d} {total:10d}")
 
 
 if __name__ == "__main__":
