@@ -402,6 +402,12 @@ void run_type(const char *tname, int n, int L, const char *only)
             CANDW("grouped pol w11 f0", true, 2, 5, 0, 2, 11);
             CANDW("grouped pol w1 f2", true, 2, 5, 2, 2, 1);
             CANDW("grouped pol w9 f0 b4", true, 2, 4, 0, 2, 9);
+            // 48 registers (5 CTAs): the lowest static counts of the f64 sweeps
+            CANDW("grouped vel w5 f2 b5", false, 2, 5, 2, 2, 5);
+            CANDW("grouped vel w1 f0 b5", false, 2, 5, 0, 2, 1);
+            CANDW("grouped vel w9 f0 u4 b5", false, 4, 5, 0, 2, 9);
+            CANDW("grouped pol w1 f0 b4", true, 2, 4, 0, 2, 1);
+            CANDW("grouped pol w9 f0 u4 b4", true, 4, 4, 0, 2, 9);
         }
         // the later CAND()s compare with the velocity result of the shipped kernel
         auto kref = rlic::lic_pass_kernel<T, false, PT, int>;
