@@ -54,7 +54,7 @@ extern "C" {
 #define RLIC_B200_PERIODIC 1
 
 /* ABI version of this header; bumped on any signature change. */
-#define RLIC_B200_ABI_VERSION 2
+#define RLIC_B200_ABI_VERSION 3
 int rlic_b200_abi_version(void);
 
 /* Message of the last failure on the calling thread ("" if none). */
@@ -71,8 +71,9 @@ int rlic_b200_device_count(void);
  *                                   (.github/workflows/cd.yml:93,143,210).  Default here.
  *   RLIC_B200_ARITH_FMA             `fma` alone: the x86-64 wheels (cd.yml:89,139,210).
  * The two agree on almost every pixel (a last-bit difference in an edge time matters only
- * where it flips a `tx < ty` decision).  Process-wide; takes effect for calls that start
- * after it returns, so set it before computing rather than concurrently with calls. */
+ * where it flips a `tx < ty` decision).  This sets the PROCESS-WIDE DEFAULT (set it once, at
+ * start-up); a thread that wants something else for its own calls uses
+ * rlic_b200_set_thread_options below, which never touches shared state. */
 #define RLIC_B200_ARITH_FMA_BRANCHLESS 0
 #define RLIC_B200_ARITH_FMA 1
 int rlic_b200_set_arithmetic(int which);
@@ -83,30 +84,45 @@ int rlic_b200_get_arithmetic(void);
  * same bits; they differ in how much of the transfers hides behind the passes.
  *   RLIC_B200_SCHEDULE_TRAILING   pass 1 follows the uploads band by band, the middle
  *                                 passes run over the whole image, the last pass releases
- *                                 bands to the download.  Default.
+ *                                 bands to the download.
  *   RLIC_B200_SCHEDULE_WAVEFRONT  every pass follows the uploads band by band (pass p of
  *                                 band b runs once pass p-1 of bands b-1..b+1 is done), so
  *                                 early bands finish, and leave, while late bands are still
  *                                 arriving.  Used when y is not periodic and iterations >= 2;
  *                                 otherwise the call falls back to the trailing order.
- * Process-wide, like rlic_b200_set_arithmetic. */
+ *                                 Default since round 2 (measured on a B200: 4096^2 x 5 passes
+ *                                 end to end 11.7 -> 11.1 ms, 16384^2 x 20 599 -> 559 ms).
+ * A process-wide default, like rlic_b200_set_arithmetic. */
 #define RLIC_B200_SCHEDULE_TRAILING 0
 #define RLIC_B200_SCHEDULE_WAVEFRONT 1
 int rlic_b200_set_schedule(int which);
 int rlic_b200_get_schedule(void);
 
-/* How the pass kernels are written.  Same results bit for bit; a process-wide choice like the
+/* How the pass kernels are written.  Same results bit for bit; a process-wide default like the
  * two above.
- *   RLIC_B200_WALK_PER_STEP  the kernels every measurement of round 1 was made with (default)
- *   RLIC_B200_WALK_GROUPED   the loop-exit test once per group of steps, no negation of the
- *                            record in the backward pass: 6 (f32) / 1-2 (f64) fewer
- *                            instructions per step in the sm_100a SASS; reproduces the oracle on
- *                            the CPU emulation of the kernel source, not yet run or timed on a GPU.
- *                            Applies to the default arithmetic only. */
+ *   RLIC_B200_WALK_GROUPED   (default since round 2) the loop-exit test once per group of steps,
+ *                            no negation of the record in the backward pass: 6 (f32) / 1-2 (f64)
+ *                            fewer instructions per step in the sm_100a SASS; measured on a B200
+ *                            at 1.43 ms against 1.59 ms per 4096^2 x 65-tap f32 pass
+ *                            (profiles/r2_session_lab_grouped_f32_f64.txt).  Applies to the
+ *                            default arithmetic only.
+ *   RLIC_B200_WALK_PER_STEP  the kernels every measurement of round 1 was made with; kept as
+ *                            the yardstick of tools/kernel_lab and for the `fma` arithmetic. */
 #define RLIC_B200_WALK_PER_STEP 0
 #define RLIC_B200_WALK_GROUPED 1
 int rlic_b200_set_walk(int which);
 int rlic_b200_get_walk(void);
+
+/* Per-thread overrides of the three choices above, for the calls the CALLING THREAD makes from
+ * now on (every entry point reads its choices once, on the thread that entered the library;
+ * the batch entry hands them to its worker threads).  -1 = no override, use the process-wide
+ * default.  Nothing shared is written: two threads that want different arithmetic do not
+ * race (the reference is re-entrant, src/lib.rs:448 `gil_used = false`).
+ * rlic_b200_get_thread_options reads the overrides back, rlic_b200_get_effective_options
+ * what a call made now by this thread would use. */
+int rlic_b200_set_thread_options(int arithmetic, int schedule, int walk);
+void rlic_b200_get_thread_options(int *arithmetic, int *schedule, int *walk);
+void rlic_b200_get_effective_options(int *arithmetic, int *schedule, int *walk);
 
 /* Testing hook (host code only): the (pass, band) launch order of the wavefront schedule
  * for `nbands` bands and `iterations` passes, as pairs pass_band[2k] = pass (1-based),

@@ -35,8 +35,10 @@
  * Build: see oracle/Makefile  (-O3 -march=x86-64-v3 -ffp-contract=off, which
  * mirrors .cargo/config.toml:3 and Rust's no-contraction rule).
  */
+#define _GNU_SOURCE
 #include <math.h>
 #include <pthread.h>
+#include <sched.h>
 #include <stdatomic.h>
 #include <stddef.h>
 #include <stdint.h>
@@ -54,16 +56,37 @@ typedef struct {
     int polarization;         /* 0 velocity, 1 polarization */
 } lic_geometry;
 
-/* Runs `body(arg)` on `threads` threads (the caller is one of them). */
+/* Runs `body(arg)` on `threads` threads (the caller is one of them).  Helper
+ * threads are pinned, one per CPU of the caller's affinity mask in turn, so that
+ * the all-cores baseline does not depend on where the scheduler puts them (the
+ * caller keeps its own mask: the library never changes its caller's affinity). */
 static void lic_run_threads(void *(*body)(void *), void *arg, int threads)
 {
     if (threads > 256)
         threads = 256;
     pthread_t tid[256];
     int started = 0;
-    for (int t = 1; t < threads; ++t)
-        if (pthread_create(&tid[started], NULL, body, arg) == 0)
+    cpu_set_t allowed;
+    int ncpu = 0, cpus[CPU_SETSIZE];
+    if (sched_getaffinity(0, sizeof allowed, &allowed) == 0)
+        for (int c = 0; c < CPU_SETSIZE; ++c)
+            if (CPU_ISSET(c, &allowed))
+                cpus[ncpu++] = c;
+    for (int t = 1; t < threads; ++t) {
+        pthread_attr_t attr;
+        pthread_attr_init(&attr);
+        if (ncpu > 1) {
+            cpu_set_t one;
+            CPU_ZERO(&one);
+            CPU_SET(cpus[t % ncpu], &one);
+            pthread_attr_setaffinity_np(&attr, sizeof one, &one);
+        }
+        if (pthread_create(&tid[started], &attr, body, arg) == 0)
             ++started;
+        else if (pthread_create(&tid[started], NULL, body, arg) == 0)   /* pinning refused: unpinned */
+            ++started;
+        pthread_attr_destroy(&attr);
+    }
     body(arg);
     for (int t = 0; t < started; ++t)
         pthread_join(tid[t], NULL);
@@ -262,6 +285,13 @@ KAT_CROSS(double, f64)
 #include <unistd.h>
 int lic_oracle_max_threads(void)
 {
+    /* the CPUs this process may run on (a container's share), not the machine's */
+    cpu_set_t allowed;
+    if (sched_getaffinity(0, sizeof allowed, &allowed) == 0) {
+        int n = CPU_COUNT(&allowed);
+        if (n > 0)
+            return n;
+    }
     long n = sysconf(_SC_NPROCESSORS_ONLN);
     return n > 0 ? (int)n : 1;
 }

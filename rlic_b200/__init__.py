@@ -13,14 +13,16 @@ __all__ = [
     "convolve",
     "convolve_batch",
     "convolve_sharded",
+    "effective_options",
     "get_arithmetic",
     "get_schedule",
     "get_walk",
+    "options",
     "set_arithmetic",
     "set_schedule",
     "set_walk",
 ]
 
-from rlic_b200._core import (get_arithmetic, get_schedule, get_walk, set_arithmetic, set_schedule,
-                             set_walk)
+from rlic_b200._core import (effective_options, get_arithmetic, get_schedule, get_walk, options,
+                             set_arithmetic, set_schedule, set_walk)
 from rlic_b200._lib import convolve, convolve_batch, convolve_sharded

@@ -30,7 +30,7 @@ import numpy as np
 _LIB_PATH = Path(__file__).resolve().parent / "librlic_b200.so"
 
 OK, EINVAL, ENODEVICE, ECUDA, ESHARD = range(5)
-ABI_VERSION = 2
+ABI_VERSION = 3
 ARITHMETICS = {"fma+branchless": 0, "fma": 1}   # RLIC_B200_ARITH_* in include/rlic_b200.h
 SCHEDULES = {"trailing": 0, "wavefront": 1}      # RLIC_B200_SCHEDULE_*
 WALKS = {"per-step": 0, "grouped": 1}            # RLIC_B200_WALK_*
@@ -108,6 +108,13 @@ def _load() -> ctypes.CDLL:
     cdll.rlic_b200_peer_wait.argtypes = [_vp, ctypes.c_uint32, _i64, _vp, _vp]
     for name in ("alloc", "open", "close", "free", "signal", "wait"):
         getattr(cdll, f"rlic_b200_peer_{name}").restype = _int
+    cdll.rlic_b200_set_thread_options.argtypes = [_int, _int, _int]
+    cdll.rlic_b200_set_thread_options.restype = _int
+    _pi = ctypes.POINTER(ctypes.c_int)
+    cdll.rlic_b200_get_thread_options.argtypes = [_pi, _pi, _pi]
+    cdll.rlic_b200_get_thread_options.restype = None
+    cdll.rlic_b200_get_effective_options.argtypes = [_pi, _pi, _pi]
+    cdll.rlic_b200_get_effective_options.restype = None
     cdll.rlic_b200_set_walk.argtypes = [_int]
     cdll.rlic_b200_set_walk.restype = _int
     cdll.rlic_b200_get_walk.restype = _int
@@ -152,7 +159,8 @@ def set_arithmetic(name: str) -> None:
     """Choose which build of the reference the kernels reproduce bit for bit
     (include/rlic_b200.h): ``"fma+branchless"`` -- the crate default, i.e. source
     builds and the aarch64 wheels, the default here -- or ``"fma"``, the x86-64
-    wheels.  Process-wide; also settable with ``RLIC_B200_ARITHMETIC``."""
+    wheels.  The process-wide default; also settable with ``RLIC_B200_ARITHMETIC``.  For one
+    thread's calls use ``options``."""
     try:
         code = ARITHMETICS[name]
     except KeyError:
@@ -167,8 +175,9 @@ def get_arithmetic() -> str:
 
 def set_schedule(name: str) -> None:
     """How the host path orders uploads, passes and downloads of one large image
-    (include/rlic_b200.h): ``"trailing"`` (default) or ``"wavefront"``.  Same results
-    either way.  Process-wide; also settable with ``RLIC_B200_SCHEDULE``."""
+    (include/rlic_b200.h): ``"wavefront"`` (default since round 2) or ``"trailing"``.  Same
+    results either way.  The process-wide default; also settable with ``RLIC_B200_SCHEDULE``.
+    For one thread's calls use ``options``."""
     try:
         code = SCHEDULES[name]
     except KeyError:
@@ -182,9 +191,10 @@ def get_schedule() -> str:
 
 
 def set_walk(name: str) -> None:
-    """Which formulation of the pass kernels runs (include/rlic_b200.h): ``"per-step"``
-    (default: what every published measurement used) or ``"grouped"`` (fewer instructions
-    per step, same bits).  Process-wide; also settable with ``RLIC_B200_WALK``."""
+    """Which formulation of the pass kernels runs (include/rlic_b200.h): ``"grouped"``
+    (default since round 2: fewer instructions per step, same bits, 1.43 against 1.59 ms per
+    4096^2 x 65-tap pass on a B200) or ``"per-step"`` (round 1's kernels).  The process-wide
+    default; also settable with ``RLIC_B200_WALK``.  For one thread's calls use ``options``."""
     try:
         code = WALKS[name]
     except KeyError:
@@ -195,6 +205,53 @@ def set_walk(name: str) -> None:
 def get_walk() -> str:
     code = int(lib.rlic_b200_get_walk())
     return next(name for name, c in WALKS.items() if c == code)
+
+
+class options:
+    """Context manager: choices for the calls THIS THREAD makes inside the block, leaving the
+    process-wide defaults (and every other thread) alone::
+
+        with rlic_b200.options(arithmetic="fma"):
+            out = rlic_b200.convolve(...)          # the bits of rLIC's x86-64 wheels
+
+    ``arithmetic``, ``schedule``, ``walk`` take the names ``set_arithmetic`` / ``set_schedule``
+    / ``set_walk`` take; ``None`` keeps whatever is in force.  Backed by
+    ``rlic_b200_set_thread_options`` (include/rlic_b200.h): nothing shared is written, so
+    concurrent threads with different choices do not race."""
+
+    def __init__(self, *, arithmetic: str | None = None, schedule: str | None = None,
+                 walk: str | None = None):
+        def code(table, name, what):
+            if name is None:
+                return None
+            if name not in table:
+                raise ValueError(f"unknown {what} {name!r}: expected one of {sorted(table)}")
+            return table[name]
+
+        self._want = (code(ARITHMETICS, arithmetic, "arithmetic"), code(SCHEDULES, schedule, "schedule"),
+                      code(WALKS, walk, "walk"))
+        self._saved = None
+
+    def __enter__(self):
+        saved = [ctypes.c_int(), ctypes.c_int(), ctypes.c_int()]
+        lib.rlic_b200_get_thread_options(*(ctypes.byref(x) for x in saved))
+        self._saved = tuple(x.value for x in saved)
+        check(lib.rlic_b200_set_thread_options(*(s if w is None else w for s, w in zip(self._saved, self._want))))
+        return self
+
+    def __exit__(self, *exc):
+        check(lib.rlic_b200_set_thread_options(*self._saved))
+        return False
+
+
+def effective_options() -> dict:
+    """What a call made now by this thread would use: ``{"arithmetic", "schedule", "walk"}``."""
+    got = [ctypes.c_int(), ctypes.c_int(), ctypes.c_int()]
+    lib.rlic_b200_get_effective_options(*(ctypes.byref(x) for x in got))
+    names = []
+    for table, x in zip((ARITHMETICS, SCHEDULES, WALKS), got):
+        names.append(next(name for name, c in table.items() if c == x.value))
+    return dict(zip(("arithmetic", "schedule", "walk"), names))
 
 
 def device_count() -> int:

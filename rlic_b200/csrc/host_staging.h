@@ -160,7 +160,9 @@ public:
         Slot &s = slots_[cursor_.fetch_add(1) % kSlots];
         s.mu.lock();
         if (!s.host) {
-            if (cudaHostAlloc(&s.host, kChunk, cudaHostAllocDefault) != cudaSuccess ||
+            // the event belongs to the device that is current now: a pool serves ONE device
+            // (pinned_pool(device)), because an event cannot be recorded on another device's stream
+            if (cudaHostAlloc(&s.host, kChunk, cudaHostAllocPortable) != cudaSuccess ||
                 cudaEventCreateWithFlags(&s.drained, cudaEventDisableTiming) != cudaSuccess) {
                 cudaGetLastError();
                 if (s.host) { cudaFreeHost(s.host); s.host = nullptr; }
@@ -178,10 +180,21 @@ private:
     std::atomic<unsigned> cursor_{0};
 };
 
-PinnedPool &pinned_pool()
+// One pool per device ordinal (created on first use, lives for the process): a slot's
+// `drained` event is tied to the device it was created on, and the batch entry point
+// runs lanes for several devices at once.
+PinnedPool &pinned_pool(int device)
 {
-    static PinnedPool *p = new PinnedPool;
-    return *p;
+    static std::mutex mu;
+    static std::vector<PinnedPool *> pools;
+    std::lock_guard<std::mutex> lk(mu);
+    if (device < 0)
+        device = 0;
+    if ((size_t)device >= pools.size())
+        pools.resize((size_t)device + 1, nullptr);
+    if (!pools[(size_t)device])
+        pools[(size_t)device] = new PinnedPool;
+    return *pools[(size_t)device];
 }
 
 bool is_pageable(const void *ptr)
@@ -220,15 +233,18 @@ cudaError_t upload(const HostToDevice *jobs, int njobs, cudaStream_t stream)
     int device = 0;
     cudaGetDevice(&device);
     std::atomic<int> failed{(int)cudaSuccess};
+    PinnedPool &pool = pinned_pool(device);
     workers().parallel_for(pieces.size(), [&](size_t i) {
         cudaSetDevice(device);   // worker threads start on device 0
         const Piece &p = pieces[i];
         cudaError_t e;
-        if (PinnedPool::Slot *slot = pinned_pool().acquire()) {
+        if (PinnedPool::Slot *slot = pool.acquire()) {
             std::memcpy(slot->host, p.src, p.bytes);
             e = cudaMemcpyAsync(p.dst, slot->host, p.bytes, cudaMemcpyHostToDevice, stream);
             if (e == cudaSuccess)
                 e = cudaEventRecord(slot->drained, stream);
+            if (e != cudaSuccess)
+                cudaStreamSynchronize(stream);   // never hand the slot on with its DMA unfenced
             slot->mu.unlock();
         } else {
             e = cudaMemcpyAsync(p.dst, p.src, p.bytes, cudaMemcpyHostToDevice, stream);
@@ -270,9 +286,14 @@ public:
             return nullptr;
         // make room by dropping cached blocks of other sizes, oldest first
         while (total_ + cls > kCap && !free_.empty()) {
-            cudaFreeHost(free_.front().first);
+            void *gone = free_.front().first;
+            cudaFreeHost(gone);
             total_ -= free_.front().second;
             free_.erase(free_.begin());
+            // forget its size class too: the allocator may hand the address out again for another
+            sizes_.erase(std::remove_if(sizes_.begin(), sizes_.end(),
+                                        [gone](const std::pair<void *, size_t> &e) { return e.first == gone; }),
+                         sizes_.end());
         }
         if (total_ + cls > kCap)
             return nullptr;

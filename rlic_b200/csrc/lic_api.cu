@@ -29,8 +29,30 @@ thread_local std::string tls_error;
 thread_local int tls_device = 0;
 std::atomic<int64_t> g_launches{0};
 std::atomic<int> g_force_wide{0};   // testing hook: use 64-bit element indices for any size
-std::atomic<int> g_arithmetic{RLIC_B200_ARITH_FMA_BRANCHLESS};   // which reference build to reproduce
-std::atomic<int> g_walk{RLIC_B200_WALK_PER_STEP};                // which formulation of the pass kernels
+// The three choices a call can make (include/rlic_b200.h): which reference build to reproduce,
+// which formulation of the pass kernels, how the host path orders its launches.  Each has a
+// process-wide DEFAULT (the atomics: set once at start-up, e.g. from the environment) and a
+// per-thread override (rlic_b200_set_thread_options; -1 = no override) that the calling thread
+// sets around its own calls, so that two threads wanting different arithmetic never race on
+// shared state.  A call reads its choices through the effective_*() functions on the thread
+// that entered the library; the batch entry hands them to its worker threads.
+std::atomic<int> g_arithmetic{RLIC_B200_ARITH_FMA_BRANCHLESS};
+std::atomic<int> g_walk{RLIC_B200_WALK_GROUPED};
+std::atomic<int> g_schedule{RLIC_B200_SCHEDULE_WAVEFRONT};
+struct ThreadChoices { int arithmetic = -1, schedule = -1, walk = -1; };
+thread_local ThreadChoices tls_choices;
+int effective_arithmetic()
+{
+    return tls_choices.arithmetic >= 0 ? tls_choices.arithmetic : g_arithmetic.load(std::memory_order_relaxed);
+}
+int effective_schedule()
+{
+    return tls_choices.schedule >= 0 ? tls_choices.schedule : g_schedule.load(std::memory_order_relaxed);
+}
+int effective_walk()
+{
+    return tls_choices.walk >= 0 ? tls_choices.walk : g_walk.load(std::memory_order_relaxed);
+}
 
 int fail(int code, const char *fmt, ...)
 {
@@ -257,15 +279,15 @@ cudaError_t launch_one(const T *tex, const Field<T> *field, T *out, const PassGe
     using Tn = rlic::Tune<T, POL>;
     if (peer.out) {   // the default arithmetic only (checked by the caller)
         if (grouped)
-            rlic::lic_pass_peer_kernel<T, POL, Taps, Idx, rlic::kTileW, rlic::kTileH, Tn::unroll,
-                                       Tn::min_blocks, Tn::walk_flavor, Tn::admit, true, Tn::walk>
+            rlic::lic_pass_peer_kernel<T, POL, Taps, Idx, rlic::kTileW, rlic::kTileH, Tn::walk_unroll,
+                                       Tn::walk_min_blocks, Tn::walk_flavor, Tn::admit, true, Tn::walk>
                 <<<blocks, rlic::kThreads, 0, stream>>>(tex, field, out, g, taps, ntaps, peer.out, peer.delta);
         else
             rlic::lic_pass_peer_kernel<T, POL, Taps, Idx>
                 <<<blocks, rlic::kThreads, 0, stream>>>(tex, field, out, g, taps, ntaps, peer.out, peer.delta);
     } else if (branchless && grouped)
-        rlic::lic_pass_kernel<T, POL, Taps, Idx, rlic::kTileW, rlic::kTileH, Tn::unroll, Tn::min_blocks,
-                              Tn::walk_flavor, Tn::admit, true, Tn::walk>
+        rlic::lic_pass_kernel<T, POL, Taps, Idx, rlic::kTileW, rlic::kTileH, Tn::walk_unroll,
+                              Tn::walk_min_blocks, Tn::walk_flavor, Tn::admit, true, Tn::walk>
             <<<blocks, rlic::kThreads, 0, stream>>>(tex, field, out, g, taps, ntaps);
     else if (branchless)
         rlic::lic_pass_kernel<T, POL, Taps, Idx>
@@ -300,8 +322,8 @@ int launch_pass(const T *tex, const Field<T> *field, T *out, PassGeom g, int64_t
     const bool wide = g.field_stride >= (int64_t)INT_MAX ||
                       g_force_wide.load(std::memory_order_relaxed) != 0;
     const bool pol = uv_mode == RLIC_B200_POLARIZATION;
-    const bool branchless = g_arithmetic.load(std::memory_order_relaxed) == RLIC_B200_ARITH_FMA_BRANCHLESS;
-    const bool grouped = g_walk.load(std::memory_order_relaxed) == RLIC_B200_WALK_GROUPED;
+    const bool branchless = effective_arithmetic() == RLIC_B200_ARITH_FMA_BRANCHLESS;
+    const bool grouped = effective_walk() == RLIC_B200_WALK_GROUPED;
     if (peer.out && (!branchless || nfields != 1))
         return fail(RLIC_B200_EINVAL, "the fused halo exchange needs the default arithmetic and one field");
 
@@ -360,8 +382,6 @@ std::vector<BandPass> wavefront_order(int64_t nbands, int64_t iterations)
         }
     return order;
 }
-
-std::atomic<int> g_schedule{RLIC_B200_SCHEDULE_TRAILING};
 
 // Host entry: upload -> passes -> download, pipelined over row bands.
 //   stream `io`  : uploads (band by band: u, v -> packed field; texture -> padded
@@ -475,7 +495,7 @@ int convolve_host(const T *tex, const T *u, const T *v, int64_t nfields, int64_t
     // Early bands run through all their passes while later bands are still on the bus,
     // and their results go back while later bands still compute.  Needs a top and a
     // bottom that do not depend on each other (no wrap in y) and something to skew.
-    if (g_schedule.load(std::memory_order_relaxed) == RLIC_B200_SCHEDULE_WAVEFRONT && !periodic_y &&
+    if (effective_schedule() == RLIC_B200_SCHEDULE_WAVEFRONT && !periodic_y &&
         iterations >= 2 && nbands >= 2) {
         const std::vector<BandPass> order = wavefront_order(nbands, iterations);
         auto upload_needed = [&](int64_t b) {   // last band a pass-1 walker of band b can reach
@@ -815,6 +835,7 @@ int convolve_batch(const T *tex, const T *u, const T *v, int64_t nfields, int64_
     const int64_t chunk = std::max<int64_t>(1, (int64_t)((size_t)(16u << 20) / field_elems));
 
     const int lanes = 2;
+    const ThreadChoices mine{effective_arithmetic(), effective_schedule(), effective_walk()};
     std::vector<int> rcs(devs.size() * lanes, 0);
     std::vector<std::string> msgs(devs.size() * lanes);
     std::vector<std::atomic<int64_t>> cursor(devs.size());
@@ -824,6 +845,7 @@ int convolve_batch(const T *tex, const T *u, const T *v, int64_t nfields, int64_
         cursor[(size_t)d].store(f0);
         for (int lane = 0; lane < lanes; ++lane) {
             threads.emplace_back([&, d, f1, lane]() {
+                tls_choices = mine;   // the caller's choices, not this fresh thread's defaults
                 int rc = 0;
                 while (!rc) {
                     const int64_t f = cursor[(size_t)d].fetch_add(chunk);
@@ -930,6 +952,33 @@ int rlic_b200_set_schedule(int which)
 }
 
 int rlic_b200_get_schedule(void) { return g_schedule.load(std::memory_order_relaxed); }
+
+int rlic_b200_set_thread_options(int arithmetic, int schedule, int walk)
+{
+    tls_error.clear();
+    if (arithmetic != -1 && arithmetic != RLIC_B200_ARITH_FMA_BRANCHLESS && arithmetic != RLIC_B200_ARITH_FMA)
+        return fail(RLIC_B200_EINVAL, "unknown arithmetic %d", arithmetic);
+    if (schedule != -1 && schedule != RLIC_B200_SCHEDULE_TRAILING && schedule != RLIC_B200_SCHEDULE_WAVEFRONT)
+        return fail(RLIC_B200_EINVAL, "unknown schedule %d", schedule);
+    if (walk != -1 && walk != RLIC_B200_WALK_PER_STEP && walk != RLIC_B200_WALK_GROUPED)
+        return fail(RLIC_B200_EINVAL, "unknown walk %d", walk);
+    tls_choices = ThreadChoices{arithmetic, schedule, walk};
+    return RLIC_B200_OK;
+}
+
+void rlic_b200_get_thread_options(int *arithmetic, int *schedule, int *walk)
+{
+    if (arithmetic) *arithmetic = tls_choices.arithmetic;
+    if (schedule) *schedule = tls_choices.schedule;
+    if (walk) *walk = tls_choices.walk;
+}
+
+void rlic_b200_get_effective_options(int *arithmetic, int *schedule, int *walk)
+{
+    if (arithmetic) *arithmetic = effective_arithmetic();
+    if (schedule) *schedule = effective_schedule();
+    if (walk) *walk = effective_walk();
+}
 
 int64_t rlic_b200_debug_wavefront_order(int64_t nbands, int64_t iterations, int32_t *pass_band,
                                         int64_t capacity)

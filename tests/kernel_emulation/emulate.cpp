@@ -130,8 +130,9 @@ void run_pass(const T *tex, const T *field, T *out, const PassGeom &g, const Tap
     using Tn = rlic::Tune<T, POL>;
     auto *f = reinterpret_cast<const rlic::PackedField<T> *>(field);
     launch(blocks, rlic::kThreads, [&] {
-        rlic::lic_pass_kernel<T, POL, Taps, Idx, rlic::kTileW, rlic::kTileH, Tn::unroll, Tn::min_blocks,
-                              FLAVOR, ADMIT, BRANCHLESS, WALK>(tex, f, out, g, taps, ntaps);
+        rlic::lic_pass_kernel<T, POL, Taps, Idx, rlic::kTileW, rlic::kTileH, (WALK ? Tn::walk_unroll : Tn::unroll),
+                              (WALK ? Tn::walk_min_blocks : Tn::min_blocks), FLAVOR, ADMIT, BRANCHLESS, WALK>(
+            tex, f, out, g, taps, ntaps);
     });
 }
 
@@ -227,8 +228,8 @@ void run_pass_peer(const T *tex, const T *field, T *out, const PassGeom &g, cons
     auto *f = reinterpret_cast<const rlic::PackedField<T> *>(field);
     if (walk)
         launch(blocks, rlic::kThreads, [&] {
-            rlic::lic_pass_peer_kernel<T, POL, Taps, int, rlic::kTileW, rlic::kTileH, Tn::unroll, Tn::min_blocks,
-                                       Tn::walk_flavor, Tn::admit, true, Tn::walk>(tex, f, out, g, taps, ntaps,
+            rlic::lic_pass_peer_kernel<T, POL, Taps, int, rlic::kTileW, rlic::kTileH, Tn::walk_unroll,
+                                       Tn::walk_min_blocks, Tn::walk_flavor, Tn::admit, true, Tn::walk>(tex, f, out, g, taps, ntaps,
                                                                                     peer_out, peer_delta);
         });
     else

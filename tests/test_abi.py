@@ -171,15 +171,15 @@ def test_schedule_selection_round_trips():
     for name, code in _core.SCHEDULES.items():
         m = re.search(rf"#define RLIC_B200_SCHEDULE_{name.upper()} (\d+)", HEADER)
         assert int(m.group(1)) == code
-    assert rlic_b200.get_schedule() == "trailing"
+    assert rlic_b200.get_schedule() == "wavefront"     # measured on a B200: the faster order
     try:
-        rlic_b200.set_schedule("wavefront")
-        assert rlic_b200.get_schedule() == "wavefront"
+        rlic_b200.set_schedule("trailing")
+        assert rlic_b200.get_schedule() == "trailing"
         with pytest.raises(ValueError, match="unknown schedule"):
             rlic_b200.set_schedule("diagonal")
         assert _core.lib.rlic_b200_set_schedule(9) == _core.EINVAL
     finally:
-        rlic_b200.set_schedule("trailing")
+        rlic_b200.set_schedule("wavefront")
 
 
 def test_walk_selection_round_trips_and_reads_the_environment():
@@ -192,20 +192,55 @@ def test_walk_selection_round_trips_and_reads_the_environment():
     for name, code in _core.WALKS.items():
         m = re.search(rf"#define RLIC_B200_WALK_{name.upper().replace('-', '_')} (\d+)", HEADER)
         assert int(m.group(1)) == code
-    assert rlic_b200.get_walk() == "per-step"      # the kernels every published number was measured with
+    assert rlic_b200.get_walk() == "grouped"       # measured on a B200: the faster formulation
     try:
-        rlic_b200.set_walk("grouped")
-        assert rlic_b200.get_walk() == "grouped"
+        rlic_b200.set_walk("per-step")
+        assert rlic_b200.get_walk() == "per-step"
         with pytest.raises(ValueError, match="unknown walk"):
             rlic_b200.set_walk("sideways")
         assert _core.lib.rlic_b200_set_walk(5) == _core.EINVAL
-        assert rlic_b200.get_walk() == "grouped"
+        assert rlic_b200.get_walk() == "per-step"
     finally:
-        rlic_b200.set_walk("per-step")
+        rlic_b200.set_walk("grouped")
     code = "import rlic_b200; print(rlic_b200.get_walk())"
-    env = dict(os.environ, RLIC_B200_WALK="grouped", PYTHONPATH=str(ROOT))
+    env = dict(os.environ, RLIC_B200_WALK="per-step", PYTHONPATH=str(ROOT))
     assert subprocess.run([sys.executable, "-c", code], env=env, capture_output=True,
-                          text=True).stdout.strip() == "grouped"
+                          text=True).stdout.strip() == "per-step"
     env["RLIC_B200_WALK"] = "nonsense"
     bad = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
     assert bad.returncode != 0 and "RLIC_B200_WALK" in bad.stderr
+
+
+def test_thread_options_override_the_defaults_for_one_thread_only():
+    """rlic_b200.options: a thread's choices for its own calls (rlic_b200_set_thread_options);
+    other threads and the process-wide defaults are untouched, and -1 / None inherit."""
+    import threading
+
+    import rlic_b200
+
+    base = rlic_b200.effective_options()
+    assert base == {"arithmetic": "fma+branchless", "schedule": "wavefront", "walk": "grouped"}
+    seen = {}
+
+    def other_thread():
+        seen["other"] = rlic_b200.effective_options()
+        with rlic_b200.options(walk="per-step"):
+            seen["other_inside"] = rlic_b200.effective_options()
+
+    with rlic_b200.options(arithmetic="fma", schedule="trailing"):
+        mine = rlic_b200.effective_options()
+        t = threading.Thread(target=other_thread)
+        t.start()
+        t.join()
+        with rlic_b200.options(walk="per-step"):          # nests: keeps the outer overrides
+            nested = rlic_b200.effective_options()
+        assert rlic_b200.effective_options() == mine
+    assert mine == {"arithmetic": "fma", "schedule": "trailing", "walk": "grouped"}
+    assert nested == {"arithmetic": "fma", "schedule": "trailing", "walk": "per-step"}
+    assert seen["other"] == base
+    assert seen["other_inside"] == dict(base, walk="per-step")
+    assert rlic_b200.effective_options() == base
+    assert rlic_b200.get_arithmetic() == "fma+branchless"   # the defaults never moved
+    with pytest.raises(ValueError, match="unknown walk"):
+        rlic_b200.options(walk="sideways")
+    assert _core.lib.rlic_b200_set_thread_options(7, -1, -1) == _core.EINVAL

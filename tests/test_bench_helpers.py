@@ -47,14 +47,41 @@ def test_path_divergence_is_zero_for_the_oracle_itself_and_sees_the_other_build(
     json.dumps(other)
 
 
-def test_cpu_baseline_sample_is_a_band_of_the_headline_workload():
-    info = bench.cpu_baseline(None, 0.5)
-    r0, band = info.pop("_band")
+def test_cpu_baseline_times_whole_passes_of_the_headline_workload():
+    info = bench.cpu_baseline(None, reps=1)
+    pass1 = info.pop("_pass1")
+    tex, u, v, kernel = info.pop("_inputs")
     assert info["kind"] == "port" and info["cores"] == oracle.max_threads() and info["unit"] == "Mpix/s"
-    assert band.shape[1] == bench.N_SIDE and band.dtype == np.float32 and 0 <= r0 < bench.N_SIDE
-    assert f"rows [{r0}, {r0 + band.shape[0]})" in info["sample"]
+    assert pass1.shape == (bench.N_SIDE, bench.N_SIDE) and pass1.dtype == np.float32
+    assert "whole passes" in info["sample"] and info["spread"][0] <= info["seconds"] <= info["spread"][1]
+    assert abs(info["value"] - bench.N_SIDE ** 2 / info["seconds"] / 1e6) < 1e-6
     json.dumps(info)
-    # the band is pass 1 of the workload bench.py times on the GPU
-    tex, u, v, kernel = bench.make_slab(0, 1)
-    want = oracle.pass_rows(tex, u, v, kernel=kernel, rows=(r0, r0 + 8), threads=oracle.max_threads())
-    np.testing.assert_array_equal(band[:8], want)
+    # what was timed is pass 1 of the workload bench.py times on the GPU
+    want = oracle.pass_rows(tex, u, v, kernel=kernel, rows=(1000, 1008), threads=oracle.max_threads())
+    np.testing.assert_array_equal(pass1[1000:1008], want)
+    single = bench.cpu_single_thread(tex, u, v, kernel, reps=1)
+    assert single["cores"] == 1 and single["value"] > 0
+    json.dumps(single)
+
+
+def test_slab_parity_band_checks_slab_edges_against_a_whole_image_run(monkeypatch):
+    """bench.py --gpus N: every rank compares the first and last rows of its slab of the final
+    result with the oracle run on a sub-image wide enough that the artificial cuts cannot
+    reach them.  Here the 'ranks' results are cut from a whole-image oracle run at a reduced
+    size: every band agrees, and a perturbed one is reported."""
+    monkeypatch.setattr(bench, "N_SIDE", 384)
+    world = 3
+    slabs = [bench.make_slab(r, world) for r in range(world)]
+    tex, u, v = (np.concatenate([s[k] for s in slabs]) for k in range(3))
+    full = oracle.convolve(tex, u, v, kernel=slabs[0][3], iterations=bench.ITERATIONS, threads=oracle.max_threads())
+    for rank in range(world):
+        for first in (0, bench.N_SIDE - 64):
+            rows = full[rank * bench.N_SIDE + first:rank * bench.N_SIDE + first + 64]
+            got = bench.slab_parity_band(rank, world, rows, first)
+            assert got["bit_equal"] and got["mismatches"] == 0
+            assert got["rows"] == [rank * bench.N_SIDE + first, rank * bench.N_SIDE + first + 64]
+            json.dumps(got)
+    wrong = full[bench.N_SIDE:bench.N_SIDE + 64].copy()
+    wrong[3, 7] = np.nextafter(wrong[3, 7], np.float32(9))
+    got = bench.slab_parity_band(1, world, wrong, 0)
+    assert not got["bit_equal"] and got["mismatches"] == 1

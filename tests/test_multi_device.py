@@ -11,7 +11,6 @@ from numpy.testing import assert_array_equal
 
 import kernel_emulation
 import oracle
-from _status import first_gpu_run
 from rlic_b200.multi import MultiDeviceConvolver
 
 CASES = {
@@ -83,7 +82,6 @@ def test_public_entry_validates_like_convolve():
     assert_array_equal(out, tex) and out is not tex
 
 
-@first_gpu_run
 @pytest.mark.gpu
 @pytest.mark.parametrize("ndev", [1, 2, 3])
 def test_convolve_sharded_on_gpus_equals_convolve(ndev):

@@ -15,7 +15,6 @@ import pytest
 from numpy.testing import assert_array_equal
 
 import oracle
-from _status import first_gpu_run
 import rlic_b200 as rlic
 from rlic_b200 import _core, workloads
 
@@ -249,7 +248,6 @@ def test_mismatch_fraction_against_the_pypi_x86_64_variant(capsys):
     assert bit_equal > 0.5
 
 
-@first_gpu_run
 def test_path_divergence_is_zero_against_the_oracle_and_small_against_the_other_build(capsys):
     """north_star: "the fraction of pixels whose traced path diverges is reported".  On the
     path-signature inputs (workloads.path_probe) a pass returns exact integer sums, so the

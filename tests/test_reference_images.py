@@ -18,7 +18,6 @@ from __future__ import annotations
 import numpy as np
 import pytest
 
-from _status import first_gpu_run
 
 import oracle
 import reference_images as ri
@@ -112,7 +111,6 @@ def test_comparison_tells_the_uv_modes_apart(published):
 
 
 # ---- the CUDA path, called exactly as the README calls rlic.convolve --------------------
-@first_gpu_run
 @pytest.mark.gpu
 @pytest.mark.parametrize("iterations", [1, 5, 100])
 def test_cuda_reproduces_base_example(published, iterations):
@@ -125,7 +123,6 @@ def test_cuda_reproduces_base_example(published, iterations):
     assert mean < MEAN_LEVELS and worst < MAX_LEVELS, (mean, worst)
 
 
-@first_gpu_run
 @pytest.mark.gpu
 @pytest.mark.parametrize("uv_mode", ["velocity", "polarization"])
 def test_cuda_reproduces_polarization_example(published, uv_mode):

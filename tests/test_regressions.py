@@ -13,7 +13,6 @@ import pytest
 from numpy.testing import assert_allclose, assert_array_equal
 
 import kernel_emulation as ke
-from _status import first_gpu_run
 import oracle
 from oracle import pyoracle
 from regression_cases import ATOL, CASES, K0, RTOL, TEXTURE, exact_streamline_sum
@@ -52,7 +51,6 @@ def test_the_cases_are_not_degenerate(expected):
     assert_array_equal(expected["U1-V1-velocity"], expected["U1-V1-polarization"])
 
 
-@first_gpu_run
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", CASES)
 def test_outputs(name, expected):

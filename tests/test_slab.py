@@ -16,7 +16,6 @@ from pathlib import Path
 
 import numpy as np
 import pytest
-from _status import first_gpu_run
 
 import oracle
 from rlic_b200 import _core
@@ -202,7 +201,6 @@ def test_two_gpu_sharded_run():
     assert "SHARDED_OK" in proc.stdout
 
 
-@first_gpu_run
 @pytest.mark.skipif(_core.device_count() < 2, reason="needs two GPUs")
 def test_two_gpu_fused_peer_exchange():
     """exchange="peer": the edge-strip passes store into the neighbour's halo through CUDA IPC

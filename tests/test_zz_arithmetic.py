@@ -10,21 +10,17 @@ from numpy.testing import assert_array_equal
 
 import oracle
 import rlic_b200
-from _status import first_gpu_run
 from golden_cases import CASES, as_spec, expected, load
 from rlic_b200 import workloads
 from test_kernel_emulation import WALLS, fuzz_case, random_case
 
-pytestmark = [pytest.mark.gpu, first_gpu_run]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture
 def fma_only():
-    rlic_b200.set_arithmetic("fma")
-    try:
+    with rlic_b200.options(arithmetic="fma"):
         yield
-    finally:
-        rlic_b200.set_arithmetic("fma+branchless")
 
 
 def check(tex, u, v, kernel, mode, walls, iterations, variant):
@@ -78,3 +74,39 @@ def test_switching_back_restores_the_default_build():
     assert_array_equal(default, oracle.convolve(w.texture, w.u, w.v, kernel=w.kernel, iterations=2, variant=3))
     assert_array_equal(other, oracle.convolve(w.texture, w.u, w.v, kernel=w.kernel, iterations=2, variant=1))
     assert (default != other).any()
+
+
+def test_two_threads_with_different_arithmetic_do_not_race():
+    """The choice is per call (per calling thread), not shared mutable state: two threads
+    running concurrently, one per build of the reference, each get exactly their build's
+    bits, call after call, and so does a batch call (its worker threads inherit the
+    caller's choice)."""
+    import threading
+
+    w = workloads.vortex_noise(384, iterations=2)
+    want = {name: oracle.convolve(w.texture, w.u, w.v, kernel=w.kernel, iterations=2, variant=variant)
+            for name, variant in (("fma", 1), ("fma+branchless", 3))}
+    assert (want["fma"] != want["fma+branchless"]).any()
+    failures = []
+    barrier = threading.Barrier(2)
+
+    def worker(name):
+        with rlic_b200.options(arithmetic=name):
+            barrier.wait()
+            for _ in range(12):
+                got = rlic_b200.convolve(w.texture, w.u, w.v, kernel=w.kernel, iterations=2)
+                if not np.array_equal(got, want[name]):
+                    failures.append(name)
+            stack = np.stack([w.texture] * 3)
+            got = rlic_b200.convolve_batch(stack, np.stack([w.u] * 3), np.stack([w.v] * 3), kernel=w.kernel,
+                                           iterations=2)
+            if not all(np.array_equal(g, want[name]) for g in got):
+                failures.append(name + " (batch)")
+
+    threads = [threading.Thread(target=worker, args=(name,)) for name in want]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not failures
+    assert rlic_b200.get_arithmetic() == "fma+branchless"

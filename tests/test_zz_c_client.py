@@ -11,7 +11,6 @@ from pathlib import Path
 import numpy as np
 import pytest
 
-from _status import first_gpu_run
 
 ROOT = Path(__file__).resolve().parents[1]
 LIBDIR = ROOT / "rlic_b200"
@@ -80,7 +79,6 @@ def test_python_regenerates_the_c_inputs_exactly(client):
     assert first == f"inputs {inputs_checksum():016x}"
 
 
-@first_gpu_run
 @pytest.mark.gpu
 def test_c_client_matches_the_oracle(client):
     import oracle

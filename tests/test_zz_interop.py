@@ -5,7 +5,6 @@ from __future__ import annotations
 import numpy as np
 import pytest
 
-from _status import first_gpu_run
 
 torch = pytest.importorskip("torch")
 
@@ -47,7 +46,6 @@ def test_host_arrays_are_rejected_with_a_type_error():
         _check_image("texture", [[0.0]])
 
 
-@first_gpu_run
 @pytest.mark.gpu
 @pytest.mark.parametrize("wrap", [CudaArrayOnly, DLPackOnly], ids=["cuda_array_interface", "dlpack"])
 @pytest.mark.parametrize("dtype", ["float32", "float64"])

@@ -1,5 +1,7 @@
-"""``rlic_b200.set_schedule("wavefront")`` on the GPU: same bits as the default order of the
-host path, on images large enough to be cut into row bands.  The launch order itself is
+"""The two launch orders of the host path on the GPU: the wavefront schedule (default since
+round 2) and the trailing one give the same bits, on images large enough to be cut into row
+bands; the tests below pin the wavefront order explicitly for their own thread
+(``rlic_b200.options``) whatever the process-wide default is.  The launch order itself is
 checked on the CPU (tests/test_kernel_emulation.py: dependencies, and an in-order replay of
 the schedule through the emulated kernels)."""
 from __future__ import annotations
@@ -10,31 +12,25 @@ from numpy.testing import assert_array_equal
 
 import oracle
 import rlic_b200
-from _status import first_gpu_run
 from rlic_b200 import workloads
 
-pytestmark = [pytest.mark.gpu, first_gpu_run]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture
 def wavefront():
-    rlic_b200.set_schedule("wavefront")
-    try:
+    with rlic_b200.options(schedule="wavefront"):
         yield
-    finally:
-        rlic_b200.set_schedule("trailing")
 
 
 @pytest.mark.parametrize("n,iterations", [(2048, 2), (3072, 5), (4096, 3)])
-def test_wavefront_gives_the_default_orders_bits(n, iterations):
+def test_wavefront_and_trailing_orders_give_the_same_bits(n, iterations):
     w = workloads.vortex_noise(n, iterations=iterations)
-    default = rlic_b200.convolve(w.texture, w.u, w.v, kernel=w.kernel, iterations=iterations)
-    rlic_b200.set_schedule("wavefront")
-    try:
+    with rlic_b200.options(schedule="trailing"):
+        trailing = rlic_b200.convolve(w.texture, w.u, w.v, kernel=w.kernel, iterations=iterations)
+    with rlic_b200.options(schedule="wavefront"):
         skewed = rlic_b200.convolve(w.texture, w.u, w.v, kernel=w.kernel, iterations=iterations)
-    finally:
-        rlic_b200.set_schedule("trailing")
-    assert_array_equal(skewed, default)
+    assert_array_equal(skewed, trailing)
 
 
 def test_wavefront_against_the_oracle_f64_polarization(wavefront):

@@ -1,7 +1,8 @@
-"""``rlic_b200.set_walk("grouped")`` on the GPU: the second formulation of the pass kernels
-(loop-exit test once per group of steps; backward pass and polarization flip applied to the
-travel direction instead of the record) must return the same bits as the default one, i.e.
-the oracle's.  The kernel source is held to the oracle on the CPU by
+"""The two formulations of the pass kernels on the GPU.  The grouped walk (loop-exit test once
+per group of steps; backward pass and polarization flip applied to the travel direction instead
+of the record) is the default since round 2 and is what every other GPU test exercises; here
+the per-step walk of round 1 -- selected for this thread's calls with
+``rlic_b200.options(walk="per-step")`` -- must return the same bits, i.e. the oracle's.  The kernel source is held to the oracle on the CPU by
 tests/test_kernel_emulation.py (``test_grouped_walk_*``); what only hardware can show is
 nvcc's code for it."""
 from __future__ import annotations
@@ -12,21 +13,20 @@ from numpy.testing import assert_array_equal
 
 import oracle
 import rlic_b200
-from _status import first_gpu_run
 from golden_cases import CASES, as_spec, expected, load
 from rlic_b200 import _core, workloads
 from test_kernel_emulation import WALLS, fuzz_case, random_case
 
-pytestmark = [pytest.mark.gpu, first_gpu_run]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture
-def grouped():
-    rlic_b200.set_walk("grouped")
-    try:
+def per_step():
+    assert rlic_b200.get_walk() == "grouped"
+    with rlic_b200.options(walk="per-step"):
+        assert rlic_b200.effective_options()["walk"] == "per-step"
         yield
-    finally:
-        rlic_b200.set_walk("per-step")
+    assert rlic_b200.effective_options()["walk"] == "grouped"
 
 
 def check(tex, u, v, kernel, mode="velocity", walls="closed", iterations=1):
@@ -40,7 +40,7 @@ def check(tex, u, v, kernel, mode="velocity", walls="closed", iterations=1):
 
 
 @pytest.mark.parametrize("name", CASES)
-def test_golden_vectors(grouped, name):
+def test_golden_vectors(per_step, name):
     mode, bnd, its = CASES[name]
     tex, u, v, kernel = load(name)
     got = rlic_b200.convolve(tex, u, v, kernel=kernel, uv_mode=mode, boundaries=as_spec(bnd), iterations=its)
@@ -48,26 +48,26 @@ def test_golden_vectors(grouped, name):
 
 
 @pytest.mark.parametrize("seed", range(24))
-def test_randomised_configurations(grouped, seed):
+def test_randomised_configurations(per_step, seed):
     tex, u, v, kernel, mode, walls, its = fuzz_case(seed)
     check(tex, u, v, kernel, mode, walls, its)
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
-def test_special_pixels_every_wall_and_mode(grouped, dtype):
+def test_special_pixels_every_wall_and_mode(per_step, dtype):
     for mode in ("velocity", "polarization"):
         for walls in WALLS:
             check(*random_case((45, 70), dtype, 23, seed=11), mode, walls, 2)
 
 
 @pytest.mark.parametrize("klen", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 33, 64, 200, 1001])
-def test_every_remainder_of_the_group_size_and_long_kernels(grouped, klen):
+def test_every_remainder_of_the_group_size_and_long_kernels(per_step, klen):
     for dtype in (np.float32, np.float64):
         check(*random_case((19, 21), dtype, klen, seed=klen), "polarization", "x-periodic")
         check(*random_case((19, 21), dtype, klen, seed=klen + 1), "velocity", "periodic", 2)
 
 
-def test_workloads(grouped):
+def test_workloads(per_step):
     w = workloads.readme_example()                                     # C1 in full
     check(w.texture, w.u, w.v, w.kernel, walls="periodic")
     for dtype in (np.float32, np.float64):                             # C2, reduced
@@ -83,17 +83,14 @@ def test_full_size_c2_pass_equals_the_default_walk():
     """4096 x 4096 f32, 65 taps, 5 iterations: both formulations, bit for bit."""
     w = workloads.vortex_noise(4096, iterations=5)
     default = rlic_b200.convolve(w.texture, w.u, w.v, **w.kwargs())
-    rlic_b200.set_walk("grouped")
-    try:
+    with rlic_b200.options(walk="per-step"):
         before = _core.launch_count()
         other = rlic_b200.convolve(w.texture, w.u, w.v, **w.kwargs())
         assert _core.launch_count() - before >= 5
-    finally:
-        rlic_b200.set_walk("per-step")
     assert_array_equal(default, other)
 
 
-def test_wide_indices_and_batches(grouped):
+def test_wide_indices_and_batches(per_step):
     _core.lib.rlic_b200_debug_force_wide_index(1)
     try:
         check(*random_case((70, 45), np.float32, 19, seed=77), "polarization", "x-periodic", 2)

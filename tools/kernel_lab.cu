@@ -372,8 +372,8 @@ void run_type(const char *tname, int n, int L, const char *only)
     {
         using TV = rlic::Tune<T, false>;
         using TP = rlic::Tune<T, true>;
-        CANDW("grouped tuned vel", false, TV::unroll, TV::min_blocks, TV::walk_flavor, TV::admit, TV::walk);
-        CANDW("grouped tuned pol", true, TP::unroll, TP::min_blocks, TP::walk_flavor, TP::admit, TP::walk);
+        CANDW("grouped tuned vel", false, TV::walk_unroll, TV::walk_min_blocks, TV::walk_flavor, TV::admit, TV::walk);
+        CANDW("grouped tuned pol", true, TP::walk_unroll, TP::walk_min_blocks, TP::walk_flavor, TP::admit, TP::walk);
         if (sizeof(T) == 4) {
             CANDW("grouped vel w1 f1", false, 4, 8, 1, 3, 1);
             CANDW("grouped vel w1 f2", false, 4, 8, 2, 3, 1);

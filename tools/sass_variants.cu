@@ -8,8 +8,8 @@ using PT64 = ParamTaps<double, kParamTapBytes / 8>;
 template <typename T, bool POL, typename PT, int WALK, int FLAVOR> const void *variant()
 {
     using Tn = Tune<T, POL>;
-    return (const void *)&lic_pass_kernel<T, POL, PT, int, kTileW, kTileH, Tn::unroll, Tn::min_blocks, FLAVOR,
-                                          Tn::admit, true, WALK>;
+    return (const void *)&lic_pass_kernel<T, POL, PT, int, kTileW, kTileH, Tn::walk_unroll, Tn::walk_min_blocks,
+                                          FLAVOR, Tn::admit, true, WALK>;
 }
 template <typename T, bool POL, typename PT> const void *shipped()
 {
