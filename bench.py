@@ -459,21 +459,57 @@ def run_ours(args) -> dict:
         "note": "achieved = (3*(L-1)+2)*4 gather bytes per pixel x pixels per launch / mean launch time",
     }
 
+    roofline["frac_note"] = ("nominal: section 8(d)'s algorithmic gather bytes over the HBM copy peak; the gathers "
+                             "are served by L1/L2 (DRAM traffic per launch is the compulsory 0.4 GB), so this "
+                             "fraction exceeds 1 -- the bound that holds is gather_peak below")
+    if world == 1:
+        # The memory system's own limit for this access pattern, measured now, on this box
+        # (SURVEY.md section 8(d)): the library's gather-ceiling probe -- the loads of a pass and
+        # the tap FMA, nothing else -- on the very buffers the timed passes used.  Best of the
+        # two forms (address chain through the loaded record, or free), best of 5 launches each.
+        try:
+            best = {}
+            for dependent in (1, 0):
+                times = []
+                for _ in range(6):
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    _core.check(lib.rlic_b200_measure_gather_ceiling_f32(
+                        pad_a.data_ptr(), field.data_ptr(), pad_b.data_ptr(), N_SIDE, N_SIDE, taps_ptr,
+                        kernel.size, dependent, int(torch.cuda.current_stream().cuda_stream)))
+                    b.record()
+                    b.synchronize()
+                    times.append(a.elapsed_time(b))
+                best["dependent" if dependent else "free"] = min(times[1:])
+            ceil_ms = min(best.values())
+            peak_g = gather_bytes_per_pixel() * pixels_local / (ceil_ms * 1e-3) / 1e9
+            roofline["gather_peak"] = {
+                "GBps": peak_g, "launch_ms": ceil_ms, "forms_ms": best,
+                "how": "rlic_b200_measure_gather_ceiling_f32 (gather_ceiling_kernel in lic_walk.cuh): same loads "
+                       "per step as the walk (one 16-byte field record, one texture value) + the tap FMA, "
+                       "staircase walkers, same image, same launch shape; CUDA events, best of 5, this run",
+            }
+            roofline["frac_of_gather_peak"] = achieved / peak_g
+        except Exception as exc:  # noqa: BLE001 -- a reporting extra
+            roofline["gather_peak"] = {"error": f"{type(exc).__name__}: {exc}"}
+
     # Secondary ceiling: instruction issue.  The pass kernel is
     # issue-bound, not memory-bound: warp instructions per pixel-step
-    # as ncu counted them for this kernel, against 4 issue slots per SM per clock at the SM
-    # clock sampled during the timed region.  Arithmetic on recorded figures only.
+    # as ncu counted them for the kernel of the walk in force, against 4 issue slots per SM per
+    # clock at the SM clock sampled during the timed region.  Arithmetic on recorded figures only.
     try:
-        prof = json.loads((ROOT / "profiles" / "r1_pass_kernel_ncu_summary.json").read_text())
+        walk = rlic_b200.effective_options()["walk"]
+        src = {"per-step": "r1_pass_kernel_ncu_summary.json", "grouped": "r2_pass_kernel_ncu_summary.json"}[walk]
+        prof = json.loads((ROOT / "profiles" / src).read_text())
         ips = float(prof["warp_instructions_per_pixel_step"])
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
         mhz = clocks.summary().get("sm_mhz") or clocks.summary().get("sm_max_mhz")
-        if world == 1 and rlic_b200.get_walk() == "per-step" and mhz:
+        if world == 1 and mhz:
             warp_instr = pixels_local * (TAPS - 1) / 32 * ips
             ceiling_ms = warp_instr / (4 * sms * mhz * 1e6) * 1e3
             roofline["issue"] = {
                 "warp_instructions_per_pixel_step": ips,
-                "source": "profiles/r1_pass_kernel_ncu_summary.json (smsp__inst_executed.sum / pixel-steps)",
+                "source": f"profiles/{src} (smsp__inst_executed.sum / pixel-steps)",
                 "sms": sms, "sm_mhz": mhz, "ceiling_ms": ceiling_ms, "frac": ceiling_ms / pass_avg_ms,
                 "note": "launch time if every issue slot of every SM issued a warp instruction of this kernel",
             }
@@ -498,39 +534,53 @@ def run_ours(args) -> dict:
         e2e_val = pixels_all * ITERATIONS / dt / 1e6
         e2e_ms = dt * 1e3
         assert np.array_equal(out, result.cpu().numpy()), "host and device paths disagree"
+        # the same call as a drop-in user makes it: ordinary (pageable) NumPy arrays
+        p_tex, p_u, p_v = texture.copy(), np.ascontiguousarray(u).copy(), np.ascontiguousarray(v).copy()
+        for _ in range(2):
+            out_p = rlic_b200.convolve(p_tex, p_u, p_v, kernel=kernel, boundaries="closed", iterations=ITERATIONS)
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            out_p = rlic_b200.convolve(p_tex, p_u, p_v, kernel=kernel, boundaries="closed", iterations=ITERATIONS)
+        dt_p = (time.perf_counter() - t0) / n_e2e
+        assert np.array_equal(out_p, out)
+        pageable = {"value": pixels_all * ITERATIONS / dt_p / 1e6, "unit": METRIC, "ms_per_step": dt_p * 1e3,
+                    "api": "rlic_b200.convolve(ordinary pageable numpy arrays)"}
     else:
-        # each rank moves its slab host -> device, runs the sharded passes, reads its slab back
-        pinned_out = torch.empty(texture.shape, dtype=torch.float32).pin_memory()
-        t_u, t_v, t_t = (torch.from_numpy(a) for a in (h_u, h_v, h_tex))
+        # each rank: its slab of texture, u and v from page-locked host memory through
+        # ShardedConvolver.convolve_host (band pipeline: uploads, passes and downloads overlap;
+        # the field is re-packed and its halos re-sent every step, as a convolve(texture, u, v)
+        # call implies) into a page-locked host slab; the call returns when the slab is there
+        from rlic_b200.sharded import pinned_empty
+
+        pinned_out = pinned_empty(texture.shape, np.float32)
 
         def e2e_step():
-            a_u, a_v, a_t = (t.to(dev, non_blocking=True) for t in (t_u, t_v, t_tex_ref[0]))
-            sc.set_field(a_u, a_v)
-            res = sc.convolve(a_t, iterations=ITERATIONS)
-            pinned_out.copy_(res, non_blocking=True)
+            sc.convolve_host(h_tex, h_u, h_v, iterations=ITERATIONS, out=pinned_out)
 
-        t_tex_ref = [t_t]
-        e2e_step()
+        for _ in range(2):
+            e2e_step()
+        assert np.array_equal(pinned_out, result.cpu().numpy()), "host and device paths disagree"
         barrier()
         n_e2e = max(3, min(args.steps, 10))
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
+        t0 = time.perf_counter()
         for _ in range(n_e2e):
             e2e_step()
-        b.record()
+        dt = time.perf_counter() - t0
         barrier()
-        t = torch.tensor([a.elapsed_time(b)], device=dev, dtype=torch.float64)
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = t.item() / n_e2e
+        e2e_ms = t.item() / n_e2e * 1e3
         e2e_val = pixels_all * ITERATIONS / (e2e_ms * 1e-3) / 1e6
     e2e = {"value": e2e_val, "unit": METRIC, "h2d_bytes_per_step": h2d * world,
            "d2h_bytes_per_step": d2h * world, "ms_per_step": e2e_ms,
            "api": "rlic_b200.convolve(numpy arrays in pinned host memory)" if world == 1
-                  else "per rank: pinned host slab -> ShardedConvolver -> pinned host slab",
-           "schedule": rlic_b200.get_schedule(), "arithmetic": rlic_b200.get_arithmetic(),
-           "walk": rlic_b200.get_walk()}
+                  else "per rank: ShardedConvolver.convolve_host(texture, u, v slabs in pinned host memory) "
+                       "-> pinned host slab",
+           **rlic_b200.effective_options()}
     if world > 1:
         e2e["exchange"] = sc.exchange
+    else:
+        e2e["pageable"] = pageable
 
     line = {
         "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps,

@@ -359,6 +359,40 @@ int rlic_b200_slab_unpad_texture_f64(const double *d_padded, int64_t ny, int64_t
                                      int x_left, int x_right, int y_left, int y_right,
                                      double *d_texture, void *stream);
 
+/* Row-range variants: owned rows [sub_row0, sub_row0 + sub_nrows) only; the dense array
+ * holds just those rows (sub_nrows x nx).  With them a slab can be uploaded, converted,
+ * computed and downloaded band by band (rlic_b200/sharded.py: convolve_host). */
+int rlic_b200_slab_pack_field_rows_f32(const float *d_u, const float *d_v, int64_t ny, int64_t nx,
+                                       int64_t row0, int64_t nrows, int64_t halo_lo, int64_t halo_hi,
+                                       int64_t sub_row0, int64_t sub_nrows,
+                                       int x_left, int x_right, int y_left, int y_right,
+                                       float *d_field, void *stream);
+int rlic_b200_slab_pack_field_rows_f64(const double *d_u, const double *d_v, int64_t ny, int64_t nx,
+                                       int64_t row0, int64_t nrows, int64_t halo_lo, int64_t halo_hi,
+                                       int64_t sub_row0, int64_t sub_nrows,
+                                       int x_left, int x_right, int y_left, int y_right,
+                                       double *d_field, void *stream);
+int rlic_b200_slab_pad_texture_rows_f32(const float *d_texture, int64_t ny, int64_t nx,
+                                        int64_t row0, int64_t nrows, int64_t halo_lo, int64_t halo_hi,
+                                        int64_t sub_row0, int64_t sub_nrows,
+                                        int x_left, int x_right, int y_left, int y_right,
+                                        float *d_padded, void *stream);
+int rlic_b200_slab_pad_texture_rows_f64(const double *d_texture, int64_t ny, int64_t nx,
+                                        int64_t row0, int64_t nrows, int64_t halo_lo, int64_t halo_hi,
+                                        int64_t sub_row0, int64_t sub_nrows,
+                                        int x_left, int x_right, int y_left, int y_right,
+                                        double *d_padded, void *stream);
+int rlic_b200_slab_unpad_texture_rows_f32(const float *d_padded, int64_t ny, int64_t nx,
+                                          int64_t row0, int64_t nrows, int64_t halo_lo, int64_t halo_hi,
+                                          int64_t sub_row0, int64_t sub_nrows,
+                                          int x_left, int x_right, int y_left, int y_right,
+                                          float *d_texture, void *stream);
+int rlic_b200_slab_unpad_texture_rows_f64(const double *d_padded, int64_t ny, int64_t nx,
+                                          int64_t row0, int64_t nrows, int64_t halo_lo, int64_t halo_hi,
+                                          int64_t sub_row0, int64_t sub_nrows,
+                                          int x_left, int x_right, int y_left, int y_right,
+                                          double *d_texture, void *stream);
+
 int rlic_b200_pass_slab_f32(const float *d_texture, const float *d_field, float *d_out,
                             int64_t ny, int64_t nx,
                             int64_t row0, int64_t nrows, int64_t halo_lo, int64_t halo_hi,
@@ -375,6 +409,26 @@ int rlic_b200_pass_slab_f64(const double *d_texture, const double *d_field, doub
                             int uv_mode,
                             int x_left, int x_right, int y_left, int y_right,
                             void *stream);
+
+/*
+ * MEASUREMENT — the gather ceiling ("an L2 gather peak measured by the
+ * build's own microbenchmark, same access count, straight-line walkers").  One launch performs
+ * the loads of a pass -- per step one field record and one texture value at the walker's
+ * cell -- and the tap FMA, and nothing else; the walkers climb a staircase (+1 column, +1
+ * row, ...) forward and descend it backward, so neighbouring threads touch neighbouring cells
+ * as walkers on a smooth field do.  `dependent` != 0 makes each address wait for the record
+ * loaded before it, as in the real walk.  Buffers: a padded texture, a packed field and a
+ * padded output of the whole ny x nx image (closed walls), as the slab entry points above
+ * produce them.  The caller times the launch; d_padded_out is NOT a convolution result.
+ */
+int rlic_b200_measure_gather_ceiling_f32(const float *d_padded_texture, const float *d_field,
+                                         float *d_padded_out, int64_t ny, int64_t nx,
+                                         const float *kernel, int64_t klen, int dependent,
+                                         void *stream);
+int rlic_b200_measure_gather_ceiling_f64(const double *d_padded_texture, const double *d_field,
+                                         double *d_padded_out, int64_t ny, int64_t nx,
+                                         const double *kernel, int64_t klen, int dependent,
+                                         void *stream);
 
 /*
  * FUSED HALO EXCHANGE (row-slab sharding, one process per GPU; rlic_b200/sharded.py with

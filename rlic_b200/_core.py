@@ -60,6 +60,10 @@ def _signatures(real) -> dict[str, list]:
         "slab_pack_field": [_vp, _vp, *slab, *walls, _vp, _vp],
         "slab_pad_texture": [_vp, *slab, *walls, _vp, _vp],
         "slab_unpad_texture": [_vp, *slab, *walls, _vp, _vp],
+        "slab_pack_field_rows": [_vp, _vp, *slab, _i64, _i64, *walls, _vp, _vp],
+        "slab_pad_texture_rows": [_vp, *slab, _i64, _i64, *walls, _vp, _vp],
+        "slab_unpad_texture_rows": [_vp, *slab, _i64, _i64, *walls, _vp, _vp],
+        "measure_gather_ceiling": [_vp, _vp, _vp, _i64, _i64, p, _i64, _int, _vp],
         "pass_slab": [_vp, _vp, _vp, *slab, _i64, _i64, p, _i64, _int, *walls, _vp],
         "pass_slab_peer": [_vp, _vp, _vp, *slab, _i64, _i64, p, _i64, _int, *walls, _vp, _i64, _vp],
     }

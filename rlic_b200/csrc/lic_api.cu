@@ -716,15 +716,28 @@ int convolve_packed(const T *d_tex, const T *d_field, int64_t ny, int64_t nx, co
 }
 
 // ---- slab building blocks (padded buffers owned by the caller) ----
+// Owned rows [sub0, sub0 + subn) of a slab (the whole slab: 0, sl.nrows).
+int check_sub_rows(const Slab &sl, int64_t sub0, int64_t subn)
+{
+    if (sub0 < 0 || subn < 0 || sub0 + subn > sl.nrows)
+        return fail(RLIC_B200_ESHARD, "rows [%lld,%lld) outside the slab's %lld rows",
+                    (long long)sub0, (long long)(sub0 + subn), (long long)sl.nrows);
+    return RLIC_B200_OK;
+}
+
 template <typename T>
 int slab_pack_field(const T *d_u, const T *d_v, int64_t ny, int64_t nx, const Slab &sl, const Walls &w,
-                    T *d_field, void *stream)
+                    T *d_field, void *stream, int64_t sub0 = 0, int64_t subn = -1)
 {
+    if (subn < 0)
+        subn = sl.nrows;
     if (int rc = check_common(ny, nx, 1, 0, w))
         return rc;
     if (int rc = check_slab(ny, 1, sl, w))
         return rc;
-    if (sl.nrows == 0 || nx == 0)
+    if (int rc = check_sub_rows(sl, sub0, subn))
+        return rc;
+    if (subn == 0 || nx == 0)
         return RLIC_B200_OK;
     if (!d_u || !d_v || !d_field)
         return fail(RLIC_B200_EINVAL, "null pointer argument");
@@ -733,42 +746,50 @@ int slab_pack_field(const T *d_u, const T *d_v, int64_t ny, int64_t nx, const Sl
     Field<T> *field = reinterpret_cast<Field<T> *>(d_field);
     // owned rows from the planar components, with the sentinels of any image
     // wall they touch; halo rows arrive from the neighbours, already packed
-    CUDA_TRY(launch_pack<T>(d_u, d_v, field, g, sl.halo_lo, sl.halo_lo + sl.nrows, 1, s));
+    CUDA_TRY(launch_pack<T>(d_u, d_v, field, g, sl.halo_lo + sub0, sl.halo_lo + sub0 + subn, 1, s));
     return RLIC_B200_OK;
 }
 
 template <typename T>
 int slab_pad_texture(const T *d_tex, int64_t ny, int64_t nx, const Slab &sl, const Walls &w,
-                     T *d_padded, void *stream)
+                     T *d_padded, void *stream, int64_t sub0 = 0, int64_t subn = -1)
 {
+    if (subn < 0)
+        subn = sl.nrows;
     if (int rc = check_common(ny, nx, 1, 0, w))
         return rc;
     if (int rc = check_slab(ny, 1, sl, w))
         return rc;
-    if (sl.nrows == 0 || nx == 0)
+    if (int rc = check_sub_rows(sl, sub0, subn))
+        return rc;
+    if (subn == 0 || nx == 0)
         return RLIC_B200_OK;
     if (!d_tex || !d_padded)
         return fail(RLIC_B200_EINVAL, "null pointer argument");
     const PassGeom g = make_geometry(ny, nx, sl, w);
-    CUDA_TRY(launch_pad<T>(d_tex, d_padded, g, sl.halo_lo, sl.halo_lo + sl.nrows, 1, nullptr,
+    CUDA_TRY(launch_pad<T>(d_tex, d_padded, g, sl.halo_lo + sub0, sl.halo_lo + sub0 + subn, 1, nullptr,
                            static_cast<cudaStream_t>(stream)));
     return RLIC_B200_OK;
 }
 
 template <typename T>
 int slab_unpad_texture(const T *d_padded, int64_t ny, int64_t nx, const Slab &sl, const Walls &w,
-                       T *d_tex, void *stream)
+                       T *d_tex, void *stream, int64_t sub0 = 0, int64_t subn = -1)
 {
+    if (subn < 0)
+        subn = sl.nrows;
     if (int rc = check_common(ny, nx, 1, 0, w))
         return rc;
     if (int rc = check_slab(ny, 1, sl, w))
         return rc;
-    if (sl.nrows == 0 || nx == 0)
+    if (int rc = check_sub_rows(sl, sub0, subn))
+        return rc;
+    if (subn == 0 || nx == 0)
         return RLIC_B200_OK;
     if (!d_tex || !d_padded)
         return fail(RLIC_B200_EINVAL, "null pointer argument");
     const PassGeom g = make_geometry(ny, nx, sl, w);
-    CUDA_TRY(launch_unpad<T>(d_padded, d_tex, g, sl.halo_lo, sl.halo_lo + sl.nrows, 1,
+    CUDA_TRY(launch_unpad<T>(d_padded, d_tex, g, sl.halo_lo + sub0, sl.halo_lo + sub0 + subn, 1,
                              static_cast<cudaStream_t>(stream)));
     return RLIC_B200_OK;
 }
@@ -782,9 +803,8 @@ int pass_slab(const T *d_tex, const T *d_field, T *d_out, int64_t ny, int64_t nx
         return rc;
     if (int rc = check_slab(ny, klen, sl, w))
         return rc;
-    if (sub0 < 0 || subn < 0 || sub0 + subn > sl.nrows)
-        return fail(RLIC_B200_ESHARD, "rows [%lld,%lld) outside the slab's %lld rows",
-                    (long long)sub0, (long long)(sub0 + subn), (long long)sl.nrows);
+    if (int rc = check_sub_rows(sl, sub0, subn))
+        return rc;
     if (subn == 0 || nx == 0)
         return RLIC_B200_OK;
     if (!d_tex || !d_field || !d_out || !kernel)
@@ -1151,6 +1171,53 @@ int rlic_b200_set_device(int device)
 RLIC_DEFINE(float, f32)
 RLIC_DEFINE(double, f64)
 
+// Row-range variants of the three layout conversions: owned rows [sub_row0, sub_row0 + sub_nrows)
+// only, the dense array holding just those rows.  They let a caller upload, convert, compute
+// and download a slab band by band (rlic_b200/sharded.py: convolve_host).
+#define RLIC_DEFINE_ROWS(T, sfx)                                                                 \
+    int rlic_b200_slab_pack_field_rows_##sfx(const T *d_u, const T *d_v, int64_t ny, int64_t nx, \
+                                             int64_t row0, int64_t nrows, int64_t halo_lo,       \
+                                             int64_t halo_hi, int64_t sub_row0,                  \
+                                             int64_t sub_nrows, int x_left, int x_right,         \
+                                             int y_left, int y_right, T *d_field, void *stream)  \
+    {                                                                                            \
+        tls_error.clear();                                                                       \
+        if (sub_nrows < 0)                                                                       \
+            return fail(RLIC_B200_ESHARD, "negative row count");                                 \
+        return slab_pack_field<T>(d_u, d_v, ny, nx, Slab{row0, nrows, halo_lo, halo_hi},         \
+                                  Walls{x_left, x_right, y_left, y_right}, d_field, stream,      \
+                                  sub_row0, sub_nrows);                                          \
+    }                                                                                            \
+    int rlic_b200_slab_pad_texture_rows_##sfx(const T *d_texture, int64_t ny, int64_t nx,        \
+                                              int64_t row0, int64_t nrows, int64_t halo_lo,      \
+                                              int64_t halo_hi, int64_t sub_row0,                 \
+                                              int64_t sub_nrows, int x_left, int x_right,        \
+                                              int y_left, int y_right, T *d_padded, void *stream) \
+    {                                                                                            \
+        tls_error.clear();                                                                       \
+        if (sub_nrows < 0)                                                                       \
+            return fail(RLIC_B200_ESHARD, "negative row count");                                 \
+        return slab_pad_texture<T>(d_texture, ny, nx, Slab{row0, nrows, halo_lo, halo_hi},       \
+                                   Walls{x_left, x_right, y_left, y_right}, d_padded, stream,    \
+                                   sub_row0, sub_nrows);                                         \
+    }                                                                                            \
+    int rlic_b200_slab_unpad_texture_rows_##sfx(const T *d_padded, int64_t ny, int64_t nx,       \
+                                                int64_t row0, int64_t nrows, int64_t halo_lo,    \
+                                                int64_t halo_hi, int64_t sub_row0,               \
+                                                int64_t sub_nrows, int x_left, int x_right,      \
+                                                int y_left, int y_right, T *d_texture,           \
+                                                void *stream)                                    \
+    {                                                                                            \
+        tls_error.clear();                                                                       \
+        if (sub_nrows < 0)                                                                       \
+            return fail(RLIC_B200_ESHARD, "negative row count");                                 \
+        return slab_unpad_texture<T>(d_padded, ny, nx, Slab{row0, nrows, halo_lo, halo_hi},      \
+                                     Walls{x_left, x_right, y_left, y_right}, d_texture, stream, \
+                                     sub_row0, sub_nrows);                                       \
+    }
+RLIC_DEFINE_ROWS(float, f32)
+RLIC_DEFINE_ROWS(double, f64)
+
 #define RLIC_DEFINE_PEER(T, sfx)                                                                 \
     int rlic_b200_pass_slab_peer_##sfx(const T *d_texture, const T *d_field, T *d_out,           \
                                        int64_t ny, int64_t nx, int64_t row0, int64_t nrows,      \
@@ -1170,6 +1237,48 @@ RLIC_DEFINE(double, f64)
     }
 RLIC_DEFINE_PEER(float, f32)
 RLIC_DEFINE_PEER(double, f64)
+
+// ---- measurement: the gather ceiling of the memory system for the walk's access pattern ----
+// ("an L2 gather peak measured by the build's own microbenchmark, same
+// access count, straight-line walkers").  Launches gather_ceiling_kernel (lic_walk.cuh): the
+// loads and the tap FMA of a pass and nothing else, walkers climbing a staircase.  The caller
+// times it (bench.py: CUDA events) and uses the result as the denominator of the roofline
+// fraction.  Not a convolution: `d_out` receives a checksum-like image nobody should use.
+#define RLIC_DEFINE_CEILING(T, sfx)                                                              \
+    int rlic_b200_measure_gather_ceiling_##sfx(const T *d_padded_texture, const T *d_field,      \
+                                               T *d_padded_out, int64_t ny, int64_t nx,          \
+                                               const T *kernel, int64_t klen, int dependent,     \
+                                               void *stream)                                     \
+    {                                                                                            \
+        tls_error.clear();                                                                       \
+        const Walls w{RLIC_B200_CLOSED, RLIC_B200_CLOSED, RLIC_B200_CLOSED, RLIC_B200_CLOSED};   \
+        if (int rc = check_common(ny, nx, klen, 0, w))                                           \
+            return rc;                                                                           \
+        if (!d_padded_texture || !d_field || !d_padded_out || !kernel || ny == 0 || nx == 0)     \
+            return fail(RLIC_B200_EINVAL, "null pointer or empty image");                        \
+        if (klen > TapSet<T>::kMaxParam || rlic::padded_cells(ny, nx) >= (int64_t)INT_MAX)       \
+            return fail(RLIC_B200_EINVAL, "kernel or image too large for the ceiling probe");    \
+        PassGeom g = make_geometry(ny, nx, Slab{0, ny, 0, 0}, w);                                \
+        g.first_row = 0;                                                                         \
+        g.out_rows = (int)ny;                                                                    \
+        g.tiles_x = (g.nx + 15) / 16;                                                            \
+        g.tiles_per_field = g.tiles_x * (int)((ny + 15) / 16);                                   \
+        cudaStream_t s = static_cast<cudaStream_t>(stream);                                      \
+        TapSet<T> taps;                                                                          \
+        CUDA_TRY(taps.prepare(kernel, klen, s));                                                 \
+        const Field<T> *field = reinterpret_cast<const Field<T> *>(d_field);                     \
+        if (dependent)                                                                           \
+            rlic::gather_ceiling_kernel<T, true><<<g.tiles_per_field, 256, 0, s>>>(              \
+                d_padded_texture, field, d_padded_out, g, taps.param, (int)klen);                \
+        else                                                                                     \
+            rlic::gather_ceiling_kernel<T, false><<<g.tiles_per_field, 256, 0, s>>>(             \
+                d_padded_texture, field, d_padded_out, g, taps.param, (int)klen);                \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                                      \
+        CUDA_TRY(cudaGetLastError());                                                            \
+        return RLIC_B200_OK;                                                                     \
+    }
+RLIC_DEFINE_CEILING(float, f32)
+RLIC_DEFINE_CEILING(double, f64)
 
 // ---- peer memory and flags of the fused halo exchange (one process per GPU) ----
 int rlic_b200_peer_alloc(int64_t bytes, void **ptr, unsigned char *handle)

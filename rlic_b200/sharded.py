@@ -37,7 +37,7 @@ CUDA IPC entry points of the C ABI.  There is no CPU compute path in this packag
 
 from __future__ import annotations
 
-__all__ = ["SlabPlan", "ShardedConvolver", "CudaSlabOps", "CudaPeerMemory"]
+__all__ = ["SlabPlan", "ShardedConvolver", "CudaSlabOps", "CudaPeerMemory", "pinned_empty"]
 
 import ctypes
 from dataclasses import dataclass
@@ -147,28 +147,33 @@ class CudaSlabOps:
         if not t.is_cuda:
             raise RuntimeError("rlic_b200 has no CPU fallback: pass CUDA tensors")
 
-    def pack_field(self, u, v, field, plan, walls):
+    # pack_field / pad_texture / unpad_texture take an optional ``rows=(a, b)``: owned rows
+    # [a, b) only, the dense tensor holding just those rows (the *_rows entry points)
+    def pack_field(self, u, v, field, plan, walls, rows=None):
         from rlic_b200 import _core
 
         self._need_cuda(u)
         sfx, _ = self._kind(u)
-        _core.check(getattr(_core.lib, f"rlic_b200_slab_pack_field_{sfx}")(
-            u.data_ptr(), v.data_ptr(), *plan.slab_args, *walls, field.data_ptr(), self._stream()))
+        a, b = rows if rows is not None else (0, plan.nrows)
+        _core.check(getattr(_core.lib, f"rlic_b200_slab_pack_field_rows_{sfx}")(
+            u.data_ptr(), v.data_ptr(), *plan.slab_args, a, b - a, *walls, field.data_ptr(), self._stream()))
 
-    def pad_texture(self, texture, padded, plan, walls):
+    def pad_texture(self, texture, padded, plan, walls, rows=None):
         from rlic_b200 import _core
 
         self._need_cuda(texture)
         sfx, _ = self._kind(texture)
-        _core.check(getattr(_core.lib, f"rlic_b200_slab_pad_texture_{sfx}")(
-            texture.data_ptr(), *plan.slab_args, *walls, padded.data_ptr(), self._stream()))
+        a, b = rows if rows is not None else (0, plan.nrows)
+        _core.check(getattr(_core.lib, f"rlic_b200_slab_pad_texture_rows_{sfx}")(
+            texture.data_ptr(), *plan.slab_args, a, b - a, *walls, padded.data_ptr(), self._stream()))
 
-    def unpad_texture(self, padded, texture, plan, walls):
+    def unpad_texture(self, padded, texture, plan, walls, rows=None):
         from rlic_b200 import _core
 
         sfx, _ = self._kind(texture)
-        _core.check(getattr(_core.lib, f"rlic_b200_slab_unpad_texture_{sfx}")(
-            padded.data_ptr(), *plan.slab_args, *walls, texture.data_ptr(), self._stream()))
+        a, b = rows if rows is not None else (0, plan.nrows)
+        _core.check(getattr(_core.lib, f"rlic_b200_slab_unpad_texture_rows_{sfx}")(
+            padded.data_ptr(), *plan.slab_args, a, b - a, *walls, texture.data_ptr(), self._stream()))
 
     def pass_rows(self, src, field, dst, plan, a, b, taps, mode, walls):
         from rlic_b200 import _core
@@ -250,33 +255,42 @@ class CudaPeerMemory:
         return torch.as_tensor(_DevicePointer(ptr, count, self._TYPESTR[dtype]), device=device)
 
 
+def pinned_empty(shape, dtype) -> np.ndarray:
+    """A page-locked NumPy array (what ``convolve_host`` copies asynchronously from and to)."""
+    t = torch.empty(tuple(shape), dtype=torch.from_numpy(np.empty(0, dtype=dtype)).dtype, pin_memory=True)
+    return t.numpy()
+
+
 # counters in a rank's flag block, raised by its neighbours (int32 each)
 _HALO_FROM_UP, _HALO_FROM_DOWN, _FREE_FROM_UP, _FREE_FROM_DOWN, _TIMED_OUT, _NFLAGS = 0, 1, 2, 3, 4, 8
 
 
 class _PeerExchange:
-    """One rank's side of the fused halo exchange: its two padded texture buffers and its flag
-    block in memory the neighbours can map, and the neighbours' mapped into this process."""
+    """One rank's side of the fused halo exchange: its two padded texture buffers, its packed
+    field and its flag block in memory the neighbours can map, and the neighbours' mapped
+    into this process."""
 
     def __init__(self, plan: SlabPlan, group, peers, dtype, device):
         self.plan, self.peers = plan, peers
         itemsize = torch.empty((), dtype=dtype).element_size()
         self._own = []                                   # (ptr, handle) of this rank's allocations
-        for nbytes in (plan.cells * itemsize, plan.cells * itemsize, 4 * _NFLAGS):
+        for nbytes in (plan.cells * itemsize, plan.cells * itemsize, 4 * _NFLAGS, 4 * plan.cells * itemsize):
             self._own.append(peers.alloc(nbytes))
         self.bufs = [peers.view(self._own[i][0], plan.cells, dtype, device) for i in (0, 1)]
         self.flags = peers.view(self._own[2][0], _NFLAGS, torch.int32, device)
+        self.field = peers.view(self._own[3][0], 4 * plan.cells, dtype, device)   # 4 scalars per cell
         handles = [None] * plan.world
         dist.all_gather_object(handles, [h for _, h in self._own], group=group)
-        self._opened = {}                                # rank -> [ptr, ptr, ptr]
-        self.remote = {}                                 # rank -> (bufs, flags, that rank's plan)
+        self._opened = {}                                # rank -> [ptr, ...]
+        self.remote = {}                                 # rank -> (bufs, flags, that rank's plan, field)
         for rank in {plan.up, plan.down} - {None}:
             ptrs = [peers.open(h) for h in handles[rank]]
             self._opened[rank] = ptrs
             theirs = SlabPlan(ny=plan.ny, nx=plan.nx, world=plan.world, rank=rank, reach=plan.reach,
                               periodic_y=plan.periodic_y)
             self.remote[rank] = ([peers.view(ptrs[i], theirs.cells, dtype, device) for i in (0, 1)],
-                                 peers.view(ptrs[2], _NFLAGS, torch.int32, device), theirs)
+                                 peers.view(ptrs[2], _NFLAGS, torch.int32, device), theirs,
+                                 peers.view(ptrs[3], 4 * theirs.cells, dtype, device))
         # where my edge strips land: my top rows in the upper neighbour's high halo, my
         # bottom rows in the lower neighbour's low halo (buffer rows, theirs minus mine)
         self.delta_up = self.delta_down = 0
@@ -296,7 +310,7 @@ class _PeerExchange:
                 self.peers.close(ptr)
         self._opened = {}
         dist.barrier(group=group)                        # every mapping is gone before memory is freed
-        self.bufs, self.flags = [], None
+        self.bufs, self.flags, self.field = [], None, None
         for ptr, _ in self._own:
             self.peers.free(ptr)
         self._own = []
@@ -310,6 +324,9 @@ class ShardedConvolver:
     """
 
     PEER_TIMEOUT_MS = 20_000      # a wait for a neighbour gives up after this long (and says so)
+    # read the "a wait gave up" flag back after every call with exchange="peer" and raise if it
+    # is set (one 4-byte device-to-host read, i.e. one synchronisation per call)
+    check_peer_timeouts = True
 
     def __init__(self, ny: int, nx: int, *, kernel, uv_mode: str = "velocity",
                  boundaries="closed", group=None, ops=None, exchange: str = "nccl", peers=None):
@@ -344,6 +361,9 @@ class ShardedConvolver:
         self.exchange = exchange if self.world > 1 else "nccl"
         self._peer_memory = peers
         self._peer = None            # _PeerExchange, built on the first convolve (needs dtype and device)
+        self._work = None            # ((dtype, device), padded buffer, padded buffer) of the NCCL path
+        self._staging = None         # ((dtype, device), dense texture, u, v) of convolve_host
+        self._host_streams = None    # (upload stream, download stream) of convolve_host
 
     # -- halo plumbing ------------------------------------------------------
     @staticmethod
@@ -394,10 +414,25 @@ class ShardedConvolver:
         if tuple(u.shape) != (p.nrows, p.nx) or tuple(v.shape) != (p.nrows, p.nx):
             raise ValueError(f"expected this rank's slab of shape {(p.nrows, p.nx)}")
         width, planes = self.field_layout(u.dtype)
-        field = self._alloc(u, width * planes)
+        if self.exchange == "peer":
+            # in memory the neighbours can map: convolve_host pushes its halos there
+            field = self._peer_exchange(u.dtype, u.device).field
+        elif (self.field is not None and self.field.dtype == u.dtype and self.field.device == u.device
+              and self.field.numel() == p.cells * width * planes):
+            field = self.field       # every reachable cell is rewritten by the pack and the exchange
+        else:
+            field = self._alloc(u, width * planes)
         self.ops.pack_field(u.contiguous(), v.contiguous(), field, p, self.walls)
         self._exchange(field, width, planes)
         self.field = field
+
+    def _peer_exchange(self, dtype, device) -> "_PeerExchange":
+        if self._peer is None:
+            self._peer = _PeerExchange(self.plan, self.group, self._peer_memory or CudaPeerMemory(),
+                                       dtype, device)
+        if self._peer.bufs[0].dtype != dtype:
+            raise TypeError("the peer buffers of this convolver hold another dtype")
+        return self._peer
 
     def _pass_rows(self, src, dst, a: int, b: int) -> None:
         """Compute owned rows [a, b) of ``dst`` from ``src``."""
@@ -415,8 +450,12 @@ class ShardedConvolver:
             return texture.clone()
         if self.exchange == "peer":
             return self._convolve_peer(texture, iterations)
-        src = self._alloc(texture)
-        dst = self._alloc(texture)
+        # the two padded work buffers live as long as the convolver (zero-filled once: wall
+        # cells nobody can reach are never written, every other cell is rewritten by each call)
+        key = (texture.dtype, texture.device)
+        if self._work is None or self._work[0] != key:
+            self._work = (key, self._alloc(texture), self._alloc(texture))
+        src, dst = self._work[1], self._work[2]
         self.ops.pad_texture(texture.contiguous(), src, p, self.walls)
         self._exchange(src)
         h = p.reach
@@ -459,67 +498,270 @@ class ShardedConvolver:
 
     # -- fused halo exchange --------------------------------------------------
     def _convolve_peer(self, texture: torch.Tensor, iterations: int) -> torch.Tensor:
-        """``convolve`` with ``exchange="peer"``: see the module docstring.  Per pass n (tick t):
+        """``convolve`` with ``exchange="peer"``: see the module docstring.  No message-passing
+        library is involved once the buffers are mapped: everything below is kernels and
+        device-to-device copies on the current stream, ordered across ranks by two counters
+        per neighbour that live in the consumer's memory.
 
-            wait   free >= t - 1 from both neighbours      (their pass n - 1 is over: the buffer
-                                                             my strips are about to land in is idle)
-            strips pass over the two edge strips, stored here AND in the neighbours' halos
-            signal halo = t to both neighbours
-            pass   over the interior
-            signal free = t to both neighbours              (my pass n is over)
-            wait   halo >= t from both neighbours           (their strips are in my halos)
+        One number line serves both counters.  A call that starts at count ``c`` and runs ``n``
+        passes (pass ``k`` reads X[k-1] in ``bufs[(k-1) % 2]`` and writes X[k] into
+        ``bufs[k % 2]``; X[0] is the padded texture) uses ``c + 1 .. c + n + 1``:
 
-        all on the current stream, none of it involving the host.  The first input's halos
-        travel by the ordinary exchange, which also tells each rank that its neighbours have
-        finished the previous call."""
-        p, h = self.plan, self.plan.reach
-        if self._peer is None:
-            self._peer = _PeerExchange(p, self.group, self._peer_memory or CudaPeerMemory(),
-                                       texture.dtype, texture.device)
-        px = self._peer
-        if px.bufs[0].dtype != texture.dtype:
-            raise TypeError("the peer buffers of this convolver hold another dtype")
-        bufs, flags = px.bufs, px.flags
+            halo = c + k + 1   "the halo rows of X[k] are in your buffer"  (k = 0 .. n-1;
+                               k = 0 is pushed by a copy, the others by the fused strips)
+            free = c + k       "my pass k is over" (k = 1 .. n), and free = c + n + 1
+                               "my un-padding is over: this call no longer reads anything"
+
+        X[k]'s halos land in the neighbour's ``bufs[k % 2]``, which it last read during its
+        pass k - 1 (k >= 2) or during its previous call (k = 0, 1): they may be stored once
+        ``free >= c + max(k - 1, 0)`` -- the previous call ended at exactly ``c``.  Pass k
+        needs the halos of X[k-1]: ``halo >= c + k``.  Strips go first, so in the steady
+        state every wait finds its counter already raised."""
+        p = self.plan
+        px = self._peer_exchange(texture.dtype, texture.device)
+        self.ops.pad_texture(texture.contiguous(), px.bufs[0], p, self.walls)
+        self._peer_passes(px, iterations)
+        out = torch.empty_like(texture)
+        self.ops.unpad_texture(px.bufs[iterations % 2], out, p, self.walls)
+        self._peer_finish(px, iterations)
+        return out
+
+    def _peer_signals(self, px):
+        p, flags, limit = self.plan, px.flags, self.PEER_TIMEOUT_MS
         up = px.remote.get(p.up) if p.up is not None else None
         down = px.remote.get(p.down) if p.down is not None else None
-        self.ops.pad_texture(texture.contiguous(), bufs[0], p, self.walls)
-        self._exchange(bufs[0])
-        base, limit = px.tick, self.PEER_TIMEOUT_MS
-        for it in range(iterations):
-            t = base + it + 1
-            src, dst = bufs[it % 2], bufs[(it + 1) % 2]
-            if it == iterations - 1:
-                self._pass_rows(src, dst, 0, p.nrows)
+
+        def wait(which_up, which_down, value):
+            if up is not None:
+                self.ops.wait(flags, which_up, value, limit, _TIMED_OUT)
+            if down is not None:
+                self.ops.wait(flags, which_down, value, limit, _TIMED_OUT)
+
+        def signal(which_at_up, which_at_down, value):
+            # my upper neighbour sees me below it, my lower neighbour sees me above it
+            if up is not None:
+                self.ops.signal(up[1], which_at_up, value)
+            if down is not None:
+                self.ops.signal(down[1], which_at_down, value)
+
+        return up, down, wait, signal
+
+    def _peer_passes(self, px, n: int, *, push_field: bool = False, rows_runner=None) -> None:
+        """The passes of one call under the counter protocol (see ``_convolve_peer``), on the
+        current stream.  On entry the edge rows of X[0] in ``px.bufs[0]`` (and, with
+        ``push_field``, of the packed field) are ready in stream order; on return X[n] is in
+        ``px.bufs[n % 2]``.  ``rows_runner(k, src, dst, a, b)`` computes owned rows [a, b) of
+        pass k (default: one launch); the host path cuts them into bands there."""
+        p, h = self.plan, self.plan.reach
+        bufs = px.bufs
+        up, down, wait, signal = self._peer_signals(px)
+        c = px.tick
+        lo, rows = p.halo_lo, p.nrows
+        if rows_runner is None:
+            def rows_runner(k, src, dst, a, b):
+                self._pass_rows(src, dst, a, b)
+
+        def push(theirs, mine, delta_rows, a, b, width=1, planes=1, their_cells=0):
+            """buffer rows [a, b) of `mine`, with their wall cells, into `theirs` delta_rows away"""
+            cells = p.row_cells(a, b)
+            shift = delta_rows * p.pitch
+            for plane in range(planes):
+                s0, d0 = plane * p.cells, plane * their_cells
+                theirs[(d0 + cells.start + shift) * width:(d0 + cells.stop + shift) * width].copy_(
+                    mine[(s0 + cells.start) * width:(s0 + cells.stop) * width])
+
+        # X[0]'s halos: my edge rows copied into the neighbours' bufs[0] (and field)
+        wait(_FREE_FROM_UP, _FREE_FROM_DOWN, c)
+        width, planes = self.field_layout(bufs[0].dtype)
+        if up is not None:
+            push(up[0][0], bufs[0], px.delta_up, lo, lo + h)
+            if push_field:
+                push(up[3], px.field, px.delta_up, lo, lo + h, width, planes, up[2].cells)
+        if down is not None:
+            push(down[0][0], bufs[0], px.delta_down, lo + rows - h, lo + rows)
+            if push_field:
+                push(down[3], px.field, px.delta_down, lo + rows - h, lo + rows, width, planes, down[2].cells)
+        signal(_HALO_FROM_DOWN, _HALO_FROM_UP, c + 1)
+        for k in range(1, n + 1):
+            src, dst = bufs[(k - 1) % 2], bufs[k % 2]
+            wait(_HALO_FROM_UP, _HALO_FROM_DOWN, c + k)
+            if k == n:
+                rows_runner(k, src, dst, 0, rows)
                 break
-            if it > 0:
-                if up is not None:
-                    self.ops.wait(flags, _FREE_FROM_UP, t - 1, limit, _TIMED_OUT)
-                if down is not None:
-                    self.ops.wait(flags, _FREE_FROM_DOWN, t - 1, limit, _TIMED_OUT)
+            if k >= 2:
+                wait(_FREE_FROM_UP, _FREE_FROM_DOWN, c + k - 1)
             if up is not None:
                 self.ops.pass_rows_peer(src, self.field, dst, p, 0, h, self.taps, self.mode, self.walls,
-                                        up[0][(it + 1) % 2], px.delta_up)
+                                        up[0][k % 2], px.delta_up)
             else:
                 self._pass_rows(src, dst, 0, h)
             if down is not None:
-                self.ops.pass_rows_peer(src, self.field, dst, p, p.nrows - h, p.nrows, self.taps, self.mode,
-                                        self.walls, down[0][(it + 1) % 2], px.delta_down)
+                self.ops.pass_rows_peer(src, self.field, dst, p, rows - h, rows, self.taps, self.mode,
+                                        self.walls, down[0][k % 2], px.delta_down)
             else:
-                self._pass_rows(src, dst, p.nrows - h, p.nrows)
-            if up is not None:
-                self.ops.signal(up[1], _HALO_FROM_DOWN, t)
-            if down is not None:
-                self.ops.signal(down[1], _HALO_FROM_UP, t)
-            self._pass_rows(src, dst, h, p.nrows - h)
-            if up is not None:
-                self.ops.signal(up[1], _FREE_FROM_DOWN, t)
-                self.ops.wait(flags, _HALO_FROM_UP, t, limit, _TIMED_OUT)
-            if down is not None:
-                self.ops.signal(down[1], _FREE_FROM_UP, t)
-                self.ops.wait(flags, _HALO_FROM_DOWN, t, limit, _TIMED_OUT)
-        px.tick = base + iterations
-        out = torch.empty_like(texture)
-        self.ops.unpad_texture(bufs[iterations % 2], out, p, self.walls)
+                self._pass_rows(src, dst, rows - h, rows)
+            signal(_HALO_FROM_DOWN, _HALO_FROM_UP, c + k + 1)
+            rows_runner(k, src, dst, h, rows - h)
+            signal(_FREE_FROM_DOWN, _FREE_FROM_UP, c + k)
+
+    def _peer_finish(self, px, n: int) -> None:
+        """After the last read of this call's buffers (the un-padding) has been enqueued on the
+        current stream: tell the neighbours, advance the count, and refuse to return a result
+        that was computed from stale halos."""
+        _, _, _, signal = self._peer_signals(px)
+        signal(_FREE_FROM_DOWN, _FREE_FROM_UP, px.tick + n + 1)
+        px.tick += n + 1
+        if self.check_peer_timeouts and self.peer_timed_out():
+            px.flags[_TIMED_OUT] = 0
+            raise RuntimeError(
+                f"rank {self.plan.rank}: a neighbour did not answer within {self.PEER_TIMEOUT_MS} ms during "
+                "the fused halo exchange; the result of this call is invalid")
+
+    # -- host slabs in, host slabs out ------------------------------------------
+    def convolve_host(self, texture, u=None, v=None, *, iterations: int = 1, out=None, device=None,
+                      max_bands: int = 8, min_band_pixels: int = 1 << 21, min_band_rows: int = 64):
+        """This rank's slab from HOST memory to host memory: ``texture`` (and, when given, ``u``
+        and ``v``: the field is re-packed; otherwise the one ``set_field`` left is used) are
+        NumPy arrays of this rank's rows, ``out`` a NumPy array to fill (allocated page-locked
+        if omitted).  Page-locked inputs (``pinned_empty``) are copied asynchronously.
+
+        With ``exchange="peer"`` the call is a pipeline over row bands, like the single-GPU
+        host path (``convolve_host`` in lic_api.cu): an upload stream brings the bands in --
+        the two edge bands first, so that the halos can leave for the neighbours at once --
+        and converts each to the padded layout; pass 1 trails behind it band by band; the last
+        pass hands each band to a download stream as soon as it is done.  Halo rows of the
+        texture AND of the re-packed field travel by peer copies under the same counters as
+        the device path.  Otherwise (NCCL exchange, one rank) the three steps run one after
+        the other."""
+        import contextlib
+
+        p, h = self.plan, self.plan.reach
+        t_tex = torch.from_numpy(np.ascontiguousarray(texture))
+        if tuple(t_tex.shape) != (p.nrows, p.nx):
+            raise ValueError(f"expected this rank's slab of shape {(p.nrows, p.nx)}")
+        if (u is None) != (v is None):
+            raise ValueError("pass both u and v, or neither")
+        t_u = torch.from_numpy(np.ascontiguousarray(u)) if u is not None else None
+        t_v = torch.from_numpy(np.ascontiguousarray(v)) if v is not None else None
+        if t_u is not None and (t_u.shape != t_tex.shape or t_v.shape != t_tex.shape or t_u.dtype != t_tex.dtype
+                                or t_v.dtype != t_tex.dtype):
+            raise ValueError("u and v must have the texture's shape and dtype")
+        if out is None:
+            out = pinned_empty(t_tex.shape, texture.dtype) if torch.cuda.is_available() else np.empty_like(texture)
+        t_out = torch.from_numpy(out)
+        if t_out.shape != t_tex.shape or t_out.dtype != t_tex.dtype or not t_out.is_contiguous():
+            raise ValueError("out must be a C-contiguous array of the texture's shape and dtype")
+        if iterations <= 0:
+            t_out.copy_(t_tex)
+            return out
+        if device is None:
+            device = (torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available()
+                      else torch.device("cpu"))
+        cuda = device.type == "cuda"
+        if t_u is None and self.field is None:
+            raise RuntimeError("call set_field(u, v) first, or pass u and v")
+
+        key = (t_tex.dtype, device)
+        if self._staging is None or self._staging[0] != key:
+            dense = lambda: torch.empty(t_tex.shape, dtype=t_tex.dtype, device=device)  # noqa: E731
+            self._staging = (key, dense(), dense(), dense())
+        _, s_t, s_u, s_v = self._staging
+
+        if self.exchange != "peer" or p.world == 1:
+            s_t.copy_(t_tex, non_blocking=True)
+            if t_u is not None:
+                s_u.copy_(t_u, non_blocking=True)
+                s_v.copy_(t_v, non_blocking=True)
+                self.set_field(s_u, s_v)
+            res = self.convolve(s_t, iterations=iterations)
+            t_out.copy_(res, non_blocking=True)
+            if cuda:
+                torch.cuda.current_stream(device).synchronize()
+            return out
+
+        px = self._peer_exchange(t_tex.dtype, device)
+        if t_u is not None:
+            self.field = px.field
+        n, rows = iterations, p.nrows
+        # row bands: multiples of the tile height, at least two kernel half-widths tall
+        # (the last band takes the remainder, so no band is shorter than that)
+        nb = max(1, min(max_bands, rows * p.nx // max(min_band_pixels, 1), rows // max(2 * h, min_band_rows, 16)))
+        band_rows = -(-(-(-rows // nb)) // 16) * 16
+        band_rows = max(band_rows, 2 * h, 16)
+        nb = max(1, rows // band_rows)
+        edge = [b * band_rows for b in range(nb)] + [rows]
+        if cuda:
+            main = torch.cuda.current_stream(device)
+            if self._host_streams is None:
+                self._host_streams = (torch.cuda.Stream(device=device), torch.cuda.Stream(device=device))
+            io, back = self._host_streams
+            on = torch.cuda.stream
+            # the previous call's passes and downloads are done with what the uploads overwrite
+            io.wait_stream(main)
+            io.wait_stream(back)
+        else:
+            main = io = back = None
+            on = lambda _stream: contextlib.nullcontext()  # noqa: E731
+
+        def record(stream):
+            if not cuda:
+                return None
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            return ev
+
+        def after(stream, ev):
+            if cuda and ev is not None:
+                stream.wait_event(ev)
+
+        # ---- uploads: the edge bands first (their rows are the neighbours' halos)
+        uploaded = {}
+        with on(io):
+            for b in dict.fromkeys([0, nb - 1, *range(1, nb - 1)]):
+                a, e = edge[b], edge[b + 1]
+                if t_u is not None:
+                    s_u[a:e].copy_(t_u[a:e], non_blocking=True)
+                    s_v[a:e].copy_(t_v[a:e], non_blocking=True)
+                    self.ops.pack_field(s_u[a:e], s_v[a:e], px.field, p, self.walls, rows=(a, e))
+                s_t[a:e].copy_(t_tex[a:e], non_blocking=True)
+                self.ops.pad_texture(s_t[a:e], px.bufs[0], p, self.walls, rows=(a, e))
+                uploaded[b] = record(io)
+
+        # ---- passes: pass 1 trails the uploads, the last pass releases bands to the download
+        done = {}
+
+        def rows_runner(k, src, dst, a, e):
+            if k != 1 and k != n:
+                self._pass_rows(src, dst, a, e)
+                return
+            for b in range(nb):
+                lo_, hi_ = max(a, edge[b]), min(e, edge[b + 1])
+                if k == 1:      # rows a walker of this band can reach must have arrived
+                    for nbr in (b - 1, b, b + 1):
+                        if 0 <= nbr < nb:
+                            after(main, uploaded[nbr])
+                if hi_ > lo_:
+                    self._pass_rows(src, dst, lo_, hi_)
+                if k == n:
+                    done[b] = record(main)
+
+        after(main, uploaded[0])
+        after(main, uploaded[nb - 1])
+        self._peer_passes(px, n, push_field=t_u is not None, rows_runner=rows_runner)
+
+        # ---- downloads, band by band behind the last pass
+        with on(back):
+            for b in range(nb):
+                a, e = edge[b], edge[b + 1]
+                after(back, done[b])
+                self.ops.unpad_texture(px.bufs[n % 2], s_t[a:e], p, self.walls, rows=(a, e))
+                t_out[a:e].copy_(s_t[a:e], non_blocking=True)
+            finished = record(back)
+        # the counters are raised on the stream that made the last read of this call's buffers
+        after(main, finished)
+        self._peer_finish(px, n)
+        if cuda:
+            back.synchronize()
         return out
 
     def peer_timed_out(self) -> bool:

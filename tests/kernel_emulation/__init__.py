@@ -114,26 +114,31 @@ class SlabOps:
     def _geom(plan, walls, klen=1):
         return geometry(plan.ny, plan.nx, (plan.row0, plan.nrows, plan.halo_lo, plan.halo_hi), walls, klen)
 
-    def pack_field(self, u, v, field, plan, walls):
+    # rows=(a, b): owned rows [a, b) only, the dense tensor holding just those rows
+    # (the rlic_b200_slab_*_rows_* entry points)
+    def pack_field(self, u, v, field, plan, walls, rows=None):
         sfx, real = _kind(self._np(u).dtype)
         g = self._geom(plan, walls)
+        a, b = rows if rows is not None else (0, plan.nrows)
         getattr(lib(), f"emu_pack_field_{sfx}")(
             _ptr(self._np(u), real), _ptr(self._np(v), real), _ptr(self._np(field), real), _ptr(g, _i64),
-            plan.halo_lo, plan.halo_lo + plan.nrows, 1)
+            plan.halo_lo + a, plan.halo_lo + b, 1)
 
-    def pad_texture(self, texture, padded, plan, walls):
+    def pad_texture(self, texture, padded, plan, walls, rows=None):
         sfx, real = _kind(self._np(texture).dtype)
         g = self._geom(plan, walls)
+        a, b = rows if rows is not None else (0, plan.nrows)
         getattr(lib(), f"emu_pad_texture_{sfx}")(
             _ptr(self._np(texture), real), _ptr(self._np(padded), real), _ptr(g, _i64),
-            plan.halo_lo, plan.halo_lo + plan.nrows, 1, None)
+            plan.halo_lo + a, plan.halo_lo + b, 1, None)
 
-    def unpad_texture(self, padded, texture, plan, walls):
+    def unpad_texture(self, padded, texture, plan, walls, rows=None):
         sfx, real = _kind(self._np(texture).dtype)
         g = self._geom(plan, walls)
+        a, b = rows if rows is not None else (0, plan.nrows)
         getattr(lib(), f"emu_unpad_texture_{sfx}")(
             _ptr(self._np(padded), real), _ptr(self._np(texture), real), _ptr(g, _i64),
-            plan.halo_lo, plan.halo_lo + plan.nrows, 1)
+            plan.halo_lo + a, plan.halo_lo + b, 1)
 
     def pass_rows(self, src, field, dst, plan, a, b, taps, mode, walls):
         sfx, real = _kind(self._np(src).dtype)

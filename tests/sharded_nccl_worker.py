@@ -43,6 +43,15 @@ def main() -> None:
             want = convolve_device(*(torch.from_numpy(a).to(dev) for a in (tex, u, v)), kernel=kernel,
                                    uv_mode=mode, boundaries=bnd, iterations=4)
             ok &= bool(torch.equal(got, want[mine]))
+        # host slabs in, host slabs out (with exchange="peer": the band pipeline on three
+        # streams, halos of texture and field by peer copies); then the same field, new texture
+        host = sc.convolve_host(tex[mine], u[mine], v[mine], iterations=4, min_band_pixels=1)
+        ok &= bool(np.array_equal(host, want[mine].cpu().numpy()))
+        tex2 = rng.random((ny, nx), dtype=np.float32)
+        host2 = sc.convolve_host(tex2[mine], iterations=3, min_band_pixels=1)
+        want2 = convolve_device(*(torch.from_numpy(a).to(dev) for a in (tex2, u, v)), kernel=kernel,
+                                uv_mode=mode, boundaries=bnd, iterations=3)
+        ok &= bool(np.array_equal(host2, want2[mine].cpu().numpy()))
         if exchange == "peer":
             ok &= not sc.peer_timed_out()
             sc.close()

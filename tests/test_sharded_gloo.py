@@ -341,6 +341,87 @@ def test_fused_peer_exchange_equals_unsharded(name, ops_kind):
     assert all(payload), f"ranks with mismatching slabs: {payload}"
 
 
+def _host_worker(rank, world, port, case, queue, exchange):
+    """ShardedConvolver.convolve_host: host slab in, host slab out.  With exchange="peer" this is
+    the band pipeline (uploads, pass 1 trailing them, downloads behind the last pass, halos of
+    texture and field by peer copies), run here in program order on the emulated kernels."""
+    try:
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        import oracle
+        from rlic_b200.sharded import ShardedConvolver
+
+        ny, nx, klen, boundaries, mode, iterations, dtype = case
+        rng = np.random.default_rng(17)
+        kernel = (rng.random(klen) + 0.1).astype(dtype)
+        sc = ShardedConvolver(ny, nx, kernel=kernel, uv_mode=mode, boundaries=boundaries,
+                              ops=_make_ops("emulated kernels"), exchange=exchange,
+                              peers=SharedMemoryPeers() if exchange == "peer" else None)
+        mine = slice(sc.plan.row0, sc.plan.row1)
+        bs_y = boundaries["y"] if isinstance(boundaries, dict) else boundaries
+        bs_x = boundaries["x"] if isinstance(boundaries, dict) else boundaries
+        ok = True
+        # three calls on one convolver: new field + texture, same field + new texture (u, v
+        # omitted), and a new field again with another iteration count
+        for call, (with_field, its) in enumerate(((True, iterations), (False, iterations), (True, 1))):
+            tex = rng.random((ny, nx)).astype(dtype)
+            if with_field:
+                u = (rng.random((ny, nx)) - 0.5).astype(dtype)
+                v = (rng.random((ny, nx)) - 0.5).astype(dtype)
+                u[ny // 2, 3] = np.nan
+                v[1, 1] = u[1, 1] = 0.0
+            got = sc.convolve_host(tex[mine], u[mine] if with_field else None, v[mine] if with_field else None,
+                                   iterations=its, min_band_pixels=1, min_band_rows=16)
+            want = oracle.convolve(tex, u, v, kernel=kernel, uv_mode=mode,
+                                   boundaries=((bs_x, bs_x), (bs_y, bs_y)), iterations=its)
+            ok &= bool(np.array_equal(got, want[mine], equal_nan=True))
+        if exchange == "peer":
+            assert not sc.peer_timed_out(), "a wait for a neighbour gave up"
+            sc.close()
+        gathered = [None] * world
+        dist.all_gather_object(gathered, bool(ok))
+        if rank == 0:
+            queue.put(("ok", gathered))
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:
+        queue.put(("error", f"rank {rank}:\n{traceback.format_exc()}"))
+        raise
+
+
+HOST_CASES = {
+    # slabs of 96 / 112 rows cut into bands of 16 and 32 rows
+    "closed-2": (2, (192, 23, 9, "closed", "velocity", 4, np.float32)),
+    "periodic-ring-2": (2, (224, 17, 11, "periodic", "polarization", 3, np.float64)),
+    "x-periodic-3-uneven": (3, (301, 19, 13, {"x": "periodic", "y": "closed"}, "velocity", 2, np.float32)),
+    "y-periodic-3": (3, (288, 20, 7, {"x": "closed", "y": "periodic"}, "velocity", 5, np.float64)),
+}
+
+
+@pytest.mark.parametrize("exchange", ["peer", "nccl"])
+@pytest.mark.parametrize("name", HOST_CASES)
+def test_host_slabs_in_host_slabs_out(name, exchange):
+    if exchange == "nccl" and name not in ("closed-2", "y-periodic-3"):
+        pytest.skip("the unpipelined path is covered by two cases")
+    world, case = HOST_CASES[name]
+    ctx = mp.get_context("spawn")
+    queue = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_host_worker, args=(r, world, port, case, queue, exchange)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    try:
+        status, payload = queue.get(timeout=180)
+    finally:
+        for pr in procs:
+            pr.join(timeout=60)
+            if pr.is_alive():
+                pr.terminate()
+    assert status == "ok", payload
+    assert all(payload), f"ranks with mismatching slabs: {payload}"
+
+
 def test_peer_exchange_rejects_unknown_modes_and_needs_neighbours():
     import torch.distributed as dist
 

@@ -214,3 +214,30 @@ def test_two_gpu_fused_peer_exchange():
         capture_output=True, text=True, env=env, timeout=300)
     assert proc.returncode == 0, proc.stdout[-3000:] + proc.stderr[-3000:]
     assert "SHARDED_OK" in proc.stdout
+
+
+def test_batch_over_every_visible_device_with_pageable_inputs():
+    """rlic_b200_convolve_batch_* with devices=NULL: whole fields split over all visible GPUs,
+    two host lanes per device, pageable inputs of 1 MiB per field staged through the pinned
+    pools (one pool per device: an event of one device cannot be recorded on another's stream).
+    Every field equals its own single-image convolve."""
+    rng = np.random.default_rng(21)
+    nf = 4 * max(1, _core.device_count()) + 1
+    tex = rng.random((nf, 512, 512), dtype=np.float32)
+    u = rng.random((nf, 512, 512), dtype=np.float32) - 0.5
+    v = rng.random((nf, 512, 512), dtype=np.float32) - 0.5
+    kernel = np.linspace(0.1, 1.0, 33, dtype=np.float32)
+    import rlic_b200
+
+    got = rlic_b200.convolve_batch(tex, u, v, kernel=kernel, boundaries="closed", iterations=3)
+    for f in sorted({0, 1, nf // 2, nf - 1}):
+        want = oracle.convolve(tex[f], u[f], v[f], kernel=kernel, iterations=3, threads=oracle.max_threads())
+        np.testing.assert_array_equal(got[f], want)
+    # and field by field on every device in turn through the single-image host entry
+    for d in range(_core.device_count()):
+        _core.check(_core.lib.rlic_b200_set_device(d))
+        try:
+            one = rlic_b200.convolve(tex[d % nf], u[d % nf], v[d % nf], kernel=kernel, iterations=3)
+        finally:
+            _core.check(_core.lib.rlic_b200_set_device(0))
+        np.testing.assert_array_equal(one, got[d % nf])

@@ -153,54 +153,8 @@ persistent_pass_kernel(const T *__restrict__ tex, const PackedField<T> *__restri
     }
 }
 
-// Gather ceiling ("an L2 gather peak measured by the build's own
-// microbenchmark, same access count, straight-line walkers").  The same loads as the walk
-// -- per step one 16-byte (f32) / two 16-byte (f64) field gathers and one texture gather at
-// the walker's cell, one tap FMA -- and nothing else: the walker climbs a staircase
-// (+1 column, +1 row, +1 column, ...) forward and descends it backward, so neighbouring
-// threads touch neighbouring cells exactly as walkers on a smooth field do.  DEPENDENT
-// makes the next address wait for the loaded record, as it does in the real walk.
-// Pixels closer than ntaps/2 to the right or bottom edge (or left / top, backward) stay put.
-template <typename T, bool DEPENDENT>
-__global__ void __launch_bounds__(256, 8)
-gather_ceiling_kernel(const T *__restrict__ tex, const PackedField<T> *__restrict__ field,
-                      T *__restrict__ out, const __grid_constant__ PassGeom g,
-                      const __grid_constant__ rlic::ParamTaps<T, rlic::kParamTapBytes / (int)sizeof(T)> taps,
-                      const int ntaps)
-{
-    using F = Fp<T>;
-    const unsigned tile_y = blockIdx.x / (unsigned)g.tiles_x, tile_x = blockIdx.x - tile_y * (unsigned)g.tiles_x;
-    const int j = (int)(tile_x * 16 + (threadIdx.x % 16)), r = (int)(tile_y * 16 + (threadIdx.x / 16));
-    if (j >= g.nx || r >= g.out_rows) return;
-    tex += g.pitch;
-    out += g.pitch;
-    typename rlic::FieldAccess<T>::Ptr fcell = rlic::FieldAccess<T>::block(field, 0, g.field_stride) + g.pitch;
-    asm volatile("" : "+l"(tex), "+l"(fcell));
-    const int pitch = g.pitch, plane = (int)g.field_stride;
-    const int kmid = ntaps >> 1;
-    const int start = r * pitch + j;
-    T acc = F::fma(taps.get(kmid), __ldg(tex + start), T(0));
-    T sink = T(0);
-    const bool room_fwd = j + kmid < g.nx && r + kmid < g.rows, room_bwd = j - kmid >= 0 && r - kmid >= 0;
-    for (int dir = 1; dir >= -1; dir -= 2) {
-        int at = start;
-        const bool room = dir > 0 ? room_fwd : room_bwd;
-        int hop_a = room ? dir : 0, hop_b = room ? dir * pitch : 0;
-        const int k0 = dir > 0 ? kmid + 1 : kmid - 1, k1 = dir > 0 ? ntaps : -1;
-#pragma unroll 4
-        for (int k = k0; k != k1; k += dir) {
-            const PackedField<T> p = rlic::FieldAccess<T>::load(fcell, at, plane);
-            sink = F::add(sink, F::add(p.u, p.rv));          // keeps the gather alive, two adds
-            int hop = hop_a;
-            if (DEPENDENT)
-                hop += (int)(p.ru == T(-1234.5));            // never true for these fields; the address now waits
-            at += hop;
-            const int t = hop_a; hop_a = hop_b; hop_b = t;   // staircase
-            acc = F::fma(taps.get(k), __ldg(tex + at), acc);
-        }
-    }
-    out[start] = sink == T(-1) ? sink : acc;
-}
+// (the gather-ceiling kernel lives in lic_walk.cuh: the library exposes it as a measurement entry point)
+using rlic::gather_ceiling_kernel;
 
 struct Result { std::string name; float ms; bool same; int regs; };
 
