@@ -308,6 +308,24 @@ int rlic_b200_convolve_packed_f64(const double *d_texture, const double *d_field
                                   int64_t iterations, double *d_out, void *stream);
 
 /*
+ * DEVICE-RESIDENT BATCH: rlic_b200_convolve_device_* for a stack of `nfields` independent
+ * images of ny x nx pixels each (dense, one after the other, in device memory; so are d_u,
+ * d_v and d_out).  One launch of each kernel covers the whole stack: every field has its own
+ * guard rows and wall cells in the padded scratch, so out[f] equals the single-image result
+ * of field f bit for bit (BASELINE config 5's device-side form).
+ */
+int rlic_b200_convolve_device_batch_f32(const float *d_texture, const float *d_u, const float *d_v,
+                                        int64_t nfields, int64_t ny, int64_t nx,
+                                        const float *kernel, int64_t klen, int uv_mode,
+                                        int x_left, int x_right, int y_left, int y_right,
+                                        int64_t iterations, float *d_out, void *stream);
+int rlic_b200_convolve_device_batch_f64(const double *d_texture, const double *d_u, const double *d_v,
+                                        int64_t nfields, int64_t ny, int64_t nx,
+                                        const double *kernel, int64_t klen, int uv_mode,
+                                        int x_left, int x_right, int y_left, int y_right,
+                                        int64_t iterations, double *d_out, void *stream);
+
+/*
  * ROW SLABS — the building blocks of row-slab sharding.
  * The image has ny x nx pixels globally; a device holds global rows
  * [row0 - halo_lo, row0 + nrows + halo_hi) in PADDED buffers of
@@ -501,6 +519,23 @@ int rlic_b200_convolve_batch_f64(const double *texture, const double *u, const d
                                  int x_left, int x_right, int y_left, int y_right,
                                  int64_t iterations,
                                  const int *devices, int ndev, double *out);
+
+/* The batch entry with the texture sign check fused into the uploads, as
+ * rlic_b200_convolve_checked_* does for one image: *texture_has_negative is set to 1 when any
+ * element of any field is negative (`np.any(textures < 0)`, /root/reference/src/rlic/_lib.py:174,
+ * which costs about a second on the host for BASELINE config 5's 4 GiB stack). */
+int rlic_b200_convolve_batch_checked_f32(const float *texture, const float *u, const float *v,
+                                         int64_t nfields, int64_t ny, int64_t nx,
+                                         const float *kernel, int64_t klen, int uv_mode,
+                                         int x_left, int x_right, int y_left, int y_right,
+                                         int64_t iterations, const int *devices, int ndev, float *out,
+                                         int *texture_has_negative);
+int rlic_b200_convolve_batch_checked_f64(const double *texture, const double *u, const double *v,
+                                         int64_t nfields, int64_t ny, int64_t nx,
+                                         const double *kernel, int64_t klen, int uv_mode,
+                                         int x_left, int x_right, int y_left, int y_right,
+                                         int64_t iterations, const int *devices, int ndev, double *out,
+                                         int *texture_has_negative);
 
 #ifdef __cplusplus
 }

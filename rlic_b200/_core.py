@@ -54,7 +54,10 @@ def _signatures(real) -> dict[str, list]:
                              ctypes.POINTER(_int)],
         "convolve_batch": [p, p, p, _i64, _i64, _i64, p, _i64, _int, *walls, _i64,
                            ctypes.POINTER(_int), _int, p],
+        "convolve_batch_checked": [p, p, p, _i64, _i64, _i64, p, _i64, _int, *walls, _i64,
+                                   ctypes.POINTER(_int), _int, p, ctypes.POINTER(_int)],
         "convolve_device": [_vp, _vp, _vp, _i64, _i64, p, _i64, _int, *walls, _i64, _vp, _vp],
+        "convolve_device_batch": [_vp, _vp, _vp, _i64, _i64, _i64, p, _i64, _int, *walls, _i64, _vp, _vp],
         "pack_field": [_vp, _vp, _i64, _i64, *walls, _vp, _vp],
         "convolve_packed": [_vp, _vp, _i64, _i64, p, _i64, _int, *walls, _i64, _vp, _vp],
         "slab_pack_field": [_vp, _vp, *slab, *walls, _vp, _vp],
@@ -382,10 +385,12 @@ def _convolve(sfx: str, real, texture, uv, kernel, boundaries, iterations, check
     return out
 
 
-def convolve_batch(textures, uv, kernel, boundaries, iterations=1, devices=None):
+def convolve_batch(textures, uv, kernel, boundaries, iterations=1, devices=None, *, check_texture=False):
     """``nfields`` independent images stored back to back (``(nfields, ny, nx)`` arrays of
     one dtype), split whole-image over ``devices`` (default: every visible device).
-    Binding of ``rlic_b200_convolve_batch_*``."""
+    Binding of ``rlic_b200_convolve_batch_*``; ``check_texture=True`` performs the reference's
+    "no negative texture values" validation on the devices, during the uploads
+    (``rlic_b200_convolve_batch_checked_*``)."""
     u, v, uv_mode = uv
     dtype = textures.dtype
     if dtype == np.dtype("float32"):
@@ -407,10 +412,16 @@ def convolve_batch(textures, uv, kernel, boundaries, iterations=1, devices=None)
     if devices is not None:
         devices = [int(d) for d in devices]
         dev_arr, ndev = (ctypes.c_int * len(devices))(*devices), len(devices)
-    check(getattr(lib, f"rlic_b200_convolve_batch_{sfx}")(
-        textures.ctypes.data_as(p), u.ctypes.data_as(p), v.ctypes.data_as(p), nf, ny, nx,
-        kernel.ctypes.data_as(p), kernel.size, mode_code(uv_mode), *wall_codes(boundaries),
-        int(iterations), dev_arr, ndev, out.ctypes.data_as(p)))
+    args = (textures.ctypes.data_as(p), u.ctypes.data_as(p), v.ctypes.data_as(p), nf, ny, nx,
+            kernel.ctypes.data_as(p), kernel.size, mode_code(uv_mode), *wall_codes(boundaries),
+            int(iterations), dev_arr, ndev, out.ctypes.data_as(p))
+    if check_texture:
+        negative = _int(0)
+        check(getattr(lib, f"rlic_b200_convolve_batch_checked_{sfx}")(*args, ctypes.byref(negative)))
+        if negative.value:
+            raise ValueError(NEGATIVE_TEXTURE_MESSAGE)
+    else:
+        check(getattr(lib, f"rlic_b200_convolve_batch_{sfx}")(*args))
     return out
 
 

@@ -233,8 +233,16 @@ def convolve_batch(
     problems, walls, _ = _check_inputs(
         textures[0], u[0], v[0], kernel, uv_mode, boundaries, iterations, defer_sign_check=True
     )
-    if not problems and np.any(textures < 0):
-        problems.append(ValueError(_NEGATIVE_TEXTURE))
+    # The sign scan of the whole stack (4 GiB at BASELINE config 5: about a second on the host)
+    # rides on the uploads when nothing else is wrong; otherwise it runs here, on the first
+    # field that has a negative value, so that it takes its place in the group.
+    on_device = not problems and iterations > 0 and textures.size >= _DEVICE_CHECK_MIN_SIZE
+    if not on_device:
+        negative = np.flatnonzero((textures < 0).any(axis=(1, 2)))
+        if negative.size:
+            problems, walls, _ = _check_inputs(
+                textures[negative[0]], u[0], v[0], kernel, uv_mode, boundaries, iterations
+            )
     if len(problems) == 1:
         raise problems[0]
     if problems:
@@ -243,7 +251,8 @@ def convolve_batch(
     if iterations == 0:
         return textures.copy()
     return _core.convolve_batch(
-        textures, (u, v, uv_mode), kernel, (walls.x, walls.y), iterations, devices
+        textures, (u, v, uv_mode), kernel, (walls.x, walls.y), iterations, devices,
+        check_texture=on_device,
     )
 
 

@@ -617,10 +617,11 @@ int convolve_host(const T *tex, const T *u, const T *v, int64_t nfields, int64_t
 // buffers swap roles).
 template <typename T>
 int run_device(const T *d_tex, const Field<T> *d_field, int64_t ny, int64_t nx, const TapSet<T> &taps,
-               int uv_mode, const Walls &w, int64_t iterations, T *d_out, cudaStream_t s)
+               int uv_mode, const Walls &w, int64_t iterations, T *d_out, cudaStream_t s,
+               int64_t nfields = 1)
 {
     const PassGeom g = make_geometry(ny, nx, Slab{0, ny, 0, 0}, w);
-    const size_t padded_bytes = (size_t)g.field_stride * sizeof(T);
+    const size_t padded_bytes = (size_t)g.field_stride * (size_t)nfields * sizeof(T);
     CUDA_TRY(use_current_device());
     DeviceBuf a, b;   // stream-ordered scratch, returned to the pool when the work is enqueued
     CUDA_TRY(a.alloc(padded_bytes, s));
@@ -628,17 +629,17 @@ int run_device(const T *d_tex, const Field<T> *d_field, int64_t ny, int64_t nx, 
         CUDA_TRY(b.alloc(padded_bytes, s));
     DeviceBuf in;
     CUDA_TRY(in.alloc(padded_bytes, s));
-    CUDA_TRY(launch_pad<T>(d_tex, static_cast<T *>(in.p), g, 0, ny, 1, nullptr, s));
+    CUDA_TRY(launch_pad<T>(d_tex, static_cast<T *>(in.p), g, 0, ny, nfields, nullptr, s));
     const T *src = static_cast<const T *>(in.p);
     T *dst = static_cast<T *>(a.p);
     for (int64_t it = 0; it < iterations; ++it) {
         // pass 1: in -> a; pass 2: a -> b; pass 3: b -> a; ...
         dst = static_cast<T *>(it == 0 ? a.p : ((it & 1) ? b.p : a.p));
-        if (int rc = launch_pass<T>(src, d_field, dst, g, 1, 0, ny, uv_mode, taps, s))
+        if (int rc = launch_pass<T>(src, d_field, dst, g, nfields, 0, ny, uv_mode, taps, s))
             return rc;
         src = dst;
     }
-    CUDA_TRY(launch_unpad<T>(dst, d_out, g, 0, ny, 1, s));
+    CUDA_TRY(launch_unpad<T>(dst, d_out, g, 0, ny, nfields, s));
     return RLIC_B200_OK;
 }
 
@@ -658,14 +659,16 @@ int check_device_call(const void *a, const void *b, const void *c, const void *k
 template <typename T>
 int convolve_device(const T *d_tex, const T *d_u, const T *d_v, int64_t ny, int64_t nx,
                     const T *kernel, int64_t klen, int uv_mode, const Walls &w,
-                    int64_t iterations, T *d_out, void *stream)
+                    int64_t iterations, T *d_out, void *stream, int64_t nfields = 1)
 {
     if (int rc = check_device_call<T>(d_tex, d_u, d_v, kernel, d_out, ny, nx, klen, uv_mode, w))
         return rc;
-    if (ny == 0 || nx == 0)
+    if (nfields < 0)
+        return fail(RLIC_B200_EINVAL, "negative field count");
+    if (ny == 0 || nx == 0 || nfields == 0)
         return RLIC_B200_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const size_t count = (size_t)ny * (size_t)nx;
+    const size_t count = (size_t)ny * (size_t)nx * (size_t)nfields;
     if (iterations <= 0) {
         CUDA_TRY(cudaMemsetAsync(d_out, 0, sizeof(T) * count, s));
         return RLIC_B200_OK;
@@ -675,10 +678,10 @@ int convolve_device(const T *d_tex, const T *d_u, const T *d_v, int64_t ny, int6
     CUDA_TRY(taps.prepare(kernel, klen, s));
     const PassGeom g = make_geometry(ny, nx, Slab{0, ny, 0, 0}, w);
     DeviceBuf d_field;
-    CUDA_TRY(d_field.alloc(4 * sizeof(T) * (size_t)g.field_stride, s));
-    CUDA_TRY(launch_pack<T>(d_u, d_v, static_cast<Field<T> *>(d_field.p), g, 0, ny, 1, s));
+    CUDA_TRY(d_field.alloc(4 * sizeof(T) * (size_t)g.field_stride * (size_t)nfields, s));
+    CUDA_TRY(launch_pack<T>(d_u, d_v, static_cast<Field<T> *>(d_field.p), g, 0, ny, nfields, s));
     return run_device<T>(d_tex, static_cast<Field<T> *>(d_field.p), ny, nx, taps, uv_mode, w,
-                         iterations, d_out, s);
+                         iterations, d_out, s, nfields);
 }
 
 template <typename T>
@@ -826,8 +829,11 @@ int pass_slab(const T *d_tex, const T *d_field, T *d_out, int64_t ny, int64_t nx
 template <typename T>
 int convolve_batch(const T *tex, const T *u, const T *v, int64_t nfields, int64_t ny, int64_t nx,
                    const T *kernel, int64_t klen, int uv_mode, const Walls &w,
-                   int64_t iterations, const int *devices, int ndev, T *out)
+                   int64_t iterations, const int *devices, int ndev, T *out,
+                   int *texture_has_negative = nullptr)
 {
+    if (texture_has_negative)
+        *texture_has_negative = 0;
     if (int rc = check_common(ny, nx, klen, uv_mode, w))
         return rc;
     if (nfields < 0)
@@ -856,6 +862,7 @@ int convolve_batch(const T *tex, const T *u, const T *v, int64_t nfields, int64_
 
     const int lanes = 2;
     const ThreadChoices mine{effective_arithmetic(), effective_schedule(), effective_walk()};
+    std::atomic<int> any_negative{0};
     std::vector<int> rcs(devs.size() * lanes, 0);
     std::vector<std::string> msgs(devs.size() * lanes);
     std::vector<std::atomic<int64_t>> cursor(devs.size());
@@ -873,8 +880,12 @@ int convolve_batch(const T *tex, const T *u, const T *v, int64_t nfields, int64_
                         break;
                     const int64_t n = std::min(chunk, f1 - f);
                     const size_t off = (size_t)f * field_elems;
+                    int negative = 0;
                     rc = convolve_host<T>(tex + off, u + off, v + off, n, ny, nx, kernel, klen,
-                                          uv_mode, w, iterations, out + off, devs[(size_t)d]);
+                                          uv_mode, w, iterations, out + off, devs[(size_t)d],
+                                          texture_has_negative ? &negative : nullptr);
+                    if (negative)
+                        any_negative.store(1, std::memory_order_relaxed);
                 }
                 rcs[(size_t)d * lanes + lane] = rc;
                 if (rc)
@@ -889,6 +900,8 @@ int convolve_batch(const T *tex, const T *u, const T *v, int64_t nfields, int64_
             tls_error = msgs[i];
             return rcs[i];
         }
+    if (texture_has_negative)
+        *texture_has_negative = any_negative.load();
     return RLIC_B200_OK;
 }
 
@@ -1100,6 +1113,20 @@ int rlic_b200_set_device(int device)
                                  Walls{x_left, x_right, y_left, y_right}, iterations, devices,   \
                                  ndev, out);                                                     \
     }                                                                                            \
+    int rlic_b200_convolve_batch_checked_##sfx(const T *texture, const T *u, const T *v,         \
+                                               int64_t nfields, int64_t ny, int64_t nx,          \
+                                               const T *kernel, int64_t klen, int uv_mode,       \
+                                               int x_left, int x_right, int y_left, int y_right, \
+                                               int64_t iterations, const int *devices, int ndev, \
+                                               T *out, int *texture_has_negative)                \
+    {                                                                                            \
+        tls_error.clear();                                                                       \
+        if (!texture_has_negative)                                                               \
+            return fail(RLIC_B200_EINVAL, "texture_has_negative is null");                       \
+        return convolve_batch<T>(texture, u, v, nfields, ny, nx, kernel, klen, uv_mode,          \
+                                 Walls{x_left, x_right, y_left, y_right}, iterations, devices,   \
+                                 ndev, out, texture_has_negative);                               \
+    }                                                                                            \
     int rlic_b200_convolve_device_##sfx(const T *d_texture, const T *d_u, const T *d_v,          \
                                         int64_t ny, int64_t nx, const T *kernel, int64_t klen,   \
                                         int uv_mode, int x_left, int x_right, int y_left,        \
@@ -1109,6 +1136,17 @@ int rlic_b200_set_device(int device)
         return convolve_device<T>(d_texture, d_u, d_v, ny, nx, kernel, klen, uv_mode,            \
                                   Walls{x_left, x_right, y_left, y_right}, iterations, d_out,    \
                                   stream);                                                       \
+    }                                                                                            \
+    int rlic_b200_convolve_device_batch_##sfx(const T *d_texture, const T *d_u, const T *d_v,    \
+                                              int64_t nfields, int64_t ny, int64_t nx,           \
+                                              const T *kernel, int64_t klen, int uv_mode,        \
+                                              int x_left, int x_right, int y_left, int y_right,  \
+                                              int64_t iterations, T *d_out, void *stream)        \
+    {                                                                                            \
+        tls_error.clear();                                                                       \
+        return convolve_device<T>(d_texture, d_u, d_v, ny, nx, kernel, klen, uv_mode,            \
+                                  Walls{x_left, x_right, y_left, y_right}, iterations, d_out,    \
+                                  stream, nfields);                                              \
     }                                                                                            \
     int rlic_b200_pack_field_##sfx(const T *d_u, const T *d_v, int64_t ny, int64_t nx,           \
                                    int x_left, int x_right, int y_left, int y_right,             \

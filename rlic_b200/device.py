@@ -12,7 +12,7 @@ used for device memory and streams only.
 
 from __future__ import annotations
 
-__all__ = ["PackedField", "convolve_device", "pack_field"]
+__all__ = ["PackedField", "convolve_device", "convolve_device_batch", "pack_field"]
 
 import ctypes
 from dataclasses import dataclass
@@ -150,5 +150,42 @@ def convolve_device(texture: torch.Tensor, u: torch.Tensor | None = None, v: tor
             rc = getattr(_core.lib, f"rlic_b200_convolve_packed_{sfx}")(
                 texture.data_ptr(), field.data.data_ptr(), ny, nx, tap_ptr, taps.size, mode,
                 *walls, int(iterations), out.data_ptr(), _stream_handle(stream))
+    _core.check(rc)
+    return out
+
+
+def convolve_device_batch(textures: torch.Tensor, u: torch.Tensor, v: torch.Tensor, *, kernel,
+                          uv_mode: str = "velocity", boundaries="closed", iterations: int = 1,
+                          out: torch.Tensor | None = None, stream=None) -> torch.Tensor:
+    """``convolve_device`` for a stack of independent fields: CUDA tensors of shape
+    ``(nfields, ny, nx)``; ``out[f]`` equals ``convolve_device(textures[f], u[f], v[f], ...)`` bit
+    for bit.  One launch of each kernel covers the whole stack (``rlic_b200_convolve_device_batch_*``):
+    the device-resident form of BASELINE config 5."""
+    textures, u, v, out = _as_tensor(textures), _as_tensor(u), _as_tensor(v), _as_tensor(out)
+    for name, t in (("textures", textures), ("u", u), ("v", v)) + ((("out", out),) if out is not None else ()):
+        if not isinstance(t, torch.Tensor) or not t.is_cuda:
+            raise TypeError(f"{name} must be a CUDA tensor or an array exporting "
+                            "__cuda_array_interface__ / DLPack from device memory")
+        if t.dim() != 3 or not t.is_contiguous():
+            raise ValueError(f"{name} must be a contiguous 3-D tensor (nfields, ny, nx)")
+        if t.shape != textures.shape or t.dtype != textures.dtype or t.device != textures.device:
+            raise ValueError(f"{name} must match the textures' shape, dtype and device")
+    sfx, real, np_dtype = _kind(textures)
+    if iterations < 0:
+        raise ValueError(
+            f"Invalid number of iterations: {iterations}\nExpected a strictly positive integer.")
+    taps = _host_taps(kernel, np_dtype)
+    walls = _walls(boundaries)
+    mode = _core.mode_code(uv_mode)
+    if iterations == 0:
+        return textures.clone()
+    if out is None:
+        out = torch.empty_like(textures)
+    nf, ny, nx = textures.shape
+    with torch.cuda.device(textures.device):
+        rc = getattr(_core.lib, f"rlic_b200_convolve_device_batch_{sfx}")(
+            textures.data_ptr(), u.data_ptr(), v.data_ptr(), nf, ny, nx,
+            taps.ctypes.data_as(ctypes.POINTER(real)), taps.size, mode, *walls, int(iterations),
+            out.data_ptr(), _stream_handle(stream))
     _core.check(rc)
     return out

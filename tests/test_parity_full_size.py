@@ -1,0 +1,135 @@
+"""Bit-for-bit parity at the BASELINE configurations' own sizes (C3, C4,
+C5) and the reference's "kernel longer than the image" case, against the CPU oracle.
+
+Where the oracle cannot walk the whole image in seconds it walks a sub-image that contains the
+checked band plus a margin no walker can cross: a walker moves at most ``len(kernel) // 2`` rows
+per pass (/root/reference/src/lib.rs:325-329), so rows further than ``iterations * reach`` from an
+artificial cut are exactly the whole image's.
+"""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+from numpy.testing import assert_array_equal
+
+import oracle
+import rlic_b200 as rlic
+from rlic_b200 import _core, workloads
+
+pytestmark = pytest.mark.gpu
+
+
+def test_c3_full_size():
+    """BASELINE config 3 as stated: 2048 x 2048 f64, polarization, sign-flipping U, x periodic /
+    y closed, 129 taps -- the whole image against the oracle on every host core."""
+    w = workloads.polarization_split(2048, 129)
+    got = rlic.convolve(w.texture, w.u, w.v, **w.kwargs())
+    want = oracle.convolve(w.texture, w.u, w.v, kernel=w.kernel, uv_mode="polarization",
+                           boundaries=(("periodic", "periodic"), ("closed", "closed")),
+                           threads=oracle.max_threads())
+    assert_array_equal(got, want)
+
+
+def test_c3_full_size_on_a_rotating_field_two_iterations():
+    """The same size and kernel on a field that exercises both axes (C3's own field is
+    horizontal), both modes' arithmetic differing only in the alignment step."""
+    w = workloads.vortex_noise(2048, dtype=np.float64, taps=129, iterations=2)
+    for mode in ("polarization", "velocity"):
+        got = rlic.convolve(w.texture, w.u, w.v, kernel=w.kernel, uv_mode=mode,
+                            boundaries={"x": "periodic", "y": "closed"}, iterations=2)
+        band = slice(960, 1088)                     # 128 rows mid-image, margin 2 x 64 rows
+        sub = slice(band.start - 128, band.stop + 128)
+        want = oracle.convolve(w.texture[sub], w.u[sub], w.v[sub], kernel=w.kernel, uv_mode=mode,
+                               boundaries=(("periodic", "periodic"), ("closed", "closed")), iterations=2,
+                               threads=oracle.max_threads())[128:256]
+        assert_array_equal(got[band], want)
+
+
+def test_c4_size_bands_at_top_middle_and_bottom():
+    """BASELINE config 4's image (16384 x 16384 f32, 65 taps, closed walls) on one GPU, two
+    passes: the first, a middle and the last 32 rows against the oracle (64-bit cell offsets
+    are not needed yet at this size; 32-bit ones are at 2^28.0 cells of 2^31)."""
+    n, its, reach = 16384, 2, 32
+    w = workloads.vortex_noise(n, iterations=its)
+    got = rlic.convolve(w.texture, w.u, w.v, **w.kwargs())
+    assert got.shape == (n, n)
+    m = its * reach
+    for a in (0, n // 2 - 16, n - 32):
+        g0, g1 = max(0, a - m), min(n, a + 32 + m)
+        want = oracle.convolve(w.texture[g0:g1], w.u[g0:g1], w.v[g0:g1], kernel=w.kernel, iterations=its,
+                               threads=oracle.max_threads())[a - g0:a - g0 + 32]
+        assert_array_equal(got[a:a + 32], want)
+    # and the passes compose at this size: two calls of one pass equal one call of two
+    once = rlic.convolve(w.texture, w.u, w.v, kernel=w.kernel, iterations=1)
+    again = rlic.convolve(once, w.u, w.v, kernel=w.kernel, iterations=1)
+    assert_array_equal(again, got)
+
+
+def test_c5_shape_batch_sampled_fields_and_device_batch_entry():
+    """BASELINE config 5's fields (512 x 512 f32, 33 taps, 3 iterations) through the public
+    batch API on every visible GPU: sampled fields against the oracle; the device-resident
+    batch entry returns the same stack.  (All 4096 fields at once: tools/bench_c5_batch.py,
+    whose JSON line carries the same two checks.)"""
+    import torch
+
+    from rlic_b200.device import convolve_device_batch
+
+    w = workloads.snapshot_batch(256, 512, 33, 3)
+    got = rlic.convolve_batch(w.texture, w.u, w.v, **w.kwargs())
+    for f in (0, 1, 17, 100, 127, 128, 200, 255):
+        want = oracle.convolve(w.texture[f], w.u[f], w.v[f], kernel=w.kernel, iterations=3,
+                               threads=oracle.max_threads())
+        assert_array_equal(got[f], want)
+    part = slice(40, 104)
+    dev = convolve_device_batch(*(torch.from_numpy(x[part]).cuda() for x in (w.texture, w.u, w.v)),
+                                kernel=w.kernel, iterations=3)
+    assert_array_equal(dev.cpu().numpy(), got[part])
+    # a negative value anywhere in the stack is caught on the device, during the uploads
+    bad = w.texture.copy()
+    bad[201, 300, 7] = -1.0
+    with pytest.raises(ValueError, match=r"^Found invalid texture element\(s\)\. Expected only positive values\.$"):
+        rlic.convolve_batch(bad, w.u, w.v, **w.kwargs())
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("mode", ["velocity", "polarization"])
+def test_kernel_longer_than_the_image_every_boundary_kind(dtype, mode):
+    """/root/reference/tests/test_convolution.py:180-207: a 128-tap kernel on a 64 x 64 image
+    with closed, periodic and mixed boundaries (the reference asserts the three differ
+    everywhere; here each is also the oracle's, bit for bit, and so are two iterations)."""
+    rng = np.random.default_rng(0)
+    shape = (64, 64)
+    tex = rng.random(shape).astype(dtype)
+    u = rng.random(shape).astype(dtype)
+    v = rng.random(shape).astype(dtype)
+    kernel = np.linspace(0, 1, 128, dtype=dtype)
+    outs = {}
+    for name, spec, pairs in (
+        ("closed", "closed", (("closed", "closed"), ("closed", "closed"))),
+        ("periodic", "periodic", (("periodic", "periodic"), ("periodic", "periodic"))),
+        ("mixed", {"x": "closed", "y": "periodic"}, (("closed", "closed"), ("periodic", "periodic"))),
+        ("mixed-2", {"x": "periodic", "y": "closed"}, (("periodic", "periodic"), ("closed", "closed"))),
+    ):
+        for its in (1, 2):
+            got = rlic.convolve(tex, u, v, kernel=kernel, uv_mode=mode, boundaries=spec, iterations=its)
+            want = oracle.convolve(tex, u, v, kernel=kernel, uv_mode=mode, boundaries=pairs, iterations=its)
+            assert_array_equal(got, want)
+            if its == 1:
+                outs[name] = got
+    assert np.all(outs["closed"] != outs["periodic"])
+    assert np.all(outs["closed"] != outs["mixed"])
+    assert np.all(outs["periodic"] != outs["mixed"])
+
+
+def test_every_visible_device_gives_the_same_bits():
+    w = workloads.vortex_noise(1024, iterations=2)
+    want = None
+    for d in range(_core.device_count()):
+        _core.check(_core.lib.rlic_b200_set_device(d))
+        try:
+            got = rlic.convolve(w.texture, w.u, w.v, **w.kwargs())
+        finally:
+            _core.check(_core.lib.rlic_b200_set_device(0))
+        if want is None:
+            want = oracle.convolve(w.texture, w.u, w.v, kernel=w.kernel, iterations=2, threads=oracle.max_threads())
+        assert_array_equal(got, want)
