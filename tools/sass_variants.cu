@@ -26,6 +26,8 @@ template <typename T, bool POL, typename PT> const void *tuned_grouped()
     variant<T, POL, PT, 7, FLAVOR>(), variant<T, POL, PT, 9, FLAVOR>(), variant<T, POL, PT, 11, FLAVOR>()
 
 const void *table[] = {
+    variant<float, false, PT32, 7, 4>(), variant<float, false, PT32, 5, 4>(), variant<float, false, PT32, 1, 4>(),
+    variant<float, true, PT32, 1, 4>(), variant<float, true, PT32, 7, 4>(),
     shipped<float, false, PT32>(), shipped<float, true, PT32>(),
     shipped<double, false, PT64>(), shipped<double, true, PT64>(),
     tuned_grouped<float, false, PT32>(), tuned_grouped<float, true, PT32>(),
