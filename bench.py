@@ -571,12 +571,47 @@ def run_ours(args) -> dict:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = t.item() / n_e2e * 1e3
         e2e_val = pixels_all * ITERATIONS / (e2e_ms * 1e-3) / 1e6
+    # The floor the host link sets for such a step: nothing but the step's copies -- the three
+    # input slabs up on one stream, a result-sized slab down on another, page-locked memory,
+    # every rank at once -- no kernels.  On a box whose GPUs share host links or host memory
+    # bandwidth this, not the compute, bounds the end-to-end figure at N > 1.
+    up_s, down_s = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    staging = [torch.empty(texture.shape, dtype=torch.float32, device=dev) for _ in range(4)]
+    host_in = [torch.from_numpy(a) for a in (h_tex, h_u, h_v)]
+    host_out = torch.empty(texture.shape, dtype=torch.float32).pin_memory()
+
+    def copies_only():
+        with torch.cuda.stream(up_s):
+            for dst, src in zip(staging, host_in):
+                dst.copy_(src, non_blocking=True)
+        with torch.cuda.stream(down_s):
+            host_out.copy_(staging[3], non_blocking=True)
+        up_s.synchronize()
+        down_s.synchronize()
+
+    copies_only()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        copies_only()
+    dt_copy = (time.perf_counter() - t0) / 5
+    barrier()
+    if dist is not None:
+        t = torch.tensor([dt_copy], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt_copy = t.item()
+    del staging
+    host_link = {"copies_only_ms_per_step": dt_copy * 1e3,
+                 "aggregate_GBps": (h2d + d2h) * world / dt_copy / 1e9,
+                 "note": "the step's host<->device copies alone (3 slabs up, 1 down, pinned, all ranks at once): "
+                         "the floor the host link sets for ms_per_step"}
     e2e = {"value": e2e_val, "unit": METRIC, "h2d_bytes_per_step": h2d * world,
            "d2h_bytes_per_step": d2h * world, "ms_per_step": e2e_ms,
            "api": "rlic_b200.convolve(numpy arrays in pinned host memory)" if world == 1
                   else "per rank: ShardedConvolver.convolve_host(texture, u, v slabs in pinned host memory) "
                        "-> pinned host slab",
            **rlic_b200.effective_options()}
+    e2e["host_link"] = host_link
     if world > 1:
         e2e["exchange"] = sc.exchange
     else:

@@ -324,9 +324,18 @@ class ShardedConvolver:
     """
 
     PEER_TIMEOUT_MS = 20_000      # a wait for a neighbour gives up after this long (and says so)
-    # read the "a wait gave up" flag back after every call with exchange="peer" and raise if it
-    # is set (one 4-byte device-to-host read, i.e. one synchronisation per call)
-    check_peer_timeouts = True
+    # What happens to the "a wait for a neighbour gave up" flag of exchange="peer" (a result
+    # computed from stale halos must never pass for a good one):
+    #   "lazy"  (default) every call ends with an asynchronous 4-byte copy of the flag to
+    #           page-locked memory; the NEXT call, `synchronize()` and `close()` look at the
+    #           copies that have landed and raise.  No host synchronisation: the host keeps
+    #           running ahead of the device, which is what hides its launch latencies
+    #           (measured on 8 GPUs: a blocking read per call cost 1-2 ms of a 7.6 ms call,
+    #           profiles/r2_peer_diag_*.json).  Host entry points (`convolve_host`) synchronise
+    #           anyway and check before they return.
+    #   True    read the flag back before the call returns (one synchronisation per call)
+    #   False   never look
+    check_peer_timeouts = "lazy"
 
     def __init__(self, ny: int, nx: int, *, kernel, uv_mode: str = "velocity",
                  boundaries="closed", group=None, ops=None, exchange: str = "nccl", peers=None):
@@ -362,6 +371,8 @@ class ShardedConvolver:
         self._peer_memory = peers
         self._peer = None            # _PeerExchange, built on the first convolve (needs dtype and device)
         self._work = None            # ((dtype, device), padded buffer, padded buffer) of the NCCL path
+        self.trace = None            # diagnostics: list of (label, CUDA event), see _mark
+        self._timeout_probes = []    # (pinned copy of the time-out flag, event) of earlier calls
         self._staging = None         # ((dtype, device), dense texture, u, v) of convolve_host
         self._host_streams = None    # (upload stream, download stream) of convolve_host
 
@@ -519,12 +530,21 @@ class ShardedConvolver:
         state every wait finds its counter already raised."""
         p = self.plan
         px = self._peer_exchange(texture.dtype, texture.device)
+        self._poll_timeout_probes()
         self.ops.pad_texture(texture.contiguous(), px.bufs[0], p, self.walls)
         self._peer_passes(px, iterations)
         out = torch.empty_like(texture)
         self.ops.unpad_texture(px.bufs[iterations % 2], out, p, self.walls)
         self._peer_finish(px, iterations)
         return out
+
+    def _mark(self, label: str) -> None:
+        """Diagnostics (tools/peer_diag.py): with ``self.trace`` a list, record a timing event on
+        the current stream after the operation called ``label``."""
+        if self.trace is not None and torch.cuda.is_available():
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.trace.append((label, ev))
 
     def _peer_signals(self, px):
         p, flags, limit = self.plan, px.flags, self.PEER_TIMEOUT_MS
@@ -571,7 +591,9 @@ class ShardedConvolver:
                     mine[(s0 + cells.start) * width:(s0 + cells.stop) * width])
 
         # X[0]'s halos: my edge rows copied into the neighbours' bufs[0] (and field)
+        self._mark("begin")
         wait(_FREE_FROM_UP, _FREE_FROM_DOWN, c)
+        self._mark("wait free (previous call)")
         width, planes = self.field_layout(bufs[0].dtype)
         if up is not None:
             push(up[0][0], bufs[0], px.delta_up, lo, lo + h)
@@ -582,14 +604,18 @@ class ShardedConvolver:
             if push_field:
                 push(down[3], px.field, px.delta_down, lo + rows - h, lo + rows, width, planes, down[2].cells)
         signal(_HALO_FROM_DOWN, _HALO_FROM_UP, c + 1)
+        self._mark("push initial halos")
         for k in range(1, n + 1):
             src, dst = bufs[(k - 1) % 2], bufs[k % 2]
             wait(_HALO_FROM_UP, _HALO_FROM_DOWN, c + k)
+            self._mark("wait halo")
             if k == n:
                 rows_runner(k, src, dst, 0, rows)
+                self._mark("last pass")
                 break
             if k >= 2:
                 wait(_FREE_FROM_UP, _FREE_FROM_DOWN, c + k - 1)
+                self._mark("wait free")
             if up is not None:
                 self.ops.pass_rows_peer(src, self.field, dst, p, 0, h, self.taps, self.mode, self.walls,
                                         up[0][k % 2], px.delta_up)
@@ -601,21 +627,57 @@ class ShardedConvolver:
             else:
                 self._pass_rows(src, dst, rows - h, rows)
             signal(_HALO_FROM_DOWN, _HALO_FROM_UP, c + k + 1)
+            self._mark("strips + signal")
             rows_runner(k, src, dst, h, rows - h)
             signal(_FREE_FROM_DOWN, _FREE_FROM_UP, c + k)
+            self._mark("interior + signal")
 
-    def _peer_finish(self, px, n: int) -> None:
+    def _peer_finish(self, px, n: int, blocking: bool = False) -> None:
         """After the last read of this call's buffers (the un-padding) has been enqueued on the
-        current stream: tell the neighbours, advance the count, and refuse to return a result
-        that was computed from stale halos."""
+        current stream: tell the neighbours, advance the count, and see to it that a result
+        computed from stale halos is reported (`check_peer_timeouts`); `blocking`: the caller
+        synchronises anyway, so the flag can be read on the spot."""
         _, _, _, signal = self._peer_signals(px)
         signal(_FREE_FROM_DOWN, _FREE_FROM_UP, px.tick + n + 1)
         px.tick += n + 1
-        if self.check_peer_timeouts and self.peer_timed_out():
-            px.flags[_TIMED_OUT] = 0
+        if self.check_peer_timeouts is True or (blocking and self.check_peer_timeouts):
+            self._raise_if_timed_out(bool(int(px.flags[_TIMED_OUT].item()) != 0))
+        elif self.check_peer_timeouts == "lazy":
+            if px.flags.is_cuda:
+                probe = torch.empty(1, dtype=torch.int32, pin_memory=True)
+                probe.copy_(px.flags[_TIMED_OUT:_TIMED_OUT + 1], non_blocking=True)
+                landed = torch.cuda.Event()
+                landed.record()
+                self._timeout_probes.append((probe, landed))
+            else:
+                self._raise_if_timed_out(bool(int(px.flags[_TIMED_OUT]) != 0))
+
+    def _raise_if_timed_out(self, timed_out: bool) -> None:
+        if timed_out:
+            self._peer.flags[_TIMED_OUT] = 0
+            self._timeout_probes.clear()
             raise RuntimeError(
                 f"rank {self.plan.rank}: a neighbour did not answer within {self.PEER_TIMEOUT_MS} ms during "
-                "the fused halo exchange; the result of this call is invalid")
+                "the fused halo exchange; results computed since the last check are invalid")
+
+    def _poll_timeout_probes(self, wait: bool = False) -> None:
+        """Look at the flag copies of earlier calls that have landed (all of them with `wait`)."""
+        keep, bad = [], False
+        for probe, landed in self._timeout_probes:
+            if wait:
+                landed.synchronize()
+            if landed.query():
+                bad |= bool(int(probe[0]) != 0)
+            else:
+                keep.append((probe, landed))
+        self._timeout_probes = keep
+        self._raise_if_timed_out(bad)
+
+    def synchronize(self) -> None:
+        """Wait for everything this convolver enqueued and raise if a wait for a neighbour gave up."""
+        if self._peer is not None and self._peer.flags.is_cuda:
+            torch.cuda.current_stream(self._peer.flags.device).synchronize()
+        self._poll_timeout_probes(wait=True)
 
     # -- host slabs in, host slabs out ------------------------------------------
     def convolve_host(self, texture, u=None, v=None, *, iterations: int = 1, out=None, device=None,
@@ -680,6 +742,7 @@ class ShardedConvolver:
             return out
 
         px = self._peer_exchange(t_tex.dtype, device)
+        self._poll_timeout_probes()
         if t_u is not None:
             self.field = px.field
         n, rows = iterations, p.nrows
@@ -759,9 +822,9 @@ class ShardedConvolver:
             finished = record(back)
         # the counters are raised on the stream that made the last read of this call's buffers
         after(main, finished)
-        self._peer_finish(px, n)
         if cuda:
             back.synchronize()
+        self._peer_finish(px, n, blocking=True)
         return out
 
     def peer_timed_out(self) -> bool:
@@ -769,7 +832,12 @@ class ShardedConvolver:
         return bool(self._peer is not None and int(self._peer.flags[_TIMED_OUT].item()) != 0)
 
     def close(self) -> None:
-        """Release the peer mappings and buffers (collective; only needed with ``exchange="peer"``)."""
+        """Release the peer mappings and buffers (collective; only needed with ``exchange="peer"``).
+        Raises if a wait for a neighbour gave up since the last check."""
         if self._peer is not None:
-            self._peer.close(self.group)
-            self._peer = None
+            try:
+                if self.check_peer_timeouts:
+                    self.synchronize()
+            finally:
+                self._peer.close(self.group)
+                self._peer = None

@@ -155,7 +155,18 @@ int pick_formulation(const T *tex, const T *field, T *out, const PassGeom &g, co
     RLIC_CASE(1, 0) RLIC_CASE(1, 1) RLIC_CASE(1, 2) RLIC_CASE(1, 3)
     RLIC_CASE(2, 0) RLIC_CASE(2, 1) RLIC_CASE(2, 2) RLIC_CASE(2, 3)
     RLIC_CASE(3, 0) RLIC_CASE(3, 1) RLIC_CASE(3, 2) RLIC_CASE(3, 3)
+    RLIC_CASE(0, 4) RLIC_CASE(1, 4) RLIC_CASE(2, 4) RLIC_CASE(3, 4)
 #undef RLIC_CASE
+    // flavour 4: the packed-pair formulation of the grouped walk, single precision only
+    if constexpr (sizeof(T) == 4) {
+        if (flavor == 4 && (walk == 1 || walk == 9) && (admit == 3 || admit == 4)) {
+            if (walk == 1 && admit == 3) run_pass<T, POL, Taps, int, 4, 3, true, 1>(tex, field, out, g, taps, ntaps, blocks);
+            else if (walk == 1) run_pass<T, POL, Taps, int, 4, 4, true, 1>(tex, field, out, g, taps, ntaps, blocks);
+            else if (admit == 3) run_pass<T, POL, Taps, int, 4, 3, true, 9>(tex, field, out, g, taps, ntaps, blocks);
+            else run_pass<T, POL, Taps, int, 4, 4, true, 9>(tex, field, out, g, taps, ntaps, blocks);
+            return 0;
+        }
+    }
     return 1;
 }
 

@@ -341,6 +341,45 @@ def test_grouped_walk_every_formulation(flavor, walk):
           flavor=flavor, admit=2, walk=walk)
 
 
+@pytest.mark.parametrize("walk", [1, 9])
+@pytest.mark.parametrize("admit", [3, 4])
+def test_packed_pair_formulation_f32(admit, walk):
+    """Flavour 4: both axes of a step as one packed pair (FADD2 / FMUL2 / FFMA2 on the GPU, two
+    scalars here), and ADMIT 4: the flag test folded into a NaN-propagating three-input
+    minimum.  Same bits as the oracle on special pixels, every wall kind, both modes, zero and
+    signed-zero components, huge and tiny velocities, every remainder of the group size."""
+    for mode in ("velocity", "polarization"):
+        for walls in WALLS:
+            check(*random_case((45, 70), np.float32, 23, seed=11), mode=mode, walls=walls, iterations=2,
+                  flavor=4, admit=admit, walk=walk)
+    for seed in range(24):
+        tex, u, v, kernel, mode, walls, its = fuzz_case(seed)
+        if tex.dtype != np.float32:
+            continue
+        with np.errstate(all="ignore"):
+            check(tex, u, v, kernel, mode=mode, walls=walls, iterations=its, flavor=4, admit=admit, walk=walk)
+    for klen in (1, 2, 3, 4, 5, 6, 7, 8, 9, 10):
+        check(*random_case((19, 21), np.float32, klen, seed=klen), mode="polarization", walls="x-periodic",
+              flavor=4, admit=admit, walk=walk)
+    rng = np.random.default_rng(3)
+    tex = rng.random((40, 50), dtype=np.float32)
+    k = np.linspace(0.1, 1, 15, dtype=np.float32)
+    for u0, v0 in ((1.0, 0.0), (0.0, -1.0), (-0.0, 1.0), (1e-30, 1.0), (3e20, -2.0), (-1.0, -0.0)):
+        u = np.full((40, 50), u0, dtype=np.float32)
+        v = np.full((40, 50), v0, dtype=np.float32)
+        with np.errstate(all="ignore"):
+            check(tex, u, v, k, walls="periodic", flavor=4, admit=admit, walk=walk)
+            check(tex, u, v, k, mode="polarization", walls="closed", flavor=4, admit=admit, walk=walk)
+
+
+def test_admit_4_with_the_scalar_flavours_both_dtypes():
+    for dtype in (np.float32, np.float64):
+        for flavor in (0, 2):
+            for mode in ("velocity", "polarization"):
+                check(*random_case((45, 70), dtype, 23, seed=21), mode=mode, walls="y-periodic", iterations=2,
+                      flavor=flavor, admit=4, walk=1)
+
+
 def test_grouped_walk_axis_aligned_zero_and_signed_zero_fields():
     rng = np.random.default_rng(3)
     tex = rng.random((40, 50))

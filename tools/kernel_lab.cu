@@ -14,6 +14,9 @@
 //         bits x sign flavours 0-3; static SASS counts in profiles/r1_sass_steps_grouped_walk.txt
 #include "../rlic_b200/csrc/lic_walk.cuh"
 
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -155,6 +158,133 @@ persistent_pass_kernel(const T *__restrict__ tex, const PackedField<T> *__restri
 
 // (the gather-ceiling kernel lives in lic_walk.cuh: the library exposes it as a measurement entry point)
 using rlic::gather_ceiling_kernel;
+
+// lab20 (round 2): the north star's "texture tiles staged in shared memory (TMA) with a halo of
+// half the kernel length", built to be measured rather than argued about.  f32 velocity.
+// One CTA per TW x TH tile of output pixels.  A CTA whose tile plus a halo of H = ntaps / 2 cells
+// lies inside the image stages that (TW + 2H) x (TH + 2H) window of the texture with ONE TMA
+// box copy (cp.async.bulk.tensor.2d, completion on an mbarrier) and its walkers read the
+// texture from shared memory: a walker takes at most H steps per direction, one cell each, so
+// it cannot leave the window, and it cannot meet a wall cell.  CTAs near the image border
+// (3 % of them at 4096^2) run the global-memory walk.  The field is gathered from global
+// memory in both cases.  TMA wants row strides that are multiples of 16 bytes; the padded
+// layout's pitch of nx + 2 cells is not one for nx = 4096, so the window is read from a copy of
+// the padded texture with its pitch rounded up to a multiple of four cells (a product version
+// would round the padded layout's pitch instead).
+// The step is walk_step's flavour 2 with one more piece of state: the walker's byte offset in
+// the shared window, moved by the same unit step (+-4 bytes or +-row bytes).
+template <int TW, int TH, int H> struct StagedShape {
+    static constexpr int SW = TW + 2 * H, SH = TH + 2 * H;
+    static constexpr unsigned bytes = SW * SH * sizeof(float);
+};
+
+template <int DIR, typename Taps>
+__device__ __forceinline__ float staged_half_walk(float acc, int at, unsigned sat, const float *__restrict__ tex,
+                                                  const float4 *__restrict__ field, const char *smem_tile,
+                                                  const Taps &taps, int k, const int k_end, const int pitch,
+                                                  const int srow_bytes, const bool staged)
+{
+    using F = Fp<float>;
+    using S = rlic::SignWord<float>;
+    constexpr bool kNeg = DIR < 0;
+    float fx = 0.5f, fy = 0.5f;
+    const int kb_end = k_end * 4;
+#pragma unroll 4
+    for (int kb = k * 4; kb != kb_end; kb += DIR * 4) {
+        PackedField<float> p = rlic::FieldAccess<float>::load(field, at, 0);
+        const float sgx = F::with_sign_of(1.0f, p.u), sgy = F::with_sign_of(1.0f, p.v);
+        const float ax = kNeg ? F::sub(1.0f, sgx) : F::add(1.0f, sgx);
+        const float ay = kNeg ? F::sub(1.0f, sgy) : F::add(1.0f, sgy);
+        const float remx = F::fma(ax, F::sub(0.5f, fx), fx), remy = F::fma(ay, F::sub(0.5f, fy), fy);
+        const float tx = F::abs(rlic::div_tail(remx, p.u, p.ru)), ty = F::abs(rlic::div_tail(remy, p.v, p.rv));
+        const bool x_first = tx < ty;
+        const float fy_if_x = F::fma(tx, kNeg ? -p.v : p.v, fy), fx_if_y = F::fma(ty, kNeg ? -p.u : p.u, fx);
+        const int unit = x_first ? S::unit_step_of_two(ax) : S::unit_step_of_two(ay);
+        int at2 = at + unit * (x_first ? 1 : pitch);
+        unsigned sat2 = sat + (unsigned)(unit * (x_first ? 4 : srow_bytes));
+        float fx2 = x_first ? F::fma(ax, -0.5f, 1.0f) : fx_if_y;
+        float fy2 = x_first ? fy_if_x : F::fma(ay, -0.5f, 1.0f);
+        if (!rlic::fast_path_admits<float, 3>(remx, remy, p.ru)) {
+            float pu = p.u, pv = p.v;
+            if (rlic::is_sentinel(p)) {               // border CTAs only
+                at += rlic::Sentinel<float>::decode<int>(p);
+                p = rlic::FieldAccess<float>::load(field, at, 0);
+                pu = p.u; pv = p.v;
+            }
+            if (kNeg) { pu = -pu; pv = -pv; }
+            if (pu != pu || pv != pv)
+                break;
+            const rlic::Moved<float, int> m = rlic::generic_step<float, int, true>(pu, pv, at, fx, fy, pitch);
+            const int d = m.at - at;                  // 0, +-1 or +-pitch
+            sat2 = sat + (unsigned)(d == 0 ? 0 : (d == 1 ? 4 : (d == -1 ? -4 : (d > 0 ? srow_bytes : -srow_bytes))));
+            at2 = m.at; fx2 = m.fx; fy2 = m.fy;
+        }
+        at = at2; sat = sat2; fx = fx2; fy = fy2;
+        const float t = staged ? *reinterpret_cast<const float *>(smem_tile + sat) : __ldg(tex + at);
+        acc = F::fma(taps.at_byte(kb), t, acc);
+    }
+    return acc;
+}
+
+template <int TW, int TH, int H, typename Taps>
+__global__ void __launch_bounds__(TW *TH, (TW * TH >= 1024 ? 2 : (TW * TH >= 512 ? 3 : 8)))
+staged_pass_kernel(const float *__restrict__ tex, const PackedField<float> *__restrict__ field,
+                   float *__restrict__ out, const __grid_constant__ PassGeom g,
+                   const __grid_constant__ Taps taps, const int ntaps,
+                   const __grid_constant__ CUtensorMap tmap)
+{
+    using Shape = StagedShape<TW, TH, H>;
+    extern __shared__ __align__(128) char smem_tile[];
+    __shared__ __align__(8) unsigned long long bar;
+    const unsigned tile_y = blockIdx.x / (unsigned)g.tiles_x, tile_x = blockIdx.x - tile_y * (unsigned)g.tiles_x;
+    const int x0 = (int)tile_x * TW, y0 = (int)tile_y * TH;
+    // the window [x0 - H, x0 + TW + H) x [y0 - H, y0 + TH + H) must lie inside the image
+    const bool staged = ntaps / 2 <= H && x0 >= H && y0 >= H && x0 + TW + H <= g.nx && y0 + TH + H <= g.rows;
+    const unsigned bar_addr = (unsigned)__cvta_generic_to_shared(&bar);
+    if (staged) {
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_tile);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(Shape::bytes)
+                         : "memory");
+            // coordinates: {column, buffer row}; buffer row = image row + 1 (one guard row)
+            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
+                         "[%0], [%1, {%2, %3}], [%4];"
+                         ::"r"(dst), "l"(&tmap), "r"(x0 - H), "r"(y0 - H + 1), "r"(bar_addr)
+                         : "memory");
+        }
+    }
+    const int j = x0 + (int)(threadIdx.x % TW), r = y0 + (int)(threadIdx.x / TW);
+    const bool live = j < g.nx && r < g.out_rows;
+    tex += g.pitch;
+    out += g.pitch;
+    const float4 *fcell = reinterpret_cast<const float4 *>(field) + g.pitch;
+    asm volatile("" : "+l"(tex), "+l"(fcell));
+    const int pitch = g.pitch, kmid = ntaps >> 1;
+    const int at = r * pitch + j;
+    if (staged) {
+        unsigned done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done) : "r"(bar_addr) : "memory");
+    }
+    if (!live)
+        return;
+    const unsigned sat = (unsigned)((((int)(threadIdx.x / TW) + H) * Shape::SW + (int)(threadIdx.x % TW) + H) * 4);
+    const float centre = staged ? *reinterpret_cast<const float *>(smem_tile + sat) : __ldg(tex + at);
+    float acc = Fp<float>::fma(taps.get(kmid), centre, 0.0f);
+    acc = staged_half_walk<+1>(acc, at, sat, tex, fcell, smem_tile, taps, kmid + 1, ntaps, pitch, Shape::SW * 4, staged);
+    acc = staged_half_walk<-1>(acc, at, sat, tex, fcell, smem_tile, taps, kmid - 1, -1, pitch, Shape::SW * 4, staged);
+    out[at] = acc;
+    if (j == g.j_above_to) out[r * pitch + g.nx] = acc;
+    if (j == g.j_below_to) out[r * pitch - 1] = acc;
+    if (g.lo_wall && r == g.i_below_to) out[-pitch + j] = acc;
+    if (g.hi_wall && r == g.i_above_to) out[g.rows * pitch + j] = acc;
+}
 
 struct Result { std::string name; float ms; bool same; int regs; };
 
@@ -328,7 +458,7 @@ void run_type(const char *tname, int n, int L, const char *only)
         using TP = rlic::Tune<T, true>;
         CANDW("grouped tuned vel", false, TV::walk_unroll, TV::walk_min_blocks, TV::walk_flavor, TV::admit, TV::walk);
         CANDW("grouped tuned pol", true, TP::walk_unroll, TP::walk_min_blocks, TP::walk_flavor, TP::admit, TP::walk);
-        if (sizeof(T) == 4) {
+        if constexpr (sizeof(T) == 4) {
             CANDW("grouped vel w1 f1", false, 4, 8, 1, 3, 1);
             CANDW("grouped vel w1 f2", false, 4, 8, 2, 3, 1);
             CANDW("grouped vel w3 f2", false, 4, 8, 2, 3, 3);
@@ -340,6 +470,18 @@ void run_type(const char *tname, int n, int L, const char *only)
             CANDW("grouped vel w7 f3", false, 4, 8, 3, 3, 7);
             CANDW("grouped vel w1 f0", false, 4, 8, 0, 3, 1);
             CANDW("grouped vel w7 f2 a2", false, 4, 8, 2, 2, 7);
+            // lab19 (round 2): the packed-pair step (flavour 4: FADD2 / FMUL2 / FFMA2) and the
+            // NaN-propagating three-input minimum in the admission test (admit 4)
+            CANDW("packed vel w1 f4 a3", false, 4, 8, 4, 3, 1);
+            CANDW("packed vel w1 f4 a4", false, 4, 8, 4, 4, 1);
+            CANDW("packed vel w1 f4 a4 u8", false, 8, 8, 4, 4, 1);
+            CANDW("packed vel w1 f4 a4 u2", false, 2, 8, 4, 4, 1);
+            CANDW("packed vel w3 f4 a4", false, 4, 8, 4, 4, 3);
+            CANDW("packed vel w5 f4 a4", false, 4, 8, 4, 4, 5);
+            CANDW("packed vel w9 f4 a4", false, 4, 8, 4, 4, 9);
+            CANDW("packed vel w7 f2 a4 (scalar, admit 4)", false, 4, 8, 2, 4, 7);
+            CANDW("packed pol w1 f4 a4", true, 4, 8, 4, 4, 1);
+            CANDW("packed pol w1 f0 a4 (scalar, admit 4)", true, 4, 8, 0, 4, 1);
             CANDW("grouped pol w1 f0", true, 4, 8, 0, 3, 1);
             CANDW("grouped pol w9 f0", true, 4, 8, 0, 3, 9);
             CANDW("grouped pol w1 f2", true, 4, 8, 2, 3, 1);
@@ -367,6 +509,53 @@ void run_type(const char *tname, int n, int L, const char *only)
         auto kref = rlic::lic_pass_kernel<T, false, PT, int>;
         kref<<<g.tiles_per_field, 256>>>(ptex, field, ref, g, taps, L);
         CK(cudaMemcpy(h_ref.data(), ref, cells * sizeof(T), cudaMemcpyDeviceToHost));
+    }
+    // lab20: TMA-staged texture window (f32, this image only: closed walls, 65 taps -> H = 32)
+    if constexpr (sizeof(T) == 4) if (L / 2 <= 32 && (!only || strstr("staged", only))) {
+        const int pitch4 = (n + 2 + 3) / 4 * 4;                  // row stride a multiple of 16 bytes
+        float *ttex;
+        CK(cudaMalloc(&ttex, (size_t)(n + 2) * pitch4 * sizeof(float)));
+        CK(cudaMemset(ttex, 0, (size_t)(n + 2) * pitch4 * sizeof(float)));
+        CK(cudaMemcpy2D(ttex, (size_t)pitch4 * 4, ptex, (size_t)(n + 2) * 4, (size_t)(n + 2) * 4, n + 2,
+                        cudaMemcpyDeviceToDevice));
+        PFN_cuTensorMapEncodeTiled encode = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void **)&encode, cudaEnableDefault, &qres));
+#define CANDSTAGED(NAME, TW, TH) do { \
+        using Shape = StagedShape<TW, TH, 32>; \
+        CUtensorMap tmap; \
+        const cuuint64_t gdim[2] = {(cuuint64_t)pitch4, (cuuint64_t)(n + 2)}; \
+        const cuuint64_t gstr[1] = {(cuuint64_t)pitch4 * 4}; \
+        const cuuint32_t box[2] = {Shape::SW, Shape::SH}; \
+        const cuuint32_t estr[2] = {1, 1}; \
+        CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ttex, gdim, gstr, box, estr, \
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, \
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE); \
+        if (cr != CUDA_SUCCESS) { fprintf(stderr, "cuTensorMapEncodeTiled failed: %d\n", (int)cr); break; } \
+        auto k = staged_pass_kernel<TW, TH, 32, PT>; \
+        CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Shape::bytes)); \
+        PassGeom gc = g; \
+        gc.tiles_x = (n + TW - 1) / TW; \
+        gc.tiles_per_field = gc.tiles_x * ((n + TH - 1) / TH); \
+        float best = 1e9; \
+        CK(cudaMemset(out, 0, cells * sizeof(T))); \
+        for (int r = 0; r < reps + 1; ++r) { \
+            CK(cudaEventRecord(e0)); \
+            k<<<gc.tiles_per_field, TW * TH, Shape::bytes>>>((const float *)ptex, (const PackedField<float> *)field, \
+                                                             (float *)out, gc, *(const PT *)&taps, L, tmap); \
+            CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); \
+            float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); if (r) best = fminf(best, ms); \
+        } \
+        CK(cudaGetLastError()); \
+        CK(cudaMemcpy(h_out.data(), out, cells * sizeof(T), cudaMemcpyDeviceToHost)); \
+        bool same = memcmp(h_out.data(), h_ref.data(), cells * sizeof(T)) == 0; \
+        cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, k)); \
+        results.push_back({NAME, best, same, fa.numRegs}); \
+    } while (0)
+        CANDSTAGED("staged TMA window 16x16 (80x80 f32 = 25.6 KB)", 16, 16);
+        CANDSTAGED("staged TMA window 32x16 (96x80 = 30.7 KB)", 32, 16);
+        CANDSTAGED("staged TMA window 32x32 (96x96 = 36.9 KB)", 32, 32);
+        CK(cudaFree(ttex));
     }
     //    name              TW  TH  unroll minblocks flavor admit
     CAND("u2 b8 f1 a3", 16, 16, 2, 8, 1, 3);

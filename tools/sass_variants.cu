@@ -11,6 +11,12 @@ template <typename T, bool POL, typename PT, int WALK, int FLAVOR> const void *v
     return (const void *)&lic_pass_kernel<T, POL, PT, int, kTileW, kTileH, Tn::walk_unroll, Tn::walk_min_blocks,
                                           FLAVOR, Tn::admit, true, WALK>;
 }
+template <typename T, bool POL, typename PT, int WALK, int FLAVOR, int ADMIT, int UNROLL> const void *variant_a()
+{
+    using Tn = Tune<T, POL>;
+    return (const void *)&lic_pass_kernel<T, POL, PT, int, kTileW, kTileH, UNROLL, Tn::walk_min_blocks,
+                                          FLAVOR, ADMIT, true, WALK>;
+}
 template <typename T, bool POL, typename PT> const void *shipped()
 {
     return (const void *)&lic_pass_kernel<T, POL, PT, int>;
@@ -26,6 +32,10 @@ template <typename T, bool POL, typename PT> const void *tuned_grouped()
     variant<T, POL, PT, 7, FLAVOR>(), variant<T, POL, PT, 9, FLAVOR>(), variant<T, POL, PT, 11, FLAVOR>()
 
 const void *table[] = {
+    variant_a<float, false, PT32, 1, 4, 4, 4>(), variant_a<float, false, PT32, 7, 2, 4, 4>(),
+    variant_a<float, false, PT32, 1, 4, 4, 8>(), variant_a<float, false, PT32, 3, 4, 4, 4>(),
+    variant_a<float, true, PT32, 1, 4, 4, 4>(), variant_a<float, true, PT32, 1, 0, 4, 4>(),
+    variant_a<double, false, PT64, 9, 0, 4, 4>(), variant_a<double, true, PT64, 9, 0, 4, 4>(),
     variant<float, false, PT32, 7, 4>(), variant<float, false, PT32, 5, 4>(), variant<float, false, PT32, 1, 4>(),
     variant<float, true, PT32, 1, 4>(), variant<float, true, PT32, 7, 4>(),
     shipped<float, false, PT32>(), shipped<float, true, PT32>(),
