@@ -55,18 +55,24 @@ class ClockSampler:
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
+    PERIOD_MS = 50
 
-    def __init__(self, index: int):
+    def __init__(self, index):
+        """`index`: a GPU ordinal, or a comma-separated list of them (ONE nvidia-smi process for all:
+        a poller per rank, every 20 ms, slowed the launches of eight ranks measurably); None
+        disables the sampler (ranks other than 0)."""
         self.index = index
         self.proc = None
         self.lines: list[tuple[float, str]] = []
         self.t0 = self.t1 = None
 
     def __enter__(self):
+        if self.index is None:
+            return self
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "20", "-i", str(self.index)],
+                 "-lms", str(self.PERIOD_MS), "-i", str(self.index)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -96,7 +102,7 @@ class ClockSampler:
     def summary(self) -> dict:
         sm, smax, power, reasons = [], [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        inside = [l for t, l in self.lines if self.t0 is not None and self.t0 <= t <= (self.t1 or t) + 0.03]
+        inside = [l for t, l in self.lines if self.t0 is not None and self.t0 <= t <= (self.t1 or t) + 0.06]
         where = "timed region"
         if not inside:   # region shorter than one sampling period: fall back to the whole loaded run
             inside = [l for _, l in self.lines]
@@ -114,7 +120,7 @@ class ClockSampler:
             for name, flag in zip(names, parts[4:8]):
                 if flag.lower().startswith("active"):
                     reasons.add(name)
-        if not sm:
+        if self.index is None or not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax),
                 "power_w_max": max(power), "reasons": sorted(reasons), "samples": len(sm),
@@ -413,7 +419,8 @@ def run_ours(args) -> dict:
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
           for _ in range(args.steps)]
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:
+    # one sampler for the job: rank 0 watches every GPU the job uses
+    with ClockSampler(",".join(str(i) for i in range(world)) if rank == 0 else None) as clocks:
         for _ in range(max(args.warmup, 3)):
             step()
         barrier()

@@ -80,54 +80,90 @@ struct Stream {
     cudaStream_t s = nullptr;
     ~Stream() { if (s) cudaStreamDestroy(s); }
 };
+// The library's scratch comes from PRIVATE stream-ordered pools, one per device, never from the
+// device's default pool: the device entry points run next to a host framework's own allocator
+// (torch), and a process-wide release threshold on the shared default pool would keep our
+// scratch away from it for good.  A private pool keeps freed blocks cached up to a bounded
+// threshold -- half the device's memory, or RLIC_B200_POOL_KEEP_BYTES -- so that repeated calls
+// do not pay cudaMalloc every time, and returns the rest to the driver at the next
+// synchronisation.
+cudaError_t device_pool(int device, cudaMemPool_t *pool)
+{
+    static std::mutex mu;
+    static std::vector<cudaMemPool_t> pools;
+    std::lock_guard<std::mutex> lock(mu);
+    if (device < 0)
+        return cudaErrorInvalidDevice;
+    if ((size_t)device >= pools.size())
+        pools.resize((size_t)device + 1, nullptr);
+    if (!pools[(size_t)device]) {
+        cudaMemPoolProps props{};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        cudaMemPool_t created;
+        cudaError_t e = cudaMemPoolCreate(&created, &props);
+        if (e != cudaSuccess)
+            return e;
+        uint64_t keep = 0;
+        if (const char *env = getenv("RLIC_B200_POOL_KEEP_BYTES")) {
+            keep = strtoull(env, nullptr, 10);
+        } else {
+            cudaDeviceProp dp;
+            if (cudaGetDeviceProperties(&dp, device) == cudaSuccess)
+                keep = (uint64_t)dp.totalGlobalMem / 2;
+        }
+        e = cudaMemPoolSetAttribute(created, cudaMemPoolAttrReleaseThreshold, &keep);
+        if (e != cudaSuccess) {
+            cudaMemPoolDestroy(created);
+            return e;
+        }
+        pools[(size_t)device] = created;
+    }
+    *pool = pools[(size_t)device];
+    return cudaSuccess;
+}
+
 struct DeviceBuf {
     void *p = nullptr;
     cudaStream_t s = nullptr;
     ~DeviceBuf() { if (p) cudaFreeAsync(p, s); }
+    // from the current device's private pool, ordered on `stream`
     cudaError_t alloc(size_t bytes, cudaStream_t stream)
     {
         s = stream;
-        return cudaMallocAsync(&p, bytes ? bytes : 1, stream);
+        int device = 0;
+        cudaError_t e = cudaGetDevice(&device);
+        cudaMemPool_t pool = nullptr;
+        if (e == cudaSuccess)
+            e = device_pool(device, &pool);
+        return e != cudaSuccess ? e : cudaMallocFromPoolAsync(&p, bytes ? bytes : 1, pool, stream);
+    }
+};
+
+// Waits for the streams of a host call before its buffers go: declared AFTER the DeviceBufs, so
+// that on every exit path -- early error returns included -- no kernel is still using a buffer
+// when cudaFreeAsync hands it back on another stream.
+struct StreamDrain {
+    const Stream *streams[3];
+    ~StreamDrain()
+    {
+        for (const Stream *st : streams)
+            if (st && st->s)
+                cudaStreamSynchronize(st->s);
     }
 };
 
 struct Walls { int x_left, x_right, y_left, y_right; };
 
-// Keep freed stream-ordered allocations cached in the device pool instead of
-// returning them to the OS at every synchronisation (first call per device).
-cudaError_t keep_pool_warm(int device)
-{
-    static std::mutex mu;
-    static std::vector<char> tuned;
-    std::lock_guard<std::mutex> lock(mu);
-    if ((size_t)device >= tuned.size())
-        tuned.resize((size_t)device + 1, 0);
-    if (!tuned[(size_t)device]) {
-        cudaMemPool_t pool;
-        cudaError_t e = cudaDeviceGetDefaultMemPool(&pool, device);
-        if (e != cudaSuccess)
-            return e;
-        uint64_t keep = UINT64_MAX;
-        e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        if (e != cudaSuccess)
-            return e;
-        tuned[(size_t)device] = 1;
-    }
-    return cudaSuccess;
-}
-
-cudaError_t use_device(int device)
-{
-    cudaError_t e = cudaSetDevice(device);
-    return e != cudaSuccess ? e : keep_pool_warm(device);
-}
+cudaError_t use_device(int device) { return cudaSetDevice(device); }
 
 // device entry points run on whatever device is current for the caller
 cudaError_t use_current_device()
 {
     int device = 0;
-    cudaError_t e = cudaGetDevice(&device);
-    return e != cudaSuccess ? e : keep_pool_warm(device);
+    return cudaGetDevice(&device);
 }
 
 int check_common(int64_t ny, int64_t nx, int64_t klen, int uv_mode, const Walls &w)
@@ -280,14 +316,14 @@ cudaError_t launch_one(const T *tex, const Field<T> *field, T *out, const PassGe
     if (peer.out) {   // the default arithmetic only (checked by the caller)
         if (grouped)
             rlic::lic_pass_peer_kernel<T, POL, Taps, Idx, rlic::kTileW, rlic::kTileH, Tn::walk_unroll,
-                                       Tn::walk_min_blocks, Tn::walk_flavor, Tn::admit, true, Tn::walk>
+                                       Tn::walk_min_blocks, Tn::walk_flavor, Tn::walk_admit, true, Tn::walk>
                 <<<blocks, rlic::kThreads, 0, stream>>>(tex, field, out, g, taps, ntaps, peer.out, peer.delta);
         else
             rlic::lic_pass_peer_kernel<T, POL, Taps, Idx>
                 <<<blocks, rlic::kThreads, 0, stream>>>(tex, field, out, g, taps, ntaps, peer.out, peer.delta);
     } else if (branchless && grouped)
         rlic::lic_pass_kernel<T, POL, Taps, Idx, rlic::kTileW, rlic::kTileH, Tn::walk_unroll,
-                              Tn::walk_min_blocks, Tn::walk_flavor, Tn::admit, true, Tn::walk>
+                              Tn::walk_min_blocks, Tn::walk_flavor, Tn::walk_admit, true, Tn::walk>
             <<<blocks, rlic::kThreads, 0, stream>>>(tex, field, out, g, taps, ntaps);
     else if (branchless)
         rlic::lic_pass_kernel<T, POL, Taps, Idx>
@@ -426,13 +462,14 @@ int convolve_host(const T *tex, const T *u, const T *v, int64_t nfields, int64_t
     auto band_begin = [&](int64_t b) { return std::min(ny, b * band_rows); };
 
     CUDA_TRY(use_device(device));
-    Stream io, run;
+    Stream io, run, back;   // `back` is created by the wavefront schedule only
     CUDA_TRY(cudaStreamCreateWithFlags(&io.s, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&run.s, cudaStreamNonBlocking));
     // Two padded texture buffers (the uploaded texture's doubles as the second
     // work buffer), the packed field, and dense staging for the three uploads
     // (the texture's staging is reused for the download).
     DeviceBuf d_tex, d_work, d_field, d_su, d_sv, d_st, d_flag;
+    StreamDrain drain{{&io, &run, &back}};
     CUDA_TRY(d_tex.alloc(padded_bytes, io.s));
     CUDA_TRY(d_work.alloc(padded_bytes, io.s));
     CUDA_TRY(d_field.alloc(4 * padded_bytes, io.s));
@@ -534,7 +571,6 @@ int convolve_host(const T *tex, const T *u, const T *v, int64_t nfields, int64_t
         if (is_pageable(out))
             prefault_for_write(out, bytes);
         // results leave on their own stream: the bus is full duplex, and `io` may still be uploading
-        Stream back;
         CUDA_TRY(cudaStreamCreateWithFlags(&back.s, cudaStreamNonBlocking));
         for (int64_t b = 0; b < nbands; ++b) {
             const int64_t rb = band_begin(b), re = band_begin(b + 1);

@@ -178,8 +178,8 @@ int tuned(const T *tex, const T *field, T *out, const PassGeom &g, const Taps &t
 {
     using Tn = rlic::Tune<T, POL>;
     if (branchless && walk) {
-        if (wide) run_pass<T, POL, Taps, long long, Tn::walk_flavor, Tn::admit, true, Tn::walk>(tex, field, out, g, taps, ntaps, blocks);
-        else run_pass<T, POL, Taps, int, Tn::walk_flavor, Tn::admit, true, Tn::walk>(tex, field, out, g, taps, ntaps, blocks);
+        if (wide) run_pass<T, POL, Taps, long long, Tn::walk_flavor, Tn::walk_admit, true, Tn::walk>(tex, field, out, g, taps, ntaps, blocks);
+        else run_pass<T, POL, Taps, int, Tn::walk_flavor, Tn::walk_admit, true, Tn::walk>(tex, field, out, g, taps, ntaps, blocks);
     } else if (branchless) {
         if (wide) run_pass<T, POL, Taps, long long, Tn::flavor, Tn::admit>(tex, field, out, g, taps, ntaps, blocks);
         else run_pass<T, POL, Taps, int, Tn::flavor, Tn::admit>(tex, field, out, g, taps, ntaps, blocks);
@@ -240,7 +240,7 @@ void run_pass_peer(const T *tex, const T *field, T *out, const PassGeom &g, cons
     if (walk)
         launch(blocks, rlic::kThreads, [&] {
             rlic::lic_pass_peer_kernel<T, POL, Taps, int, rlic::kTileW, rlic::kTileH, Tn::walk_unroll,
-                                       Tn::walk_min_blocks, Tn::walk_flavor, Tn::admit, true, Tn::walk>(tex, f, out, g, taps, ntaps,
+                                       Tn::walk_min_blocks, Tn::walk_flavor, Tn::walk_admit, true, Tn::walk>(tex, f, out, g, taps, ntaps,
                                                                                     peer_out, peer_delta);
         });
     else

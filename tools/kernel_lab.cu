@@ -456,8 +456,8 @@ void run_type(const char *tname, int n, int L, const char *only)
     {
         using TV = rlic::Tune<T, false>;
         using TP = rlic::Tune<T, true>;
-        CANDW("grouped tuned vel", false, TV::walk_unroll, TV::walk_min_blocks, TV::walk_flavor, TV::admit, TV::walk);
-        CANDW("grouped tuned pol", true, TP::walk_unroll, TP::walk_min_blocks, TP::walk_flavor, TP::admit, TP::walk);
+        CANDW("grouped tuned vel", false, TV::walk_unroll, TV::walk_min_blocks, TV::walk_flavor, TV::walk_admit, TV::walk);
+        CANDW("grouped tuned pol", true, TP::walk_unroll, TP::walk_min_blocks, TP::walk_flavor, TP::walk_admit, TP::walk);
         if constexpr (sizeof(T) == 4) {
             CANDW("grouped vel w1 f1", false, 4, 8, 1, 3, 1);
             CANDW("grouped vel w1 f2", false, 4, 8, 2, 3, 1);
@@ -480,6 +480,13 @@ void run_type(const char *tname, int n, int L, const char *only)
             CANDW("packed vel w5 f4 a4", false, 4, 8, 4, 4, 5);
             CANDW("packed vel w9 f4 a4", false, 4, 8, 4, 4, 9);
             CANDW("packed vel w7 f2 a4 (scalar, admit 4)", false, 4, 8, 2, 4, 7);
+            CANDW("packed vel w7 f2 a4 u8 (scalar)", false, 8, 8, 2, 4, 7);
+            CANDW("packed vel w5 f2 a4 (scalar)", false, 4, 8, 2, 4, 5);
+            CANDW("packed vel w3 f2 a4 (scalar)", false, 4, 8, 2, 4, 3);
+            CANDW("packed vel w7 f2 a4 b7 (scalar)", false, 4, 7, 2, 4, 7);
+            CANDW("packed vel w7 f2 a4 b6 (scalar, 40 regs)", false, 4, 6, 2, 4, 7);
+            CANDW("packed vel w7 f1 a4 (scalar)", false, 4, 8, 1, 4, 7);
+            CANDW("packed vel w7 f0 a4 (scalar)", false, 4, 8, 0, 4, 7);
             CANDW("packed pol w1 f4 a4", true, 4, 8, 4, 4, 1);
             CANDW("packed pol w1 f0 a4 (scalar, admit 4)", true, 4, 8, 0, 4, 1);
             CANDW("grouped pol w1 f0", true, 4, 8, 0, 3, 1);

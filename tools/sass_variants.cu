@@ -9,7 +9,7 @@ template <typename T, bool POL, typename PT, int WALK, int FLAVOR> const void *v
 {
     using Tn = Tune<T, POL>;
     return (const void *)&lic_pass_kernel<T, POL, PT, int, kTileW, kTileH, Tn::walk_unroll, Tn::walk_min_blocks,
-                                          FLAVOR, Tn::admit, true, WALK>;
+                                          FLAVOR, Tn::walk_admit, true, WALK>;
 }
 template <typename T, bool POL, typename PT, int WALK, int FLAVOR, int ADMIT, int UNROLL> const void *variant_a()
 {
