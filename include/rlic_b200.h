@@ -139,6 +139,11 @@ int64_t rlic_b200_launch_count(void);
  * buffers of 2^31 cells or more (a 46340 x 46340 image). */
 void rlic_b200_debug_force_wide_index(int on);
 
+/* Testing hook: 0 keeps passes over small images (at most 148 x 2048 pixels) on the
+ * one-thread-per-pixel kernel instead of the two-warps-per-pixel one that halves their latency
+ * (lic_pass_pair_kernel, lic_walk.cuh).  Same bits either way; default 1. */
+void rlic_b200_debug_small_image_kernel(int on);
+
 /* Testing hook (host code only, no GPU needed): what the padded layout puts in
  * cell `cell` of the buffer of the slab {row0, nrows, halo_lo, halo_hi} of an
  * ny x nx image: out[0] = 1 for a pixel; otherwise a wall cell with out[1] = 1

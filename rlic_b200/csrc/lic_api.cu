@@ -9,6 +9,8 @@
 #include "lic_walk.cuh"
 #include "host_staging.h"
 
+#include <nvtx3/nvToolsExt.h>   // header-only: ranges show up in Nsight Systems / ncu --nvtx, cost nothing otherwise
+
 #include <atomic>
 #include <climits>
 #include <cstdarg>
@@ -29,6 +31,7 @@ thread_local std::string tls_error;
 thread_local int tls_device = 0;
 std::atomic<int64_t> g_launches{0};
 std::atomic<int> g_force_wide{0};   // testing hook: use 64-bit element indices for any size
+std::atomic<int> g_small_images{1}; // testing hook: 0 keeps small passes on the one-thread-per-pixel kernel
 // The three choices a call can make (include/rlic_b200.h): which reference build to reproduce,
 // which formulation of the pass kernels, how the host path orders its launches.  Each has a
 // process-wide DEFAULT (the atomics: set once at start-up, e.g. from the environment) and a
@@ -156,6 +159,12 @@ struct StreamDrain {
 };
 
 struct Walls { int x_left, x_right, y_left, y_right; };
+
+// NVTX range over a scope (ranges around uploads / passes / halo / downloads)
+struct Range {
+    explicit Range(const char *name) { nvtxRangePushA(name); }
+    ~Range() { nvtxRangePop(); }
+};
 
 cudaError_t use_device(int device) { return cudaSetDevice(device); }
 
@@ -338,13 +347,66 @@ cudaError_t launch_one(const T *tex, const Field<T> *field, T *out, const PassGe
 
 // One pass over buffer rows [first_row, first_row + out_rows) of `nfields`
 // fields.  tex, field, out: padded buffers of geometry g.
+// Whether a pass is small enough for the two-warps-per-pixel kernel (lic_pass_pair_kernel):
+// too few pixels to fill the GPU, parked samples that fit in shared memory, taps in the
+// parameter block, 32-bit cell indices, the default arithmetic.
+template <typename T>
+bool pair_kernel_fits(const PassGeom &g, int64_t nfields, int64_t out_rows, const TapSet<T> &taps)
+{
+    const int64_t kmid = taps.ntaps / 2;
+    return g_small_images.load(std::memory_order_relaxed) != 0 && taps.in_param && kmid >= 1 &&
+           out_rows * g.nx * nfields <= rlic::kPairMaxPixels &&
+           kmid * rlic::kPairPixels * (int64_t)sizeof(T) <= rlic::kPairSmemBytes &&
+           g.field_stride < (int64_t)INT_MAX && g_force_wide.load(std::memory_order_relaxed) == 0 &&
+           effective_arithmetic() == RLIC_B200_ARITH_FMA_BRANCHLESS;
+}
+
+template <typename T, bool POL>
+cudaError_t launch_pair(const T *tex, const Field<T> *field, T *out, PassGeom g, int64_t nfields,
+                        int64_t out_rows, const TapSet<T> &taps, T *dense_out, cudaStream_t stream)
+{
+    using PT = rlic::ParamTaps<T, TapSet<T>::kMaxParam>;
+    auto kernel = rlic::lic_pass_pair_kernel<T, POL, PT, int>;
+    static std::once_flag once;
+    static cudaError_t attr = cudaSuccess;
+    std::call_once(once, [&] {
+        attr = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rlic::kPairSmemBytes);
+    });
+    if (attr != cudaSuccess)
+        return attr;
+    g.tiles_x = (g.nx + rlic::kPairTileW - 1) / rlic::kPairTileW;
+    g.tiles_per_field = g.tiles_x * (int)((out_rows + rlic::kPairTileH - 1) / rlic::kPairTileH);
+    const size_t smem = (size_t)(taps.ntaps / 2) * rlic::kPairPixels * sizeof(T);
+    kernel<<<(unsigned)(g.tiles_per_field * nfields), rlic::kPairThreads, smem, stream>>>(
+        tex, field, out, g, taps.param, taps.ntaps, dense_out);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+// `dense_out`: when not null and the pass runs on the small-image kernel, the results go there
+// (dense rows, as rlic_b200_slab_unpad_texture would leave them) instead of the padded `out`,
+// and *wrote_dense is set; the caller then skips its un-padding launch.
 template <typename T>
 int launch_pass(const T *tex, const Field<T> *field, T *out, PassGeom g, int64_t nfields,
                 int64_t first_row, int64_t out_rows, int uv_mode, const TapSet<T> &taps,
-                cudaStream_t stream, const PeerTarget<T> &peer = PeerTarget<T>{})
+                cudaStream_t stream, const PeerTarget<T> &peer = PeerTarget<T>{}, T *dense_out = nullptr,
+                bool *wrote_dense = nullptr)
 {
+    if (wrote_dense)
+        *wrote_dense = false;
     if (out_rows <= 0 || g.nx <= 0 || nfields <= 0)
         return RLIC_B200_OK;
+    if (!peer.out && pair_kernel_fits<T>(g, nfields, out_rows, taps)) {
+        g.first_row = (int)first_row;
+        g.out_rows = (int)out_rows;
+        T *dense = (dense_out && first_row == 0 && out_rows == g.rows) ? dense_out : nullptr;
+        CUDA_TRY(uv_mode == RLIC_B200_POLARIZATION
+                     ? (launch_pair<T, true>(tex, field, out, g, nfields, out_rows, taps, dense, stream))
+                     : (launch_pair<T, false>(tex, field, out, g, nfields, out_rows, taps, dense, stream)));
+        if (wrote_dense)
+            *wrote_dense = dense != nullptr;
+        return RLIC_B200_OK;
+    }
     g.first_row = (int)first_row;
     g.out_rows = (int)out_rows;
     g.tiles_x = (g.nx + rlic::kTileW - 1) / rlic::kTileW;
@@ -430,6 +492,7 @@ int convolve_host(const T *tex, const T *u, const T *v, int64_t nfields, int64_t
                   const T *kernel, int64_t klen, int uv_mode, const Walls &w,
                   int64_t iterations, T *out, int device, int *texture_has_negative = nullptr)
 {
+    Range whole("rlic_b200 convolve (host)");
     if (texture_has_negative)
         *texture_has_negative = 0;
     if (int rc = check_common(ny, nx, klen, uv_mode, w))
@@ -514,6 +577,7 @@ int convolve_host(const T *tex, const T *u, const T *v, int64_t nfields, int64_t
 
     // One band of the inputs: u, v -> packed field, texture -> padded buffer, all on `io`.
     auto enqueue_band_upload = [&](int64_t b) -> int {
+        Range r("upload band: u, v -> packed field; texture -> padded");
         const int64_t rb = band_begin(b), re = band_begin(b + 1);
         const size_t off = (size_t)rb * (size_t)nx * (size_t)nfields;
         const size_t n = (size_t)(re - rb) * (size_t)nx * (size_t)nfields;
@@ -629,6 +693,7 @@ int convolve_host(const T *tex, const T *u, const T *v, int64_t nfields, int64_t
         result = dst;
     }
 
+    Range downloads("downloads behind the last pass");
     // ---- downloads, trailing behind the last pass ----
     // the passes are running: get a pageable destination's pages ready meanwhile
     if (is_pageable(out))
@@ -656,6 +721,7 @@ int run_device(const T *d_tex, const Field<T> *d_field, int64_t ny, int64_t nx, 
                int uv_mode, const Walls &w, int64_t iterations, T *d_out, cudaStream_t s,
                int64_t nfields = 1)
 {
+    Range whole("rlic_b200 passes (device)");
     const PassGeom g = make_geometry(ny, nx, Slab{0, ny, 0, 0}, w);
     const size_t padded_bytes = (size_t)g.field_stride * (size_t)nfields * sizeof(T);
     CUDA_TRY(use_current_device());
@@ -668,14 +734,18 @@ int run_device(const T *d_tex, const Field<T> *d_field, int64_t ny, int64_t nx, 
     CUDA_TRY(launch_pad<T>(d_tex, static_cast<T *>(in.p), g, 0, ny, nfields, nullptr, s));
     const T *src = static_cast<const T *>(in.p);
     T *dst = static_cast<T *>(a.p);
+    bool wrote_dense = false;
     for (int64_t it = 0; it < iterations; ++it) {
         // pass 1: in -> a; pass 2: a -> b; pass 3: b -> a; ...
         dst = static_cast<T *>(it == 0 ? a.p : ((it & 1) ? b.p : a.p));
-        if (int rc = launch_pass<T>(src, d_field, dst, g, nfields, 0, ny, uv_mode, taps, s))
+        // a small image's last pass writes the dense result itself (no un-padding launch)
+        if (int rc = launch_pass<T>(src, d_field, dst, g, nfields, 0, ny, uv_mode, taps, s, PeerTarget<T>{},
+                                    it == iterations - 1 ? d_out : nullptr, &wrote_dense))
             return rc;
         src = dst;
     }
-    CUDA_TRY(launch_unpad<T>(dst, d_out, g, 0, ny, nfields, s));
+    if (!wrote_dense)
+        CUDA_TRY(launch_unpad<T>(dst, d_out, g, 0, ny, nfields, s));
     return RLIC_B200_OK;
 }
 
@@ -1103,6 +1173,8 @@ void rlic_b200_result_free(void *block)
 }
 
 void rlic_b200_debug_force_wide_index(int on) { g_force_wide.store(on ? 1 : 0); }
+
+void rlic_b200_debug_small_image_kernel(int on) { g_small_images.store(on ? 1 : 0); }
 
 int rlic_b200_set_device(int device)
 {

@@ -22,6 +22,19 @@ from golden_cases import CASES, as_spec, expected, load
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True, params=["small-image kernel", "one thread per pixel"])
+def both_pass_kernels(request):
+    """Passes over small images run on the two-warps-per-pixel kernel (lic_pass_pair_kernel);
+    every test of this file runs a second time with that kernel switched off, so that the
+    edge cases -- nearly all of them small images -- reach both kernels."""
+    _core.lib.rlic_b200_debug_small_image_kernel(1 if request.param == "small-image kernel" else 0)
+    try:
+        yield
+    finally:
+        _core.lib.rlic_b200_debug_small_image_kernel(1)
+
+
 WALLS = {
     "closed": (("closed", "closed"), ("closed", "closed")),
     "periodic": (("periodic", "periodic"), ("periodic", "periodic")),
