@@ -402,10 +402,10 @@ def run_ours(args) -> dict:
     else:
         from rlic_b200.sharded import ShardedConvolver
 
-        # RLIC_B200_EXCHANGE=peer: the halo exchange fused into the edge-strip kernels (peer
-        # stores over NVLink) instead of NCCL messages; opt-in until it has run on hardware
+        # the halo exchange fused into the edge-strip kernels (peer stores over NVLink, counters in
+        # the neighbours' memory); RLIC_B200_EXCHANGE=nccl selects point-to-point NCCL messages
         sc = ShardedConvolver(N_SIDE * world, N_SIDE, kernel=kernel, boundaries="closed",
-                              exchange=os.environ.get("RLIC_B200_EXCHANGE", "nccl"))
+                              exchange=os.environ.get("RLIC_B200_EXCHANGE", "peer"))
         sc.set_field(d_u, d_v)
 
         def step(events=None):

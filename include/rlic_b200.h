@@ -434,6 +434,32 @@ int rlic_b200_pass_slab_f64(const double *d_texture, const double *d_field, doub
                             void *stream);
 
 /*
+ * HISTOGRAM EQUALISATION of a result -- the usual step between a line integral convolution and
+ * its rendering.  rLIC only declares it (`equalize_histogram_f32 / _f64(image, nbins)`,
+ * /root/reference/src/rlic/_core.pyi:30-37: no implementation in src/lib.rs; upstream moved it
+ * to its sister project `ahe`, /root/reference/README.md:19-23), so the semantics are this
+ * library's own, every operation one IEEE operation in the image's type:
+ *
+ *     lo, hi = minimum, maximum over the pixels that are not NaN;  w = hi - lo
+ *     bin(x) = min(nbins - 1, (int) floor(((x - lo) / w) * nbins))          (0 when w == 0)
+ *     cdf[b] = (number of non-NaN pixels in bins 0..b) / (number of non-NaN pixels)
+ *     out(x) = cdf[bin(x)],  NaN where x is NaN
+ *
+ * Values are expected finite or NaN; 1 <= nbins <= 2^24.  The `_device_` form works on device
+ * memory in place of a host round trip (enqueued on `stream`, scratch from the library's
+ * pool); the plain form takes host pointers.  The adaptive variants the reference's stub also
+ * lists (sliding tile, tile interpolation: _core.pyi:38-57) are not built.
+ */
+int rlic_b200_equalize_histogram_device_f32(const float *d_image, int64_t ny, int64_t nx,
+                                            int64_t nbins, float *d_out, void *stream);
+int rlic_b200_equalize_histogram_device_f64(const double *d_image, int64_t ny, int64_t nx,
+                                            int64_t nbins, double *d_out, void *stream);
+int rlic_b200_equalize_histogram_f32(const float *image, int64_t ny, int64_t nx, int64_t nbins,
+                                     float *out);
+int rlic_b200_equalize_histogram_f64(const double *image, int64_t ny, int64_t nx, int64_t nbins,
+                                     double *out);
+
+/*
  * MEASUREMENT — the gather ceiling ("an L2 gather peak measured by the
  * build's own microbenchmark, same access count, straight-line walkers").  One launch performs
  * the loads of a pass -- per step one field record and one texture value at the walker's

@@ -14,6 +14,7 @@ __all__ = [
     "convolve_batch",
     "convolve_sharded",
     "effective_options",
+    "equalize_histogram",
     "get_arithmetic",
     "get_schedule",
     "get_walk",
@@ -25,4 +26,4 @@ __all__ = [
 
 from rlic_b200._core import (effective_options, get_arithmetic, get_schedule, get_walk, options,
                              set_arithmetic, set_schedule, set_walk)
-from rlic_b200._lib import convolve, convolve_batch, convolve_sharded
+from rlic_b200._lib import convolve, convolve_batch, convolve_sharded, equalize_histogram

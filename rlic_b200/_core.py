@@ -141,6 +141,11 @@ def _load() -> ctypes.CDLL:
             raise ImportError(f"RLIC_B200_ARITHMETIC={requested!r}: expected one of {sorted(ARITHMETICS)}")
         cdll.rlic_b200_set_arithmetic(ARITHMETICS[requested])
     for sfx, real in (("f32", ctypes.c_float), ("f64", ctypes.c_double)):
+        pr = ctypes.POINTER(real)
+        eq = getattr(cdll, f"rlic_b200_equalize_histogram_{sfx}")
+        eq.argtypes, eq.restype = [pr, _i64, _i64, _i64, pr], _int
+        eqd = getattr(cdll, f"rlic_b200_equalize_histogram_device_{sfx}")
+        eqd.argtypes, eqd.restype = [_vp, _i64, _i64, _i64, _vp, _vp], _int
         for name, argtypes in _signatures(real).items():
             fn = getattr(cdll, f"rlic_b200_{name}_{sfx}")
             fn.argtypes = argtypes
@@ -423,6 +428,29 @@ def convolve_batch(textures, uv, kernel, boundaries, iterations=1, devices=None,
     else:
         check(getattr(lib, f"rlic_b200_convolve_batch_{sfx}")(*args))
     return out
+
+
+def _equalize(sfx: str, real, image, nbins: int) -> np.ndarray:
+    dtype = np.dtype(real)
+    image = _as_image("image", image, dtype, 2)
+    if not isinstance(nbins, (int, np.integer)) or isinstance(nbins, bool):
+        raise TypeError(f"argument 'nbins': expected an int, got {type(nbins).__name__}")
+    ny, nx = image.shape
+    out = new_result((ny, nx), dtype)
+    p = ctypes.POINTER(real)
+    check(getattr(lib, f"rlic_b200_equalize_histogram_{sfx}")(
+        image.ctypes.data_as(p), ny, nx, int(nbins), out.ctypes.data_as(p)))
+    return out
+
+
+def equalize_histogram_f32(image, nbins):
+    """The reference's stub `rlic._core.equalize_histogram_f32(image, nbins)` (_core.pyi:30-33),
+    with the semantics of include/rlic_b200.h; runs on the GPU."""
+    return _equalize("f32", ctypes.c_float, image, nbins)
+
+
+def equalize_histogram_f64(image, nbins):
+    return _equalize("f64", ctypes.c_double, image, nbins)
 
 
 def convolve_f32(texture, uv, kernel, boundaries, iterations=1, *, check_texture=False):

@@ -11,6 +11,7 @@ from __future__ import annotations
 __all__ = [
     "convolve",
     "convolve_batch",
+    "equalize_histogram",
 ]
 
 from typing import TYPE_CHECKING
@@ -290,3 +291,26 @@ def convolve_sharded(
                               devices=devices)
     mc.set_field(u, v)
     return mc.convolve(texture, iterations)
+
+
+def equalize_histogram(image, /, *, nbins: int = 256):
+    """Histogram equalisation of a 2D float32 / float64 image on the GPU: the usual step between
+    a line integral convolution and its rendering (extension: rLIC only declares the operation,
+    ``rlic._core.equalize_histogram_f32/_f64(image, nbins)``, and points to its sister project
+    ``ahe`` for an implementation).
+
+    Every pixel is replaced by the fraction of the (non-NaN) pixels that fall into its own or a
+    lower one of ``nbins`` equal-width bins between the image's minimum and maximum; NaN pixels
+    stay NaN.  Returns a new array of the image's dtype with values in (0, 1].  The exact
+    arithmetic is stated in ``include/rlic_b200.h``.
+    """
+    if not isinstance(image, np.ndarray) or image.dtype not in _SUPPORTED_DTYPES:
+        raise TypeError(f"Expected a float32 or float64 numpy array, got {getattr(image, 'dtype', type(image))}")
+    if image.ndim != 2:
+        raise ValueError(f"Expected an image with exactly two dimensions. Got image.ndim={image.ndim}")
+    if isinstance(nbins, bool) or not isinstance(nbins, (int, np.integer)) or not 1 <= nbins <= 1 << 24:
+        raise ValueError(f"Invalid number of bins: {nbins!r}. Expected an integer between 1 and 2**24.")
+    if image.size == 0:
+        return image.copy()
+    run = _core.equalize_histogram_f32 if image.dtype == np.dtype("float32") else _core.equalize_histogram_f64
+    return run(image, int(nbins))

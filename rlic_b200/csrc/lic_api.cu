@@ -7,6 +7,7 @@
 // point fails.
 #include "../../include/rlic_b200.h"
 #include "lic_walk.cuh"
+#include "lic_equalize.cuh"
 #include "host_staging.h"
 
 #include <nvtx3/nvToolsExt.h>   // header-only: ranges show up in Nsight Systems / ncu --nvtx, cost nothing otherwise
@@ -1011,6 +1012,66 @@ int convolve_batch(const T *tex, const T *u, const T *v, int64_t nfields, int64_
     return RLIC_B200_OK;
 }
 
+template <typename T>
+int equalize_device(const T *d_image, int64_t ny, int64_t nx, int64_t nbins, T *d_out, cudaStream_t s)
+{
+    if (ny < 0 || nx < 0)
+        return fail(RLIC_B200_EINVAL, "negative image size %lld x %lld", (long long)ny, (long long)nx);
+    if (nbins < 1 || nbins > ((int64_t)1 << 24))
+        return fail(RLIC_B200_EINVAL, "nbins must be between 1 and 2^24, got %lld", (long long)nbins);
+    const long long n = (long long)ny * nx;
+    if (n == 0)
+        return RLIC_B200_OK;
+    if (!d_image || !d_out)
+        return fail(RLIC_B200_EINVAL, "null pointer argument");
+    Range whole("rlic_b200 equalize_histogram");
+    CUDA_TRY(use_current_device());
+    // scratch: extrema and count, 64-bit counts per bin, the cumulative distribution
+    DeviceBuf scratch;
+    const size_t hist_off = 64, cdf_off = hist_off + sizeof(unsigned long long) * (size_t)nbins;
+    CUDA_TRY(scratch.alloc(cdf_off + sizeof(T) * (size_t)nbins, s));
+    char *base = static_cast<char *>(scratch.p);
+    auto *st = reinterpret_cast<rlic::EqualizeScratch *>(base);
+    auto *hist = reinterpret_cast<unsigned long long *>(base + hist_off);
+    T *cdf = reinterpret_cast<T *>(base + cdf_off);
+    const unsigned blocks = stream_blocks(n);
+    rlic::equalize_init_kernel<<<stream_blocks(nbins), 256, 0, s>>>(st, hist, nbins);
+    rlic::equalize_extrema_kernel<T><<<blocks, 256, 0, s>>>(d_image, n, st);
+    rlic::equalize_histogram_kernel<T><<<blocks, 256, 0, s>>>(d_image, n, st, hist, nbins);
+    rlic::equalize_cdf_kernel<T><<<1, 1024, 0, s>>>(hist, nbins, st, cdf);
+    rlic::equalize_map_kernel<T><<<blocks, 256, 0, s>>>(d_image, n, st, cdf, nbins, d_out);
+    g_launches.fetch_add(5, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    return RLIC_B200_OK;
+}
+
+template <typename T>
+int equalize_host(const T *image, int64_t ny, int64_t nx, int64_t nbins, T *out, int device)
+{
+    if (ny < 0 || nx < 0)
+        return fail(RLIC_B200_EINVAL, "negative image size %lld x %lld", (long long)ny, (long long)nx);
+    const size_t bytes = (size_t)ny * (size_t)nx * sizeof(T);
+    if (bytes == 0)
+        return RLIC_B200_OK;
+    if (!image || !out)
+        return fail(RLIC_B200_EINVAL, "null pointer argument");
+    CUDA_TRY(use_device(device));
+    Stream st;
+    CUDA_TRY(cudaStreamCreateWithFlags(&st.s, cudaStreamNonBlocking));
+    DeviceBuf d_in, d_out;
+    StreamDrain drain{{&st, nullptr, nullptr}};
+    CUDA_TRY(d_in.alloc(bytes, st.s));
+    CUDA_TRY(d_out.alloc(bytes, st.s));
+    const HostToDevice job{d_in.p, image, bytes};
+    CUDA_TRY(upload(&job, 1, st.s));
+    if (int rc = equalize_device<T>(static_cast<const T *>(d_in.p), ny, nx, nbins, static_cast<T *>(d_out.p), st.s))
+        return rc;
+    if (is_pageable(out))
+        prefault_for_write(out, bytes);
+    CUDA_TRY(cudaMemcpyAsync(out, d_out.p, bytes, cudaMemcpyDeviceToHost, st.s));
+    CUDA_TRY(cudaStreamSynchronize(st.s));
+    return RLIC_B200_OK;
+}
 }  // namespace
 
 extern "C" {
@@ -1383,6 +1444,23 @@ RLIC_DEFINE_ROWS(double, f64)
     }
 RLIC_DEFINE_PEER(float, f32)
 RLIC_DEFINE_PEER(double, f64)
+
+// ---- histogram equalisation of a result (semantics: lic_equalize.cuh) ----
+#define RLIC_DEFINE_EQUALIZE(T, sfx)                                                             \
+    int rlic_b200_equalize_histogram_device_##sfx(const T *d_image, int64_t ny, int64_t nx,      \
+                                                  int64_t nbins, T *d_out, void *stream)         \
+    {                                                                                            \
+        tls_error.clear();                                                                       \
+        return equalize_device<T>(d_image, ny, nx, nbins, d_out, static_cast<cudaStream_t>(stream)); \
+    }                                                                                            \
+    int rlic_b200_equalize_histogram_##sfx(const T *image, int64_t ny, int64_t nx, int64_t nbins, \
+                                           T *out)                                               \
+    {                                                                                            \
+        tls_error.clear();                                                                       \
+        return equalize_host<T>(image, ny, nx, nbins, out, tls_device);                          \
+    }
+RLIC_DEFINE_EQUALIZE(float, f32)
+RLIC_DEFINE_EQUALIZE(double, f64)
 
 // ---- measurement: the gather ceiling of the memory system for the walk's access pattern ----
 // ("an L2 gather peak measured by the build's own microbenchmark, same

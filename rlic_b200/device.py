@@ -12,7 +12,7 @@ used for device memory and streams only.
 
 from __future__ import annotations
 
-__all__ = ["PackedField", "convolve_device", "convolve_device_batch", "pack_field"]
+__all__ = ["PackedField", "convolve_device", "convolve_device_batch", "equalize_histogram_device", "pack_field"]
 
 import ctypes
 from dataclasses import dataclass
@@ -187,5 +187,27 @@ def convolve_device_batch(textures: torch.Tensor, u: torch.Tensor, v: torch.Tens
             textures.data_ptr(), u.data_ptr(), v.data_ptr(), nf, ny, nx,
             taps.ctypes.data_as(ctypes.POINTER(real)), taps.size, mode, *walls, int(iterations),
             out.data_ptr(), _stream_handle(stream))
+    _core.check(rc)
+    return out
+
+
+def equalize_histogram_device(image: torch.Tensor, *, nbins: int = 256, out: torch.Tensor | None = None,
+                              stream=None) -> torch.Tensor:
+    """``rlic_b200.equalize_histogram`` for a CUDA tensor (e.g. the result of ``convolve_device``,
+    without a host round trip): four streaming kernels on ``stream``; returns a new tensor or
+    ``out``.  Semantics: ``include/rlic_b200.h``."""
+    image, out = _as_tensor(image), _as_tensor(out)
+    _check_image("image", image)
+    sfx, _, _ = _kind(image)
+    if isinstance(nbins, bool) or not isinstance(nbins, (int, np.integer)) or not 1 <= nbins <= 1 << 24:
+        raise ValueError(f"Invalid number of bins: {nbins!r}. Expected an integer between 1 and 2**24.")
+    if out is None:
+        out = torch.empty_like(image)
+    else:
+        _check_image("out", out, image)
+    ny, nx = image.shape
+    with torch.cuda.device(image.device):
+        rc = getattr(_core.lib, f"rlic_b200_equalize_histogram_device_{sfx}")(
+            image.data_ptr(), ny, nx, int(nbins), out.data_ptr(), _stream_handle(stream))
     _core.check(rc)
     return out

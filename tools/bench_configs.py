@@ -53,6 +53,41 @@ def time_device(w, reps=5):
     return a.elapsed_time(b) / reps
 
 
+def time_device_abi(w, reps=200):
+    """Small images: the same device call through the raw C ABI (rlic_b200_convolve_packed_*) with
+    its arguments prepared once, so that what is timed is the library and the GPU rather than
+    the Python wrapper's per-call validation (tens of microseconds, more than the kernels)."""
+    dev = torch.device("cuda", 0)
+    tex = torch.from_numpy(np.ascontiguousarray(w.texture)).to(dev)
+    u = torch.from_numpy(np.ascontiguousarray(w.u)).to(dev)
+    v = torch.from_numpy(np.ascontiguousarray(w.v)).to(dev)
+    field = pack_field(u, v, boundaries=w.boundaries)
+    out = torch.empty_like(tex)
+    sfx, real = ("f32", ctypes.c_float) if w.texture.dtype == np.float32 else ("f64", ctypes.c_double)
+    from rlic_b200._boundaries import BoundarySet
+
+    bs = BoundarySet.from_spec(w.boundaries)
+    walls = _core.wall_codes((bs.x, bs.y))
+    taps = np.ascontiguousarray(w.kernel)
+    fn = getattr(_core.lib, f"rlic_b200_convolve_packed_{sfx}")
+    ny, nx = w.texture.shape
+    args = (tex.data_ptr(), field.data.data_ptr(), ny, nx, taps.ctypes.data_as(ctypes.POINTER(real)), taps.size,
+            _core.mode_code(w.uv_mode), *walls, w.iterations, out.data_ptr(),
+            int(torch.cuda.current_stream().cuda_stream))
+    for _ in range(10):
+        _core.check(fn(*args))
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    a.record()
+    for _ in range(reps):
+        fn(*args)
+    b.record()
+    enqueue_us = (time.perf_counter() - t0) / reps * 1e6
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps, enqueue_us
+
+
 def time_host(w, reps=3):
     kw = w.kwargs()
     pin = lambda x: torch.from_numpy(np.ascontiguousarray(x)).pin_memory().numpy()  # noqa: E731
@@ -106,7 +141,11 @@ def main():
     want = set(args.configs.split(","))
     if "c1" in want:
         w = workloads.readme_example()
-        report("c1", w, time_device(w, 20), time_host(w, 20))
+        abi_ms, enqueue_us = time_device_abi(w)
+        report("c1", w, time_device(w, 20), time_host(w, 20),
+               {"device_ms_raw_abi": abi_ms, "host_enqueue_us_per_call_raw_abi": enqueue_us,
+                "note": "device_ms goes through the Python wrapper (its per-call validation outlasts the kernels); "
+                        "device_ms_raw_abi is the same call through ctypes with prepared arguments"})
     if "c2" in want:
         w = workloads.vortex_noise(4096, iterations=5)
         report("c2", w, time_device(w), time_host(w))
