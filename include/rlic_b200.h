@@ -54,7 +54,7 @@ extern "C" {
 #define RLIC_B200_PERIODIC 1
 
 /* ABI version of this header; bumped on any signature change. */
-#define RLIC_B200_ABI_VERSION 3
+#define RLIC_B200_ABI_VERSION 4
 int rlic_b200_abi_version(void);
 
 /* Message of the last failure on the calling thread ("" if none). */
@@ -123,6 +123,30 @@ int rlic_b200_get_walk(void);
 int rlic_b200_set_thread_options(int arithmetic, int schedule, int walk);
 void rlic_b200_get_thread_options(int *arithmetic, int *schedule, int *walk);
 void rlic_b200_get_effective_options(int *arithmetic, int *schedule, int *walk);
+
+/* What the passes of a call after its first do.  Which pixels a streamline visits depends on
+ * the vector field, the mode and the boundaries -- never on the texture (lib.rs:305-362; the
+ * texture only enters the accumulation, :353-360) -- and the reference hands the same u, v to
+ * every iteration (lib.rs:432-440), so every pass of a call walks the same paths.
+ *   RLIC_B200_PATHS_REPLAY     (default) the first pass of a call with iterations >= 2 records,
+ *                              per pixel and step, which way its walker went (bit planes in
+ *                              device memory, 4 bytes per pixel, plane and 32 steps: 32 bytes
+ *                              per pixel for 65 taps); the other passes replay the record:
+ *                              per step a move, the texture gather and the reference's fused
+ *                              multiply-add with that step's tap, in the reference's order --
+ *                              the same bits for about a fifth of the instructions.
+ *                              Applies with the default arithmetic and the grouped walk; a
+ *                              record that does not fit the device's free memory falls back
+ *                              to walking.
+ *   RLIC_B200_PATHS_RECOMPUTE  every pass walks, as the reference does.
+ * A process-wide default like the three above, with its own per-thread override (-1 = none). */
+#define RLIC_B200_PATHS_RECOMPUTE 0
+#define RLIC_B200_PATHS_REPLAY 1
+int rlic_b200_set_paths(int which);
+int rlic_b200_get_paths(void);
+int rlic_b200_set_thread_paths(int which);
+int rlic_b200_get_thread_paths(void);
+int rlic_b200_get_effective_paths(void);
 
 /* Testing hook (host code only): the (pass, band) launch order of the wavefront schedule
  * for `nbands` bands and `iterations` passes, as pairs pass_band[2k] = pass (1-based),
@@ -481,7 +505,8 @@ int rlic_b200_measure_gather_ceiling_f64(const double *d_padded_texture, const d
 
 /*
  * FUSED HALO EXCHANGE (row-slab sharding, one process per GPU; rlic_b200/sharded.py with
- * exchange="peer").  Not yet run on hardware: the NCCL exchange is the default.
+ * exchange="peer").  The default of bench.py --gpus N since round 2 (8 B200s: weak scaling
+ * 0.97, profiles/r2_session8b_summary.txt).
  *
  *   pass_slab_peer   rlic_b200_pass_slab_* that also stores every result of the rows it
  *                    computes -- the pixels and the two wall cells that travel with each
@@ -520,6 +545,45 @@ int rlic_b200_pass_slab_peer_f64(const double *d_texture, const double *d_field,
                                  int x_left, int x_right, int y_left, int y_right,
                                  double *d_peer_out, int64_t peer_row_delta,
                                  void *stream);
+/*
+ * SLAB PASSES WITH RECORDED PATHS (see RLIC_B200_PATHS_REPLAY above; replaces the body of the
+ * iteration loop lib.rs:432-440 for callers that drive the passes of a slab themselves).
+ *   path_record_bytes  size of the record of a padded buffer that holds `rows` image rows
+ *                      (halo rows included) of `nx` pixels, for a `klen`-tap kernel
+ *   pass_slab_paths    rlic_b200_pass_slab_* (d_peer_out NULL) or _pass_slab_peer_* with
+ *                      paths_mode  RLIC_B200_PASS_WALK    as those, d_paths ignored
+ *                                  RLIC_B200_PASS_RECORD  the walk also writes the record of the
+ *                                                         rows it computes into d_paths
+ *                                  RLIC_B200_PASS_REPLAY  the rows are computed from the record
+ *                                                         (d_field is not read, may be NULL)
+ *                      The record belongs to (field, uv_mode, boundaries, kernel length, slab):
+ *                      replaying it with anything else is the caller's error.  Default
+ *                      arithmetic and the grouped walk only (EINVAL otherwise).
+ */
+#define RLIC_B200_PASS_WALK 0
+#define RLIC_B200_PASS_RECORD 1
+#define RLIC_B200_PASS_REPLAY 2
+int64_t rlic_b200_path_record_bytes(int64_t rows, int64_t nx, int64_t klen);
+int rlic_b200_pass_slab_paths_f32(const float *d_texture, const float *d_field, float *d_out,
+                                  int64_t ny, int64_t nx,
+                                  int64_t row0, int64_t nrows, int64_t halo_lo, int64_t halo_hi,
+                                  int64_t sub_row0, int64_t sub_nrows,
+                                  const float *kernel, int64_t klen,
+                                  int uv_mode,
+                                  int x_left, int x_right, int y_left, int y_right,
+                                  float *d_peer_out, int64_t peer_row_delta,
+                                  int paths_mode, uint32_t *d_paths,
+                                  void *stream);
+int rlic_b200_pass_slab_paths_f64(const double *d_texture, const double *d_field, double *d_out,
+                                  int64_t ny, int64_t nx,
+                                  int64_t row0, int64_t nrows, int64_t halo_lo, int64_t halo_hi,
+                                  int64_t sub_row0, int64_t sub_nrows,
+                                  const double *kernel, int64_t klen,
+                                  int uv_mode,
+                                  int x_left, int x_right, int y_left, int y_right,
+                                  double *d_peer_out, int64_t peer_row_delta,
+                                  int paths_mode, uint32_t *d_paths,
+                                  void *stream);
 int rlic_b200_peer_alloc(int64_t bytes, void **ptr, unsigned char *handle);
 int rlic_b200_peer_open(const unsigned char *handle, void **ptr);
 int rlic_b200_peer_close(void *ptr);

@@ -16,14 +16,16 @@ __all__ = [
     "effective_options",
     "equalize_histogram",
     "get_arithmetic",
+    "get_paths",
     "get_schedule",
     "get_walk",
     "options",
     "set_arithmetic",
+    "set_paths",
     "set_schedule",
     "set_walk",
 ]
 
-from rlic_b200._core import (effective_options, get_arithmetic, get_schedule, get_walk, options,
-                             set_arithmetic, set_schedule, set_walk)
+from rlic_b200._core import (effective_options, get_arithmetic, get_paths, get_schedule, get_walk, options,
+                             set_arithmetic, set_paths, set_schedule, set_walk)
 from rlic_b200._lib import convolve, convolve_batch, convolve_sharded, equalize_histogram

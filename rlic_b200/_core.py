@@ -30,10 +30,12 @@ import numpy as np
 _LIB_PATH = Path(__file__).resolve().parent / "librlic_b200.so"
 
 OK, EINVAL, ENODEVICE, ECUDA, ESHARD = range(5)
-ABI_VERSION = 3
+ABI_VERSION = 4
 ARITHMETICS = {"fma+branchless": 0, "fma": 1}   # RLIC_B200_ARITH_* in include/rlic_b200.h
 SCHEDULES = {"trailing": 0, "wavefront": 1}      # RLIC_B200_SCHEDULE_*
 WALKS = {"per-step": 0, "grouped": 1}            # RLIC_B200_WALK_*
+PATHS = {"recompute": 0, "replay": 1}            # RLIC_B200_PATHS_*
+PASS_WALK, PASS_RECORD, PASS_REPLAY = range(3)   # RLIC_B200_PASS_* (paths_mode of pass_slab_paths)
 
 _MODE_CODE = {"velocity": 0, "polarization": 1}
 _WALL_CODE = {"closed": 0, "periodic": 1}
@@ -69,6 +71,7 @@ def _signatures(real) -> dict[str, list]:
         "measure_gather_ceiling": [_vp, _vp, _vp, _i64, _i64, p, _i64, _int, _vp],
         "pass_slab": [_vp, _vp, _vp, *slab, _i64, _i64, p, _i64, _int, *walls, _vp],
         "pass_slab_peer": [_vp, _vp, _vp, *slab, _i64, _i64, p, _i64, _int, *walls, _vp, _i64, _vp],
+        "pass_slab_paths": [_vp, _vp, _vp, *slab, _i64, _i64, p, _i64, _int, *walls, _vp, _i64, _int, _vp, _vp],
     }
 
 
@@ -125,6 +128,17 @@ def _load() -> ctypes.CDLL:
     cdll.rlic_b200_set_walk.argtypes = [_int]
     cdll.rlic_b200_set_walk.restype = _int
     cdll.rlic_b200_get_walk.restype = _int
+    cdll.rlic_b200_set_paths.argtypes = [_int]
+    cdll.rlic_b200_set_thread_paths.argtypes = [_int]
+    for name in ("set_paths", "get_paths", "set_thread_paths", "get_thread_paths", "get_effective_paths"):
+        getattr(cdll, f"rlic_b200_{name}").restype = _int
+    cdll.rlic_b200_path_record_bytes.argtypes = [_i64, _i64, _i64]
+    cdll.rlic_b200_path_record_bytes.restype = _i64
+    paths = os.environ.get("RLIC_B200_PATHS")
+    if paths:
+        if paths not in PATHS:
+            raise ImportError(f"RLIC_B200_PATHS={paths!r}: expected one of {sorted(PATHS)}")
+        cdll.rlic_b200_set_paths(PATHS[paths])
     walk = os.environ.get("RLIC_B200_WALK")
     if walk:
         if walk not in WALKS:
@@ -219,6 +233,30 @@ def get_walk() -> str:
     return next(name for name, c in WALKS.items() if c == code)
 
 
+def set_paths(name: str) -> None:
+    """What the passes of a call after its first do (include/rlic_b200.h): ``"replay"`` (default)
+    -- the first pass records which way every walker went at every step, the others replay
+    the record (a streamline's path depends on the field, never on the texture; same bits,
+    about a fifth of the instructions) -- or ``"recompute"``, every pass walks as the reference
+    does.  The process-wide default; also settable with ``RLIC_B200_PATHS``.  For one thread's
+    calls use ``options``."""
+    try:
+        code = PATHS[name]
+    except KeyError:
+        raise ValueError(f"unknown paths choice {name!r}: expected one of {sorted(PATHS)}") from None
+    check(lib.rlic_b200_set_paths(code))
+
+
+def get_paths() -> str:
+    code = int(lib.rlic_b200_get_paths())
+    return next(name for name, c in PATHS.items() if c == code)
+
+
+def path_record_bytes(rows: int, nx: int, klen: int) -> int:
+    """Bytes of the path record of a padded buffer holding `rows` x `nx` pixels, `klen` taps."""
+    return int(lib.rlic_b200_path_record_bytes(rows, nx, klen))
+
+
 class options:
     """Context manager: choices for the calls THIS THREAD makes inside the block, leaving the
     process-wide defaults (and every other thread) alone::
@@ -226,13 +264,14 @@ class options:
         with rlic_b200.options(arithmetic="fma"):
             out = rlic_b200.convolve(...)          # the bits of rLIC's x86-64 wheels
 
-    ``arithmetic``, ``schedule``, ``walk`` take the names ``set_arithmetic`` / ``set_schedule``
-    / ``set_walk`` take; ``None`` keeps whatever is in force.  Backed by
-    ``rlic_b200_set_thread_options`` (include/rlic_b200.h): nothing shared is written, so
-    concurrent threads with different choices do not race."""
+    ``arithmetic``, ``schedule``, ``walk``, ``paths`` take the names ``set_arithmetic`` /
+    ``set_schedule`` / ``set_walk`` / ``set_paths`` take; ``None`` keeps whatever is in force.
+    Backed by ``rlic_b200_set_thread_options`` and ``rlic_b200_set_thread_paths``
+    (include/rlic_b200.h): nothing shared is written, so concurrent threads with different
+    choices do not race."""
 
     def __init__(self, *, arithmetic: str | None = None, schedule: str | None = None,
-                 walk: str | None = None):
+                 walk: str | None = None, paths: str | None = None):
         def code(table, name, what):
             if name is None:
                 return None
@@ -242,28 +281,37 @@ class options:
 
         self._want = (code(ARITHMETICS, arithmetic, "arithmetic"), code(SCHEDULES, schedule, "schedule"),
                       code(WALKS, walk, "walk"))
+        self._want_paths = code(PATHS, paths, "paths choice")
         self._saved = None
+        self._saved_paths = -1
 
     def __enter__(self):
         saved = [ctypes.c_int(), ctypes.c_int(), ctypes.c_int()]
         lib.rlic_b200_get_thread_options(*(ctypes.byref(x) for x in saved))
         self._saved = tuple(x.value for x in saved)
+        self._saved_paths = int(lib.rlic_b200_get_thread_paths())
         check(lib.rlic_b200_set_thread_options(*(s if w is None else w for s, w in zip(self._saved, self._want))))
+        if self._want_paths is not None:
+            check(lib.rlic_b200_set_thread_paths(self._want_paths))
         return self
 
     def __exit__(self, *exc):
         check(lib.rlic_b200_set_thread_options(*self._saved))
+        check(lib.rlic_b200_set_thread_paths(self._saved_paths))
         return False
 
 
 def effective_options() -> dict:
-    """What a call made now by this thread would use: ``{"arithmetic", "schedule", "walk"}``."""
+    """What a call made now by this thread would use:
+    ``{"arithmetic", "schedule", "walk", "paths"}``."""
     got = [ctypes.c_int(), ctypes.c_int(), ctypes.c_int()]
     lib.rlic_b200_get_effective_options(*(ctypes.byref(x) for x in got))
     names = []
     for table, x in zip((ARITHMETICS, SCHEDULES, WALKS), got):
         names.append(next(name for name, c in table.items() if c == x.value))
-    return dict(zip(("arithmetic", "schedule", "walk"), names))
+    code = int(lib.rlic_b200_get_effective_paths())
+    names.append(next(name for name, c in PATHS.items() if c == code))
+    return dict(zip(("arithmetic", "schedule", "walk", "paths"), names))
 
 
 def device_count() -> int:

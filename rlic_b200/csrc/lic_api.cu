@@ -43,7 +43,8 @@ std::atomic<int> g_small_images{1}; // testing hook: 0 keeps small passes on the
 std::atomic<int> g_arithmetic{RLIC_B200_ARITH_FMA_BRANCHLESS};
 std::atomic<int> g_walk{RLIC_B200_WALK_GROUPED};
 std::atomic<int> g_schedule{RLIC_B200_SCHEDULE_WAVEFRONT};
-struct ThreadChoices { int arithmetic = -1, schedule = -1, walk = -1; };
+std::atomic<int> g_paths{RLIC_B200_PATHS_REPLAY};
+struct ThreadChoices { int arithmetic = -1, schedule = -1, walk = -1, paths = -1; };
 thread_local ThreadChoices tls_choices;
 int effective_arithmetic()
 {
@@ -56,6 +57,10 @@ int effective_schedule()
 int effective_walk()
 {
     return tls_choices.walk >= 0 ? tls_choices.walk : g_walk.load(std::memory_order_relaxed);
+}
+int effective_paths()
+{
+    return tls_choices.paths >= 0 ? tls_choices.paths : g_paths.load(std::memory_order_relaxed);
 }
 
 int fail(int code, const char *fmt, ...)
@@ -287,6 +292,7 @@ cudaError_t launch_unpad(const T *padded, T *dense, const PassGeom &g, int64_t r
 template <typename T> struct TapSet {
     static constexpr int kMaxParam = rlic::kParamTapBytes / (int)sizeof(T);
     rlic::ParamTaps<T, kMaxParam> param;
+    rlic::StepTaps<T, rlic::kStepTapsPerHalf<T>> steps;   // the same taps in walking order, for the replay
     DeviceBuf global;
     int ntaps = 0;
     bool in_param = true;
@@ -298,6 +304,13 @@ template <typename T> struct TapSet {
         if (in_param) {
             std::memset(param.w, 0, sizeof param.w);
             std::memcpy(param.w, host_taps, sizeof(T) * (size_t)klen);
+            std::memset(&steps, 0, sizeof steps);
+            const int64_t kmid = klen / 2;
+            steps.centre = host_taps[kmid];
+            for (int64_t k = kmid + 1; k < klen; ++k)
+                steps.fwd[k - kmid - 1] = host_taps[k];
+            for (int64_t k = kmid - 1; k >= 0; --k)
+                steps.bwd[kmid - 1 - k] = host_taps[k];
             return cudaSuccess;
         }
         cudaError_t e = global.alloc(sizeof(T) * (size_t)klen, stream);
@@ -317,31 +330,68 @@ template <typename T> struct PeerTarget {
     long long delta = 0;
 };
 
+// What a pass does with the recorded streamline paths (rlic::PathPlanes in lic_walk.cuh): the
+// first pass of a call with more iterations to come records them, the others replay them.
+enum class Paths { none, record, replay };
+struct PathUse {
+    Paths mode = Paths::none;
+    unsigned *rec = nullptr;       // planes * plane_cells words
+    long long plane_cells = 0;     // cells of the whole padded buffer (every field)
+};
+
+// words of the record of one padded buffer of `cells` cells, for a kernel of `klen` taps
+size_t path_record_words(int64_t cells, int64_t klen)
+{
+    return (size_t)(rlic::path_groups_fwd(klen) + rlic::path_groups_bwd(klen)) * rlic::kPlanesPerGroup * (size_t)cells;
+}
+
+// Registers: the recording walk keeps the planes of its group (three words) next to the walk's
+// own state; the f32 kernels sit at the 32-register cap of 8 CTAs per SM, so the recording
+// instantiation gets one CTA fewer instead of spills.
+template <typename T, bool POL> constexpr int record_min_blocks()
+{
+    return rlic::Tune<T, POL>::walk_min_blocks > 6 ? 6 : rlic::Tune<T, POL>::walk_min_blocks;
+}
+
 template <typename T, bool POL, typename Taps, typename Idx>
 cudaError_t launch_one(const T *tex, const Field<T> *field, T *out, const PassGeom &g,
                        const Taps &taps, int ntaps, unsigned blocks, bool branchless, bool grouped,
-                       const PeerTarget<T> &peer, cudaStream_t stream)
+                       const PeerTarget<T> &peer, const PathUse &paths, cudaStream_t stream)
 {
     using Tn = rlic::Tune<T, POL>;
+    const rlic::PathPlanes none{nullptr, 0, 0};
+    if (paths.mode == Paths::record) {   // grouped walk, default arithmetic (checked by the caller)
+        const rlic::PathPlanes planes{paths.rec, paths.plane_cells, rlic::path_groups_fwd(ntaps)};
+        if (peer.out)
+            rlic::lic_pass_peer_kernel<T, POL, Taps, Idx, rlic::kTileW, rlic::kTileH, Tn::walk_unroll,
+                                       record_min_blocks<T, POL>(), Tn::walk_flavor, Tn::walk_admit, true, Tn::walk, true>
+                <<<blocks, rlic::kThreads, 0, stream>>>(tex, field, out, g, taps, ntaps, peer.out, peer.delta, planes);
+        else
+            rlic::lic_pass_kernel<T, POL, Taps, Idx, rlic::kTileW, rlic::kTileH, Tn::walk_unroll,
+                                  record_min_blocks<T, POL>(), Tn::walk_flavor, Tn::walk_admit, true, Tn::walk, true>
+                <<<blocks, rlic::kThreads, 0, stream>>>(tex, field, out, g, taps, ntaps, planes);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        return cudaGetLastError();
+    }
     if (peer.out) {   // the default arithmetic only (checked by the caller)
         if (grouped)
             rlic::lic_pass_peer_kernel<T, POL, Taps, Idx, rlic::kTileW, rlic::kTileH, Tn::walk_unroll,
                                        Tn::walk_min_blocks, Tn::walk_flavor, Tn::walk_admit, true, Tn::walk>
-                <<<blocks, rlic::kThreads, 0, stream>>>(tex, field, out, g, taps, ntaps, peer.out, peer.delta);
+                <<<blocks, rlic::kThreads, 0, stream>>>(tex, field, out, g, taps, ntaps, peer.out, peer.delta, none);
         else
             rlic::lic_pass_peer_kernel<T, POL, Taps, Idx>
-                <<<blocks, rlic::kThreads, 0, stream>>>(tex, field, out, g, taps, ntaps, peer.out, peer.delta);
+                <<<blocks, rlic::kThreads, 0, stream>>>(tex, field, out, g, taps, ntaps, peer.out, peer.delta, none);
     } else if (branchless && grouped)
         rlic::lic_pass_kernel<T, POL, Taps, Idx, rlic::kTileW, rlic::kTileH, Tn::walk_unroll,
                               Tn::walk_min_blocks, Tn::walk_flavor, Tn::walk_admit, true, Tn::walk>
-            <<<blocks, rlic::kThreads, 0, stream>>>(tex, field, out, g, taps, ntaps);
+            <<<blocks, rlic::kThreads, 0, stream>>>(tex, field, out, g, taps, ntaps, none);
     else if (branchless)
         rlic::lic_pass_kernel<T, POL, Taps, Idx>
-            <<<blocks, rlic::kThreads, 0, stream>>>(tex, field, out, g, taps, ntaps);
+            <<<blocks, rlic::kThreads, 0, stream>>>(tex, field, out, g, taps, ntaps, none);
     else
         rlic::lic_pass_kernel<T, POL, Taps, Idx, rlic::kTileW, rlic::kTileH, Tn::unroll, Tn::min_blocks,
                               Tn::flavor, Tn::admit, false>
-            <<<blocks, rlic::kThreads, 0, stream>>>(tex, field, out, g, taps, ntaps);
+            <<<blocks, rlic::kThreads, 0, stream>>>(tex, field, out, g, taps, ntaps, none);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }
@@ -387,17 +437,58 @@ cudaError_t launch_pair(const T *tex, const Field<T> *field, T *out, PassGeom g,
 // `dense_out`: when not null and the pass runs on the small-image kernel, the results go there
 // (dense rows, as rlic_b200_slab_unpad_texture would leave them) instead of the padded `out`,
 // and *wrote_dense is set; the caller then skips its un-padding launch.
+// Whether a call of `iterations` passes records the paths of its first pass and replays them
+// in the others: the option, more than one pass, and the walk that knows how to record.
+bool paths_are_replayed(int64_t iterations)
+{
+    return iterations >= 2 && effective_paths() == RLIC_B200_PATHS_REPLAY &&
+           effective_arithmetic() == RLIC_B200_ARITH_FMA_BRANCHLESS && effective_walk() == RLIC_B200_WALK_GROUPED;
+}
+
+// One pass by replay of the recorded paths (lic_replay_kernel); g carries the launch's rows and tiles.
+template <typename T, typename Idx>
+cudaError_t launch_replay(const T *tex, T *out, const PassGeom &g, const TapSet<T> &taps, unsigned blocks,
+                          const PeerTarget<T> &peer, const PathUse &paths, cudaStream_t stream)
+{
+    using ST = rlic::StepTaps<T, rlic::kStepTapsPerHalf<T>>;
+    using GT = rlic::GlobalStepTaps<T>;
+    const int groups = std::max(rlic::path_groups_fwd(taps.ntaps), rlic::path_groups_bwd(taps.ntaps));
+#define RLIC_REPLAY(TAPS, TAPV, GROUPS)                                                                    \
+    do {                                                                                                   \
+        if (peer.out)                                                                                      \
+            rlic::lic_replay_kernel<T, TAPS, Idx, GROUPS, true><<<blocks, rlic::kThreads, 0, stream>>>(    \
+                tex, paths.rec, out, g, TAPV, taps.ntaps, paths.plane_cells, peer.out, peer.delta);        \
+        else                                                                                               \
+            rlic::lic_replay_kernel<T, TAPS, Idx, GROUPS, false><<<blocks, rlic::kThreads, 0, stream>>>(   \
+                tex, paths.rec, out, g, TAPV, taps.ntaps, paths.plane_cells, nullptr, 0);                  \
+    } while (0)
+    if (!taps.in_param) {
+        const GT gt{static_cast<const T *>(taps.global.p), taps.ntaps / 2};
+        RLIC_REPLAY(GT, gt, 0);
+    } else if (groups <= 1)
+        RLIC_REPLAY(ST, taps.steps, 1);
+    else if (groups == 2)
+        RLIC_REPLAY(ST, taps.steps, 2);
+    else
+        RLIC_REPLAY(ST, taps.steps, 0);
+#undef RLIC_REPLAY
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
 template <typename T>
 int launch_pass(const T *tex, const Field<T> *field, T *out, PassGeom g, int64_t nfields,
                 int64_t first_row, int64_t out_rows, int uv_mode, const TapSet<T> &taps,
                 cudaStream_t stream, const PeerTarget<T> &peer = PeerTarget<T>{}, T *dense_out = nullptr,
-                bool *wrote_dense = nullptr)
+                bool *wrote_dense = nullptr, const PathUse &paths = PathUse{})
 {
     if (wrote_dense)
         *wrote_dense = false;
     if (out_rows <= 0 || g.nx <= 0 || nfields <= 0)
         return RLIC_B200_OK;
-    if (!peer.out && pair_kernel_fits<T>(g, nfields, out_rows, taps)) {
+    if (paths.mode != Paths::none && !paths.rec)
+        return fail(RLIC_B200_EINVAL, "null path record");
+    if (!peer.out && paths.mode == Paths::none && pair_kernel_fits<T>(g, nfields, out_rows, taps)) {
         g.first_row = (int)first_row;
         g.out_rows = (int)out_rows;
         T *dense = (dense_out && first_row == 0 && out_rows == g.rows) ? dense_out : nullptr;
@@ -425,10 +516,18 @@ int launch_pass(const T *tex, const Field<T> *field, T *out, PassGeom g, int64_t
     const bool grouped = effective_walk() == RLIC_B200_WALK_GROUPED;
     if (peer.out && (!branchless || nfields != 1))
         return fail(RLIC_B200_EINVAL, "the fused halo exchange needs the default arithmetic and one field");
+    if (paths.mode != Paths::none && !(branchless && grouped))
+        return fail(RLIC_B200_EINVAL, "paths are recorded and replayed with the default arithmetic and the grouped walk only");
 
     cudaError_t e;
+    if (paths.mode == Paths::replay) {
+        e = wide ? launch_replay<T, long long>(tex, out, g, taps, (unsigned)blocks, peer, paths, stream)
+                 : launch_replay<T, int>(tex, out, g, taps, (unsigned)blocks, peer, paths, stream);
+        CUDA_TRY(e);
+        return RLIC_B200_OK;
+    }
 #define RLIC_LAUNCH(POL, TAPS, TAPV, IDX) \
-    e = launch_one<T, POL, TAPS, IDX>(tex, field, out, g, TAPV, taps.ntaps, (unsigned)blocks, branchless, grouped, peer, stream)
+    e = launch_one<T, POL, TAPS, IDX>(tex, field, out, g, TAPV, taps.ntaps, (unsigned)blocks, branchless, grouped, peer, paths, stream)
     using PT = rlic::ParamTaps<T, TapSet<T>::kMaxParam>;
     using GT = rlic::GlobalTaps<T>;
     const GT gt{static_cast<const T *>(taps.global.p)};
@@ -482,6 +581,41 @@ std::vector<BandPass> wavefront_order(int64_t nbands, int64_t iterations)
     return order;
 }
 
+// The record is planes * 4 bytes per cell (32 bytes for a 65-tap kernel): small next to 180 GB,
+// but a caller may have filled the device.  Large records are checked against the free memory;
+// when one does not fit the call simply walks every pass.
+bool path_record_fits(size_t bytes)
+{
+    if (bytes <= ((size_t)1 << 30))
+        return true;
+    size_t free_bytes = 0, total = 0;
+    if (cudaMemGetInfo(&free_bytes, &total) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return bytes < free_bytes / 2;
+}
+
+// The record of a call: allocated when its passes replay, and how pass `p` (1-based) uses it.
+struct CallPaths {
+    DeviceBuf buf;
+    long long plane_cells = 0;
+    bool on = false;
+    cudaError_t prepare(int64_t iterations, int64_t cells, int64_t klen, cudaStream_t stream)
+    {
+        const size_t bytes = path_record_words(cells, klen) * sizeof(unsigned);
+        on = paths_are_replayed(iterations) && bytes > 0 && path_record_fits(bytes);
+        plane_cells = cells;
+        return on ? buf.alloc(bytes, stream) : cudaSuccess;
+    }
+    PathUse use(int64_t pass) const
+    {
+        if (!on)
+            return PathUse{};
+        return PathUse{pass == 1 ? Paths::record : Paths::replay, static_cast<unsigned *>(buf.p), plane_cells};
+    }
+};
+
 // Host entry: upload -> passes -> download, pipelined over row bands.
 //   stream `io`  : uploads (band by band: u, v -> packed field; texture -> padded
 //                  buffer) and downloads (padded -> dense -> host)
@@ -533,6 +667,7 @@ int convolve_host(const T *tex, const T *u, const T *v, int64_t nfields, int64_t
     // work buffer), the packed field, and dense staging for the three uploads
     // (the texture's staging is reused for the download).
     DeviceBuf d_tex, d_work, d_field, d_su, d_sv, d_st, d_flag;
+    CallPaths paths;
     StreamDrain drain{{&io, &run, &back}};
     CUDA_TRY(d_tex.alloc(padded_bytes, io.s));
     CUDA_TRY(d_work.alloc(padded_bytes, io.s));
@@ -546,6 +681,8 @@ int convolve_host(const T *tex, const T *u, const T *v, int64_t nfields, int64_t
     }
     TapSet<T> taps;
     CUDA_TRY(taps.prepare(kernel, klen, io.s));
+    // (allocated on `io`, first used on `run` behind an `uploaded` event recorded later on `io`)
+    CUDA_TRY(paths.prepare(iterations, g.field_stride * nfields, klen, io.s));
     Events uploaded, done;
     CUDA_TRY(uploaded.make((size_t)nbands));
     CUDA_TRY(done.make((size_t)nbands));
@@ -568,7 +705,8 @@ int convolve_host(const T *tex, const T *u, const T *v, int64_t nfields, int64_t
         const int64_t need = periodic_y ? nbands - 1 : std::min(nbands - 1, last_row / band_rows);
         CUDA_TRY(cudaStreamWaitEvent(run.s, uploaded.ev[(size_t)need], 0));
         int rc = launch_pass<T>(t_tex, t_field, bufs[0], g, nfields, band_begin(b),
-                                band_begin(b + 1) - band_begin(b), uv_mode, taps, run.s);
+                                band_begin(b + 1) - band_begin(b), uv_mode, taps, run.s, PeerTarget<T>{},
+                                nullptr, nullptr, paths.use(1));
         if (rc)
             return rc;
         if (single)
@@ -611,7 +749,8 @@ int convolve_host(const T *tex, const T *u, const T *v, int64_t nfields, int64_t
             if (bp.pass == 1)
                 CUDA_TRY(cudaStreamWaitEvent(run.s, uploaded.ev[(size_t)upload_needed(b)], 0));
             if (int rc = launch_pass<T>(from, t_field, bufs[(bp.pass - 1) & 1], g, nfields, band_begin(b),
-                                        band_begin(b + 1) - band_begin(b), uv_mode, taps, run.s))
+                                        band_begin(b + 1) - band_begin(b), uv_mode, taps, run.s, PeerTarget<T>{},
+                                        nullptr, nullptr, paths.use(bp.pass)))
                 return rc;
             if (bp.pass == iterations)
                 CUDA_TRY(cudaEventRecord(done.ev[(size_t)b], run.s));
@@ -680,12 +819,14 @@ int convolve_host(const T *tex, const T *u, const T *v, int64_t nfields, int64_t
     for (int64_t it = 1; it < iterations; ++it) {
         T *dst = bufs[it & 1];
         if (it < iterations - 1) {
-            if (int rc = launch_pass<T>(src, t_field, dst, g, nfields, 0, ny, uv_mode, taps, run.s))
+            if (int rc = launch_pass<T>(src, t_field, dst, g, nfields, 0, ny, uv_mode, taps, run.s, PeerTarget<T>{},
+                                        nullptr, nullptr, paths.use(it + 1)))
                 return rc;
         } else {
             for (int64_t b = 0; b < nbands; ++b) {
                 if (int rc = launch_pass<T>(src, t_field, dst, g, nfields, band_begin(b),
-                                            band_begin(b + 1) - band_begin(b), uv_mode, taps, run.s))
+                                            band_begin(b + 1) - band_begin(b), uv_mode, taps, run.s, PeerTarget<T>{},
+                                            nullptr, nullptr, paths.use(it + 1)))
                     return rc;
                 CUDA_TRY(cudaEventRecord(done.ev[(size_t)b], run.s));
             }
@@ -732,6 +873,8 @@ int run_device(const T *d_tex, const Field<T> *d_field, int64_t ny, int64_t nx, 
         CUDA_TRY(b.alloc(padded_bytes, s));
     DeviceBuf in;
     CUDA_TRY(in.alloc(padded_bytes, s));
+    CallPaths paths;
+    CUDA_TRY(paths.prepare(iterations, g.field_stride * nfields, taps.ntaps, s));
     CUDA_TRY(launch_pad<T>(d_tex, static_cast<T *>(in.p), g, 0, ny, nfields, nullptr, s));
     const T *src = static_cast<const T *>(in.p);
     T *dst = static_cast<T *>(a.p);
@@ -741,7 +884,7 @@ int run_device(const T *d_tex, const Field<T> *d_field, int64_t ny, int64_t nx, 
         dst = static_cast<T *>(it == 0 ? a.p : ((it & 1) ? b.p : a.p));
         // a small image's last pass writes the dense result itself (no un-padding launch)
         if (int rc = launch_pass<T>(src, d_field, dst, g, nfields, 0, ny, uv_mode, taps, s, PeerTarget<T>{},
-                                    it == iterations - 1 ? d_out : nullptr, &wrote_dense))
+                                    it == iterations - 1 ? d_out : nullptr, &wrote_dense, paths.use(it + 1)))
             return rc;
         src = dst;
     }
@@ -907,8 +1050,12 @@ int slab_unpad_texture(const T *d_padded, int64_t ny, int64_t nx, const Slab &sl
 template <typename T>
 int pass_slab(const T *d_tex, const T *d_field, T *d_out, int64_t ny, int64_t nx, const Slab &sl,
               int64_t sub0, int64_t subn, const T *kernel, int64_t klen, int uv_mode,
-              const Walls &w, void *stream, T *peer_out = nullptr, int64_t peer_row_delta = 0)
+              const Walls &w, void *stream, T *peer_out = nullptr, int64_t peer_row_delta = 0,
+              int paths_mode = RLIC_B200_PASS_WALK, uint32_t *d_paths = nullptr)
 {
+    if (paths_mode != RLIC_B200_PASS_WALK && paths_mode != RLIC_B200_PASS_RECORD &&
+        paths_mode != RLIC_B200_PASS_REPLAY)
+        return fail(RLIC_B200_EINVAL, "unknown paths mode %d", paths_mode);
     if (int rc = check_common(ny, nx, klen, uv_mode, w))
         return rc;
     if (int rc = check_slab(ny, klen, sl, w))
@@ -917,7 +1064,9 @@ int pass_slab(const T *d_tex, const T *d_field, T *d_out, int64_t ny, int64_t nx
         return rc;
     if (subn == 0 || nx == 0)
         return RLIC_B200_OK;
-    if (!d_tex || !d_field || !d_out || !kernel)
+    // (a replayed pass does not look at the field)
+    if (!d_tex || (!d_field && paths_mode != RLIC_B200_PASS_REPLAY) || !d_out || !kernel ||
+        (paths_mode != RLIC_B200_PASS_WALK && !d_paths))
         return fail(RLIC_B200_EINVAL, "null pointer argument");
     const PassGeom g = make_geometry(ny, nx, sl, w);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -926,8 +1075,12 @@ int pass_slab(const T *d_tex, const T *d_field, T *d_out, int64_t ny, int64_t nx
     PeerTarget<T> peer;
     peer.out = peer_out;
     peer.delta = (long long)peer_row_delta * g.pitch;
+    PathUse paths;
+    if (paths_mode != RLIC_B200_PASS_WALK)
+        paths = PathUse{paths_mode == RLIC_B200_PASS_RECORD ? Paths::record : Paths::replay, d_paths,
+                        (long long)g.field_stride};
     return launch_pass<T>(d_tex, reinterpret_cast<const Field<T> *>(d_field), d_out, g, 1,
-                          sl.halo_lo + sub0, subn, uv_mode, taps, s, peer);
+                          sl.halo_lo + sub0, subn, uv_mode, taps, s, peer, nullptr, nullptr, paths);
 }
 
 // Whole fields split over devices.  Two host threads per device take chunks
@@ -968,7 +1121,7 @@ int convolve_batch(const T *tex, const T *u, const T *v, int64_t nfields, int64_
     const int64_t chunk = std::max<int64_t>(1, (int64_t)((size_t)(16u << 20) / field_elems));
 
     const int lanes = 2;
-    const ThreadChoices mine{effective_arithmetic(), effective_schedule(), effective_walk()};
+    const ThreadChoices mine{effective_arithmetic(), effective_schedule(), effective_walk(), effective_paths()};
     std::atomic<int> any_negative{0};
     std::vector<int> rcs(devs.size() * lanes, 0);
     std::vector<std::string> msgs(devs.size() * lanes);
@@ -1162,8 +1315,41 @@ int rlic_b200_set_thread_options(int arithmetic, int schedule, int walk)
         return fail(RLIC_B200_EINVAL, "unknown schedule %d", schedule);
     if (walk != -1 && walk != RLIC_B200_WALK_PER_STEP && walk != RLIC_B200_WALK_GROUPED)
         return fail(RLIC_B200_EINVAL, "unknown walk %d", walk);
-    tls_choices = ThreadChoices{arithmetic, schedule, walk};
+    tls_choices.arithmetic = arithmetic;
+    tls_choices.schedule = schedule;
+    tls_choices.walk = walk;
     return RLIC_B200_OK;
+}
+
+int rlic_b200_set_paths(int which)
+{
+    tls_error.clear();
+    if (which != RLIC_B200_PATHS_RECOMPUTE && which != RLIC_B200_PATHS_REPLAY)
+        return fail(RLIC_B200_EINVAL, "unknown paths choice %d", which);
+    g_paths.store(which, std::memory_order_relaxed);
+    return RLIC_B200_OK;
+}
+
+int rlic_b200_get_paths(void) { return g_paths.load(std::memory_order_relaxed); }
+
+int rlic_b200_set_thread_paths(int which)
+{
+    tls_error.clear();
+    if (which != -1 && which != RLIC_B200_PATHS_RECOMPUTE && which != RLIC_B200_PATHS_REPLAY)
+        return fail(RLIC_B200_EINVAL, "unknown paths choice %d", which);
+    tls_choices.paths = which;
+    return RLIC_B200_OK;
+}
+
+int rlic_b200_get_thread_paths(void) { return tls_choices.paths; }
+
+int rlic_b200_get_effective_paths(void) { return effective_paths(); }
+
+int64_t rlic_b200_path_record_bytes(int64_t rows, int64_t nx, int64_t klen)
+{
+    if (rows < 0 || nx < 0 || klen <= 0)
+        return 0;
+    return (int64_t)(path_record_words(rlic::padded_cells(rows, nx), klen) * sizeof(unsigned));
 }
 
 void rlic_b200_get_thread_options(int *arithmetic, int *schedule, int *walk)
@@ -1444,6 +1630,26 @@ RLIC_DEFINE_ROWS(double, f64)
     }
 RLIC_DEFINE_PEER(float, f32)
 RLIC_DEFINE_PEER(double, f64)
+
+// rlic_b200_pass_slab_* / _pass_slab_peer_* with the streamline paths recorded or replayed
+// (d_peer_out may be null: no neighbour behind these rows).
+#define RLIC_DEFINE_SLAB_PATHS(T, sfx)                                                           \
+    int rlic_b200_pass_slab_paths_##sfx(const T *d_texture, const T *d_field, T *d_out,          \
+                                        int64_t ny, int64_t nx, int64_t row0, int64_t nrows,     \
+                                        int64_t halo_lo, int64_t halo_hi, int64_t sub_row0,      \
+                                        int64_t sub_nrows, const T *kernel, int64_t klen,        \
+                                        int uv_mode, int x_left, int x_right, int y_left,        \
+                                        int y_right, T *d_peer_out, int64_t peer_row_delta,      \
+                                        int paths_mode, uint32_t *d_paths, void *stream)         \
+    {                                                                                            \
+        tls_error.clear();                                                                       \
+        return pass_slab<T>(d_texture, d_field, d_out, ny, nx,                                   \
+                            Slab{row0, nrows, halo_lo, halo_hi}, sub_row0, sub_nrows, kernel,    \
+                            klen, uv_mode, Walls{x_left, x_right, y_left, y_right}, stream,      \
+                            d_peer_out, peer_row_delta, paths_mode, d_paths);                    \
+    }
+RLIC_DEFINE_SLAB_PATHS(float, f32)
+RLIC_DEFINE_SLAB_PATHS(double, f64)
 
 // ---- histogram equalisation of a result (semantics: lic_equalize.cuh) ----
 #define RLIC_DEFINE_EQUALIZE(T, sfx)                                                             \

@@ -195,6 +195,20 @@ class CudaSlabOps:
             taps.ctypes.data_as(ctypes.POINTER(real)), taps.size, mode, *walls,
             peer.data_ptr(), peer_row_delta, self._stream()))
 
+    def pass_rows_paths(self, src, field, dst, plan, a, b, taps, mode, walls, paths_mode, paths,
+                        peer=None, peer_row_delta=0):
+        """``pass_rows`` / ``pass_rows_peer`` with the streamline paths of rows [a, b) recorded into
+        (``_core.PASS_RECORD``) or replayed from (``_core.PASS_REPLAY``) the int32 tensor ``paths``
+        (``rlic_b200_pass_slab_paths_*``)."""
+        from rlic_b200 import _core
+
+        sfx, real = self._kind(src)
+        _core.check(getattr(_core.lib, f"rlic_b200_pass_slab_paths_{sfx}")(
+            src.data_ptr(), field.data_ptr(), dst.data_ptr(), *plan.slab_args, a, b - a,
+            taps.ctypes.data_as(ctypes.POINTER(real)), taps.size, mode, *walls,
+            peer.data_ptr() if peer is not None else None, peer_row_delta, paths_mode, paths.data_ptr(),
+            self._stream()))
+
     def signal(self, flags, index, value):
         """After everything enqueued so far: raise counter ``index`` of ``flags`` (int32
         tensor, usually a neighbour's) to ``value``."""
@@ -338,8 +352,17 @@ class ShardedConvolver:
     check_peer_timeouts = "lazy"
 
     def __init__(self, ny: int, nx: int, *, kernel, uv_mode: str = "velocity",
-                 boundaries="closed", group=None, ops=None, exchange: str = "nccl", peers=None):
+                 boundaries="closed", group=None, ops=None, exchange: str = "nccl", peers=None,
+                 paths: str | None = None):
         from rlic_b200 import _core   # enum tables only; no computation
+
+        # what the passes of a call after its first do (include/rlic_b200.h, RLIC_B200_PATHS_*):
+        # None = the library's choice for this thread at the time of each call
+        if paths is not None and paths not in _core.PATHS:
+            raise ValueError(f"unknown paths choice {paths!r}: expected one of {sorted(_core.PATHS)}")
+        self.paths = paths
+        self._record = None          # int32 tensor: the recorded paths of this slab (of self.field)
+        self._call_paths = False     # whether the call in progress records / replays
 
         self.group = group
         self.world = dist.get_world_size(group)
@@ -445,9 +468,39 @@ class ShardedConvolver:
             raise TypeError("the peer buffers of this convolver hold another dtype")
         return self._peer
 
-    def _pass_rows(self, src, dst, a: int, b: int) -> None:
-        """Compute owned rows [a, b) of ``dst`` from ``src``."""
-        if b > a:
+    def _begin_call(self, iterations: int, like: torch.Tensor) -> None:
+        """Decide whether this call records the streamline paths in its first pass and replays them
+        in the others (they depend on the field, never on the texture: lib.rs:305-362), and make
+        room for the record.  Same rule as the single-GPU entry points: more than one pass, the
+        option, the default arithmetic and walk."""
+        from rlic_b200 import _core
+
+        want = self.paths
+        if want is None:
+            opts = _core.effective_options() if hasattr(self.ops, "pass_rows_paths") else {}
+            want = opts.get("paths") if (opts.get("arithmetic") == "fma+branchless"
+                                         and opts.get("walk") == "grouped") else "recompute"
+        self._call_paths = bool(iterations >= 2 and want == "replay" and hasattr(self.ops, "pass_rows_paths"))
+        if self._call_paths:
+            words = _core.path_record_bytes(self.plan.rows_alloc, self.plan.nx, int(self.taps.size)) // 4
+            if (self._record is None or self._record.device != like.device or self._record.numel() != words):
+                self._record = torch.empty(words, dtype=torch.int32, device=like.device)
+
+    def _pass_rows(self, src, dst, a: int, b: int, k: int = 0, peer=None, peer_row_delta: int = 0) -> None:
+        """Compute owned rows [a, b) of ``dst`` from ``src`` in pass ``k`` (1-based; 0: a pass outside
+        a call that records), optionally storing them into the neighbour's buffer ``peer`` too."""
+        from rlic_b200 import _core
+
+        if b <= a:
+            return
+        if self._call_paths and k >= 1:
+            self.ops.pass_rows_paths(src, self.field, dst, self.plan, a, b, self.taps, self.mode, self.walls,
+                                     _core.PASS_RECORD if k == 1 else _core.PASS_REPLAY, self._record,
+                                     peer, peer_row_delta)
+        elif peer is not None:
+            self.ops.pass_rows_peer(src, self.field, dst, self.plan, a, b, self.taps, self.mode, self.walls,
+                                    peer, peer_row_delta)
+        else:
             self.ops.pass_rows(src, self.field, dst, self.plan, a, b, self.taps, self.mode, self.walls)
 
     def convolve(self, texture: torch.Tensor, iterations: int = 1, overlap: bool = True) -> torch.Tensor:
@@ -467,6 +520,7 @@ class ShardedConvolver:
         if self._work is None or self._work[0] != key:
             self._work = (key, self._alloc(texture), self._alloc(texture))
         src, dst = self._work[1], self._work[2]
+        self._begin_call(iterations, texture)
         self.ops.pad_texture(texture.contiguous(), src, p, self.walls)
         self._exchange(src)
         h = p.reach
@@ -478,20 +532,21 @@ class ShardedConvolver:
             self.comm_stream = torch.cuda.Stream(device=texture.device)
         for it in range(iterations):
             last = it == iterations - 1
+            k = it + 1
             if not split or last:
-                self._pass_rows(src, dst, 0, p.nrows)
+                self._pass_rows(src, dst, 0, p.nrows, k)
                 if not last:
                     self._exchange(dst)
             elif not side:           # same decomposition without streams (CPU tests)
-                self._pass_rows(src, dst, 0, h)
-                self._pass_rows(src, dst, p.nrows - h, p.nrows)
+                self._pass_rows(src, dst, 0, h, k)
+                self._pass_rows(src, dst, p.nrows - h, p.nrows, k)
                 self._exchange(dst)
-                self._pass_rows(src, dst, h, p.nrows - h)
+                self._pass_rows(src, dst, h, p.nrows - h, k)
             else:
                 main = torch.cuda.current_stream()
                 # 1. the strips the neighbours are waiting for
-                self._pass_rows(src, dst, 0, h)
-                self._pass_rows(src, dst, p.nrows - h, p.nrows)
+                self._pass_rows(src, dst, 0, h, k)
+                self._pass_rows(src, dst, p.nrows - h, p.nrows, k)
                 strips_done = torch.cuda.Event()
                 strips_done.record(main)
                 # 2. ship them while 3. the interior is computed
@@ -500,7 +555,7 @@ class ShardedConvolver:
                     self._exchange(dst)
                     shipped = torch.cuda.Event()
                     shipped.record(self.comm_stream)
-                self._pass_rows(src, dst, h, p.nrows - h)
+                self._pass_rows(src, dst, h, p.nrows - h, k)
                 main.wait_event(shipped)
             src, dst = dst, src
         out = torch.empty_like(texture)
@@ -531,6 +586,7 @@ class ShardedConvolver:
         p = self.plan
         px = self._peer_exchange(texture.dtype, texture.device)
         self._poll_timeout_probes()
+        self._begin_call(iterations, texture)
         self.ops.pad_texture(texture.contiguous(), px.bufs[0], p, self.walls)
         self._peer_passes(px, iterations)
         out = torch.empty_like(texture)
@@ -579,7 +635,7 @@ class ShardedConvolver:
         lo, rows = p.halo_lo, p.nrows
         if rows_runner is None:
             def rows_runner(k, src, dst, a, b):
-                self._pass_rows(src, dst, a, b)
+                self._pass_rows(src, dst, a, b, k)
 
         def push(theirs, mine, delta_rows, a, b, width=1, planes=1, their_cells=0):
             """buffer rows [a, b) of `mine`, with their wall cells, into `theirs` delta_rows away"""
@@ -616,16 +672,15 @@ class ShardedConvolver:
             if k >= 2:
                 wait(_FREE_FROM_UP, _FREE_FROM_DOWN, c + k - 1)
                 self._mark("wait free")
+            # the edge strips, stored into the neighbours' halos as they are computed
             if up is not None:
-                self.ops.pass_rows_peer(src, self.field, dst, p, 0, h, self.taps, self.mode, self.walls,
-                                        up[0][k % 2], px.delta_up)
+                self._pass_rows(src, dst, 0, h, k, up[0][k % 2], px.delta_up)
             else:
-                self._pass_rows(src, dst, 0, h)
+                self._pass_rows(src, dst, 0, h, k)
             if down is not None:
-                self.ops.pass_rows_peer(src, self.field, dst, p, rows - h, rows, self.taps, self.mode,
-                                        self.walls, down[0][k % 2], px.delta_down)
+                self._pass_rows(src, dst, rows - h, rows, k, down[0][k % 2], px.delta_down)
             else:
-                self._pass_rows(src, dst, rows - h, rows)
+                self._pass_rows(src, dst, rows - h, rows, k)
             signal(_HALO_FROM_DOWN, _HALO_FROM_UP, c + k + 1)
             self._mark("strips + signal")
             rows_runner(k, src, dst, h, rows - h)
@@ -743,6 +798,7 @@ class ShardedConvolver:
 
         px = self._peer_exchange(t_tex.dtype, device)
         self._poll_timeout_probes()
+        self._begin_call(iterations, s_t)
         if t_u is not None:
             self.field = px.field
         n, rows = iterations, p.nrows
@@ -795,7 +851,7 @@ class ShardedConvolver:
 
         def rows_runner(k, src, dst, a, e):
             if k != 1 and k != n:
-                self._pass_rows(src, dst, a, e)
+                self._pass_rows(src, dst, a, e, k)
                 return
             for b in range(nb):
                 lo_, hi_ = max(a, edge[b]), min(e, edge[b + 1])
@@ -804,7 +860,7 @@ class ShardedConvolver:
                         if 0 <= nbr < nb:
                             after(main, uploaded[nbr])
                 if hi_ > lo_:
-                    self._pass_rows(src, dst, lo_, hi_)
+                    self._pass_rows(src, dst, lo_, hi_, k)
                 if k == n:
                     done[b] = record(main)
 

@@ -70,6 +70,11 @@ def lib() -> ctypes.CDLL:
             p, g = ctypes.POINTER(real), ctypes.POINTER(_i64)
             getattr(cdll, f"emu_pass_peer_{sfx}").argtypes = [p, p, p, g, _i64, _i64, _int, p, _i64, _int, p, _i64]
             getattr(cdll, f"emu_pass_peer_{sfx}").restype = _int
+        for sfx, real in (("f32", ctypes.c_float), ("f64", ctypes.c_double)):
+            p, g = ctypes.POINTER(real), ctypes.POINTER(_i64)
+            getattr(cdll, f"emu_pass_paths_{sfx}").argtypes = [p, p, p, g, _i64, _i64, _i64, _int, p, _i64, _int, _int,
+                                                              ctypes.POINTER(ctypes.c_uint32), p, _i64]
+            getattr(cdll, f"emu_pass_paths_{sfx}").restype = _int
         cdll.emu_step_counts.argtypes = [ctypes.POINTER(ctypes.c_ulonglong), _int]
         cdll.emu_step_counts.restype = None
         _lib = cdll
@@ -161,6 +166,21 @@ class SlabOps:
         assert rc == 0
 
 
+    def pass_rows_paths(self, src, field, dst, plan, a, b, taps, mode, walls, paths_mode, paths,
+                        peer=None, peer_row_delta=0):
+        """rlic_b200_pass_slab_paths_*: rows [a, b) with their streamline paths recorded into (1) or
+        replayed from (2) the int32 tensor `paths`; `peer`: the doubled stores of the fused exchange."""
+        sfx, real = _kind(self._np(src).dtype)
+        g = self._geom(plan, walls, taps.size)
+        rec = self._np(paths).view(np.uint32)
+        rc = getattr(lib(), f"emu_pass_paths_{sfx}")(
+            _ptr(self._np(src), real), _ptr(self._np(field), real), _ptr(self._np(dst), real), _ptr(g, _i64), 1,
+            plan.halo_lo + a, b - a, mode, _ptr(taps, real), taps.size, 0, int(paths_mode),
+            rec.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)),
+            None if peer is None else _ptr(self._np(peer), real), peer_row_delta)
+        assert rc == 0
+
+
 class Buffers:
     """Padded device-style buffers of one slab (or a batch of whole images), on the host."""
 
@@ -209,16 +229,41 @@ class Buffers:
         assert rc == 0, "no such formulation"
 
 
+    def path_record(self, klen) -> np.ndarray:
+        """Storage for the recorded paths of these buffers (rlic_b200_path_record_bytes); filled with
+        a pattern, so that a replay that reads a word the recording pass did not write shows."""
+        words = _core.path_record_bytes(self.rows, self.nx, klen) // 4 * self.nfields
+        return np.full(words, 0xDEADBEEF, dtype=np.uint32)
+
+    def run_pass_paths(self, src, dst, taps, uv_mode, mode, rec, rows=None, wide=False, peer=None,
+                       peer_row_delta=0):
+        """One pass that records (mode 1: the tuned grouped walk) or replays (mode 2) the paths."""
+        first, count = rows or (self.slab[2], self.slab[1])
+        taps = np.ascontiguousarray(taps, dtype=self.dtype)
+        rc = getattr(lib(), f"emu_pass_paths_{self.sfx}")(
+            _ptr(self.tex[src], self.real), _ptr(self.field, self.real), _ptr(self.tex[dst], self.real),
+            self._g, self.nfields, first, count, _core.mode_code(uv_mode), _ptr(taps, self.real), taps.size,
+            int(wide), int(mode), rec.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)),
+            None if peer is None else _ptr(peer, self.real), peer_row_delta)
+        assert rc == 0, "no such paths mode"
+
+
 def convolve(texture, u, v, *, kernel, uv_mode="velocity", boundaries=(("closed", "closed"),) * 2,
-             iterations=1, wide=False, flavor=-1, admit=-1, branchless=True, walk=0) -> np.ndarray:
-    """The whole-image flow of ``run_device`` in lic_api.cu: pack, pad, passes, un-pad."""
+             iterations=1, wide=False, flavor=-1, admit=-1, branchless=True, walk=0, paths=False) -> np.ndarray:
+    """The whole-image flow of ``run_device`` in lic_api.cu: pack, pad, passes, un-pad.
+    paths=True: the first pass records the streamline paths, the others replay them (what the
+    library does by default for iterations >= 2)."""
     ny, nx = texture.shape
     b = Buffers(texture.dtype, ny, nx, _core.wall_codes(boundaries), len(kernel))
     b.pack_field(u, v)
     b.pad_texture(texture, 0)
     src = 0
-    for _ in range(iterations):
-        b.run_pass(src, 1 - src, kernel, uv_mode, wide=wide, flavor=flavor, admit=admit, branchless=branchless,
-                   walk=walk)
+    rec = b.path_record(len(kernel)) if paths else None
+    for it in range(iterations):
+        if paths:
+            b.run_pass_paths(src, 1 - src, kernel, uv_mode, 1 if it == 0 else 2, rec, wide=wide)
+        else:
+            b.run_pass(src, 1 - src, kernel, uv_mode, wide=wide, flavor=flavor, admit=admit,
+                       branchless=branchless, walk=walk)
         src = 1 - src
     return b.unpad_texture(src)

@@ -132,7 +132,7 @@ void run_pass(const T *tex, const T *field, T *out, const PassGeom &g, const Tap
     launch(blocks, rlic::kThreads, [&] {
         rlic::lic_pass_kernel<T, POL, Taps, Idx, rlic::kTileW, rlic::kTileH, (WALK ? Tn::walk_unroll : Tn::unroll),
                               (WALK ? Tn::walk_min_blocks : Tn::min_blocks), FLAVOR, ADMIT, BRANCHLESS, WALK>(
-            tex, f, out, g, taps, ntaps);
+            tex, f, out, g, taps, ntaps, rlic::PathPlanes{});
     });
 }
 
@@ -241,11 +241,12 @@ void run_pass_peer(const T *tex, const T *field, T *out, const PassGeom &g, cons
         launch(blocks, rlic::kThreads, [&] {
             rlic::lic_pass_peer_kernel<T, POL, Taps, int, rlic::kTileW, rlic::kTileH, Tn::walk_unroll,
                                        Tn::walk_min_blocks, Tn::walk_flavor, Tn::walk_admit, true, Tn::walk>(tex, f, out, g, taps, ntaps,
-                                                                                    peer_out, peer_delta);
+                                                                                    peer_out, peer_delta, rlic::PathPlanes{});
         });
     else
         launch(blocks, rlic::kThreads, [&] {
-            rlic::lic_pass_peer_kernel<T, POL, Taps, int>(tex, f, out, g, taps, ntaps, peer_out, peer_delta);
+            rlic::lic_pass_peer_kernel<T, POL, Taps, int>(tex, f, out, g, taps, ntaps, peer_out, peer_delta,
+                                                          rlic::PathPlanes{});
         });
 }
 
@@ -277,6 +278,110 @@ int pass_peer(const T *tex, const T *field, T *out, const int64_t *geom, int64_t
         if (pol) run_pass_peer<T, true, GT>(tex, field, out, g, gt, ntaps, blocks, walk, peer_out, delta);
         else run_pass_peer<T, false, GT>(tex, field, out, g, gt, ntaps, blocks, walk, peer_out, delta);
     }
+    return 0;
+}
+
+// One pass that records the streamline paths (mode 1: the tuned grouped walk with REC) or
+// replays them (mode 2: lic_replay_kernel), as launch_pass() dispatches them in lic_api.cu:
+// the record of a 65-tap kernel goes through the unrolled one-group kernel, 129 taps through
+// the two-group one, longer ones through the loop; kernels beyond the parameter block read
+// their taps from memory.  peer_out: the doubled stores of the fused halo exchange.
+template <typename T, bool POL, typename Taps, typename Idx>
+void run_record(const T *tex, const T *field, T *out, const PassGeom &g, const Taps &taps, int ntaps,
+                unsigned blocks, unsigned *rec, long long plane_cells, T *peer_out, long long peer_delta)
+{
+    using Tn = rlic::Tune<T, POL>;
+    auto *f = reinterpret_cast<const rlic::PackedField<T> *>(field);
+    const rlic::PathPlanes planes{rec, plane_cells, rlic::path_groups_fwd(ntaps)};
+    constexpr int kFlavor = Tn::walk_flavor == 4 ? 2 : Tn::walk_flavor;
+    if (peer_out)
+        launch(blocks, rlic::kThreads, [&] {
+            rlic::lic_pass_peer_kernel<T, POL, Taps, Idx, rlic::kTileW, rlic::kTileH, Tn::walk_unroll,
+                                       Tn::walk_min_blocks, kFlavor, Tn::walk_admit, true, Tn::walk, true>(
+                tex, f, out, g, taps, ntaps, peer_out, peer_delta, planes);
+        });
+    else
+        launch(blocks, rlic::kThreads, [&] {
+            rlic::lic_pass_kernel<T, POL, Taps, Idx, rlic::kTileW, rlic::kTileH, Tn::walk_unroll, Tn::walk_min_blocks,
+                                  kFlavor, Tn::walk_admit, true, Tn::walk, true>(tex, f, out, g, taps, ntaps, planes);
+        });
+}
+
+template <typename T, typename Taps, typename Idx, int GROUPS>
+void run_replay(const T *tex, T *out, const PassGeom &g, const Taps &taps, int ntaps, unsigned blocks,
+                const unsigned *rec, long long plane_cells, T *peer_out, long long peer_delta)
+{
+    if (peer_out)
+        launch(blocks, rlic::kThreads, [&] {
+            rlic::lic_replay_kernel<T, Taps, Idx, GROUPS, true>(tex, rec, out, g, taps, ntaps, plane_cells, peer_out,
+                                                                peer_delta);
+        });
+    else
+        launch(blocks, rlic::kThreads, [&] {
+            rlic::lic_replay_kernel<T, Taps, Idx, GROUPS, false>(tex, rec, out, g, taps, ntaps, plane_cells, nullptr, 0);
+        });
+}
+
+template <typename T>
+int pass_paths(const T *tex, const T *field, T *out, const int64_t *geom, int64_t nfields, int64_t first_row,
+               int64_t out_rows, int uv_mode, const T *host_taps, int64_t klen, int wide, int mode, unsigned *rec,
+               T *peer_out, int64_t peer_row_delta)
+{
+    PassGeom g = geometry_from(geom);
+    if (out_rows <= 0 || g.nx <= 0 || nfields <= 0) return 0;
+    g.first_row = (int)first_row;
+    g.out_rows = (int)out_rows;
+    g.tiles_x = (g.nx + rlic::kTileW - 1) / rlic::kTileW;
+    const int64_t per_field = ((out_rows + rlic::kTileH - 1) / rlic::kTileH) * g.tiles_x;
+    g.tiles_per_field = (int)per_field;
+    const unsigned blocks = (unsigned)(per_field * nfields);
+    const long long plane_cells = g.field_stride * nfields;
+    const long long delta = (long long)peer_row_delta * g.pitch;
+    const bool pol = uv_mode == 1;
+    const int ntaps = (int)klen;
+    constexpr int kMaxParam = rlic::kParamTapBytes / (int)sizeof(T);
+    using PT = rlic::ParamTaps<T, kMaxParam>;
+    using GT = rlic::GlobalTaps<T>;
+    using ST = rlic::StepTaps<T, rlic::kStepTapsPerHalf<T>>;
+    using GST = rlic::GlobalStepTaps<T>;
+    const bool in_param = klen <= kMaxParam;
+    if (mode == 1) {
+        PT pt;
+        std::memset(pt.w, 0, sizeof pt.w);
+        if (in_param) std::memcpy(pt.w, host_taps, sizeof(T) * (size_t)klen);
+        const GT gt{host_taps};
+#define EMU_RECORD(POL, TAPS, TAPV)                                                                                   \
+    do {                                                                                                              \
+        if (wide) run_record<T, POL, TAPS, long long>(tex, field, out, g, TAPV, ntaps, blocks, rec, plane_cells, peer_out, delta); \
+        else run_record<T, POL, TAPS, int>(tex, field, out, g, TAPV, ntaps, blocks, rec, plane_cells, peer_out, delta); \
+    } while (0)
+        if (in_param) { if (pol) EMU_RECORD(true, PT, pt); else EMU_RECORD(false, PT, pt); }
+        else          { if (pol) EMU_RECORD(true, GT, gt); else EMU_RECORD(false, GT, gt); }
+#undef EMU_RECORD
+        return 0;
+    }
+    if (mode != 2) return 1;
+    // the taps in walking order, as TapSet::prepare() lays them out
+    ST st;
+    std::memset(&st, 0, sizeof st);
+    const int64_t kmid = klen / 2;
+    if (in_param) {
+        st.centre = host_taps[kmid];
+        for (int64_t k = kmid + 1; k < klen; ++k) st.fwd[k - kmid - 1] = host_taps[k];
+        for (int64_t k = kmid - 1; k >= 0; --k) st.bwd[kmid - 1 - k] = host_taps[k];
+    }
+    const GST gst{host_taps, (int)kmid};
+    const int groups = std::max(rlic::path_groups_fwd(klen), rlic::path_groups_bwd(klen));
+#define EMU_REPLAY(TAPS, TAPV, GROUPS)                                                                               \
+    do {                                                                                                              \
+        if (wide) run_replay<T, TAPS, long long, GROUPS>(tex, out, g, TAPV, ntaps, blocks, rec, plane_cells, peer_out, delta); \
+        else run_replay<T, TAPS, int, GROUPS>(tex, out, g, TAPV, ntaps, blocks, rec, plane_cells, peer_out, delta);   \
+    } while (0)
+    if (!in_param) EMU_REPLAY(GST, gst, 0);
+    else if (groups <= 1) EMU_REPLAY(ST, st, 1);
+    else if (groups == 2) EMU_REPLAY(ST, st, 2);
+    else EMU_REPLAY(ST, st, 0);
+#undef EMU_REPLAY
     return 0;
 }
 
@@ -328,4 +433,18 @@ EMU_DEFINE_PEER(f32, float)
 #endif
 #ifdef EMU_UNIT_F64
 EMU_DEFINE_PEER(f64, double)
+#endif
+
+#define EMU_DEFINE_PATHS(SFX, T)                                                                             \
+    extern "C" int emu_pass_paths_##SFX(const T *tex, const T *field, T *out, const int64_t *geom,           \
+                                        int64_t nfields, int64_t first_row, int64_t out_rows, int uv_mode,   \
+                                        const T *taps, int64_t klen, int wide, int mode, unsigned *rec,      \
+                                        T *peer_out, int64_t peer_row_delta)                                 \
+    { return pass_paths<T>(tex, field, out, geom, nfields, first_row, out_rows, uv_mode, taps, klen, wide,   \
+                           mode, rec, peer_out, peer_row_delta); }
+#ifdef EMU_UNIT_F32
+EMU_DEFINE_PATHS(f32, float)
+#endif
+#ifdef EMU_UNIT_F64
+EMU_DEFINE_PATHS(f64, double)
 #endif
