@@ -219,7 +219,7 @@ def test_thread_options_override_the_defaults_for_one_thread_only():
     import rlic_b200
 
     base = rlic_b200.effective_options()
-    assert base == {"arithmetic": "fma+branchless", "schedule": "wavefront", "walk": "grouped"}
+    assert base == {"arithmetic": "fma+branchless", "schedule": "wavefront", "walk": "grouped", "paths": "replay"}
     seen = {}
 
     def other_thread():
@@ -235,8 +235,8 @@ def test_thread_options_override_the_defaults_for_one_thread_only():
         with rlic_b200.options(walk="per-step"):          # nests: keeps the outer overrides
             nested = rlic_b200.effective_options()
         assert rlic_b200.effective_options() == mine
-    assert mine == {"arithmetic": "fma", "schedule": "trailing", "walk": "grouped"}
-    assert nested == {"arithmetic": "fma", "schedule": "trailing", "walk": "per-step"}
+    assert mine == {"arithmetic": "fma", "schedule": "trailing", "walk": "grouped", "paths": "replay"}
+    assert nested == {"arithmetic": "fma", "schedule": "trailing", "walk": "per-step", "paths": "replay"}
     assert seen["other"] == base
     assert seen["other_inside"] == dict(base, walk="per-step")
     assert rlic_b200.effective_options() == base
