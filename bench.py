@@ -321,6 +321,9 @@ def workload_config(world: int) -> dict:
         "boundaries": "closed", "uv_mode": "velocity",
         "l2": "inputs larger than L2 (padded texture 2 x 64 MiB + packed field 256 MiB + dense in/out 128 MiB per GPU vs 126 MB)",
         "step": "pack field + pad texture + 5 passes + un-pad" if world == 1 else "5 x (edge strips, halo exchange, interior)",
+        "passes": "pass 1 walks the streamlines and records each walker's moves; passes 2-5 replay the record "
+                  "(a path depends on the field, never on the texture): same bits as walking every pass; "
+                  "every step records afresh, nothing is kept between steps (RLIC_B200_PATHS=recompute walks every pass)",
     }
 
 
@@ -379,6 +382,14 @@ def run_ours(args) -> dict:
         pad_b = torch.empty(cells, dtype=torch.float32, device=dev)
         field = torch.empty(4 * cells, dtype=torch.float32, device=dev)
         taps_ptr = kernel.ctypes.data_as(p_f32)
+        # what rlic_b200_convolve_device_* does with the library's options in force: the first pass
+        # records the streamline paths, the others replay them -- or, with
+        # RLIC_B200_PATHS=recompute (or the per-step walk / `fma` arithmetic), every pass walks
+        opts = rlic_b200.effective_options()
+        replay = (opts["paths"] == "replay" and opts["walk"] == "grouped" and opts["arithmetic"] == "fma+branchless"
+                  and ITERATIONS >= 2)
+        record = (torch.empty(_core.path_record_bytes(N_SIDE, N_SIDE, TAPS) // 4, dtype=torch.int32, device=dev)
+                  if replay else None)
 
         def step(events=None):
             st = int(torch.cuda.current_stream().cuda_stream)
@@ -389,10 +400,18 @@ def run_ours(args) -> dict:
             if events is not None:
                 events[0].record()
             src, dst = pad_a, pad_b
-            for _ in range(ITERATIONS):
-                _core.check(lib.rlic_b200_pass_slab_f32(src.data_ptr(), field.data_ptr(), dst.data_ptr(),
-                                                        *slab, 0, N_SIDE, taps_ptr, kernel.size, 0,
-                                                        *closed, st))
+            for it in range(ITERATIONS):
+                if replay:
+                    _core.check(lib.rlic_b200_pass_slab_paths_f32(
+                        src.data_ptr(), field.data_ptr(), dst.data_ptr(), *slab, 0, N_SIDE, taps_ptr, kernel.size,
+                        0, *closed, None, 0, _core.PASS_RECORD if it == 0 else _core.PASS_REPLAY,
+                        record.data_ptr(), st))
+                else:
+                    _core.check(lib.rlic_b200_pass_slab_f32(src.data_ptr(), field.data_ptr(), dst.data_ptr(),
+                                                            *slab, 0, N_SIDE, taps_ptr, kernel.size, 0,
+                                                            *closed, st))
+                if it == 0 and events is not None:
+                    events[2].record()           # between the first pass and the others
                 src, dst = dst, src
             if events is not None:
                 events[1].record()
@@ -408,16 +427,18 @@ def run_ours(args) -> dict:
                               exchange=os.environ.get("RLIC_B200_EXCHANGE", "peer"))
         sc.set_field(d_u, d_v)
 
+        replay = False
+
         def step(events=None):
             if events is not None:
                 events[0].record()
+                events[2].record()
             out = sc.convolve(d_tex, iterations=ITERATIONS)
             if events is not None:
                 events[1].record()
             return out
 
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-          for _ in range(args.steps)]
+    ev = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(3)) for _ in range(args.steps)]
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     # one sampler for the job: rank 0 watches every GPU the job uses
     with ClockSampler(",".join(str(i) for i in range(world)) if rank == 0 else None) as clocks:
@@ -434,7 +455,9 @@ def run_ours(args) -> dict:
         clocks.mark_end()
         launches = _core.launch_count() - launches0
     total_ms = t_begin.elapsed_time(t_end)
-    pass_ms = sum(a.elapsed_time(b) for a, b in ev)   # the 5 pass launches of every step
+    pass_ms = sum(a.elapsed_time(b) for a, b, _ in ev)   # the 5 pass launches of every step
+    first_ms = sum(a.elapsed_time(m) for a, _, m in ev) / args.steps      # world == 1: the first pass alone
+    later_ms = sum(m.elapsed_time(b) for _, b, m in ev) / args.steps / max(ITERATIONS - 1, 1)   # each of the others
     if dist is not None:
         t = torch.tensor([total_ms, pass_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -449,6 +472,11 @@ def run_ours(args) -> dict:
     passes = args.steps * ITERATIONS
     pass_avg_ms = pass_ms / passes
     peak, peak_src = measured_peak_gbs()
+    if world == 1 and replay:
+        # `roofline` proper describes the walking pass -- the kernel SURVEY.md section 8(d)'s
+        # algorithmic bytes are defined for, and the longest launch of the step; the replay kernel
+        # (four launches per step) has its own object, roofline["replay"], below
+        pass_avg_ms = first_ms
     achieved = gather_bytes_per_pixel() * pixels_local / (pass_avg_ms * 1e-3) / 1e9
     traffic = None
     tf = ROOT / "profiles" / "traffic.json"
@@ -466,6 +494,30 @@ def run_ours(args) -> dict:
         "note": "achieved = (3*(L-1)+2)*4 gather bytes per pixel x pixels per launch / mean launch time",
     }
 
+    if world == 1 and replay:
+        groups = 2 * ((TAPS // 2 + 31) // 32)
+        replay_bytes = (TAPS - 1) * 4 + 4 + 4 + 3 * 4 * groups      # gathers + centre + store + three planes per group
+        roofline["kernel"] = ("lic_pass_kernel<float,...,REC> (pass 1: the walk, recording the paths; "
+                              f"{first_ms:.3f} of the {pass_ms / args.steps:.3f} ms the step's passes take)")
+        roofline["algorithmic_bytes_per_launch"] = gather_bytes_per_pixel() * pixels_local
+        roofline["step_share"] = {"walk_record_ms": first_ms, "replay_ms_each": later_ms,
+                                  "replay_launches": ITERATIONS - 1, "passes_ms": pass_ms / args.steps}
+        roofline["replay"] = {
+            "bound": "hbm", "kernel": "lic_replay_kernel<float,...> (passes 2-5: one launch each)",
+            "achieved": replay_bytes * pixels_local / (later_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+            "frac": replay_bytes * pixels_local / (later_ms * 1e-3) / 1e9 / peak,
+            "algorithmic_bytes_per_launch": replay_bytes * pixels_local, "launch_ms": later_ms,
+            "note": f"algorithmic bytes per pixel = (L-1)*4 texture gathers + centre + store + {3 * groups} plane words "
+                    f"x 4 = {replay_bytes} (the replay reads no field); nominal like the fraction above: the gathers "
+                    "are served by L1/L2",
+            "vs_walking_pass": first_ms / later_ms,
+        }
+        try:
+            tr = json.loads(tf.read_text())
+            roofline["traffic"] = tr.get("lic_pass_record_kernel_dram_bytes_per_launch", traffic)
+            roofline["replay"]["traffic"] = tr.get("lic_replay_kernel_dram_bytes_per_launch")
+        except Exception:
+            roofline["replay"]["traffic"] = None
     roofline["frac_note"] = ("nominal: section 8(d)'s algorithmic gather bytes over the HBM copy peak; the gathers "
                              "are served by L1/L2 (DRAM traffic per launch is the compulsory 0.4 GB), so this "
                              "fraction exceeds 1 -- the bound that holds is gather_peak below")
@@ -497,6 +549,24 @@ def run_ours(args) -> dict:
                        "staircase walkers, same image, same launch shape; CUDA events, best of 5, this run",
             }
             roofline["frac_of_gather_peak"] = achieved / peak_g
+            if replay:
+                # the replay kernel's own ceiling: the same probe without the field record
+                times = []
+                for _ in range(6):
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    _core.check(lib.rlic_b200_measure_gather_ceiling_f32(
+                        pad_a.data_ptr(), field.data_ptr(), pad_b.data_ptr(), N_SIDE, N_SIDE, taps_ptr,
+                        kernel.size, 2, int(torch.cuda.current_stream().cuda_stream)))
+                    b.record()
+                    b.synchronize()
+                    times.append(a.elapsed_time(b))
+                rp = roofline["replay"]
+                peak_r = rp["algorithmic_bytes_per_launch"] / (min(times[1:]) * 1e-3) / 1e9
+                rp["gather_peak"] = {"GBps": peak_r, "launch_ms": min(times[1:]),
+                                     "how": "the same probe with dependent=2: one texture value per step and the "
+                                            "tap FMA, no field record; best of 5, this run"}
+                rp["frac_of_gather_peak"] = rp["achieved"] / peak_r
         except Exception as exc:  # noqa: BLE001 -- a reporting extra
             roofline["gather_peak"] = {"error": f"{type(exc).__name__}: {exc}"}
 
@@ -507,6 +577,8 @@ def run_ours(args) -> dict:
     try:
         walk = rlic_b200.effective_options()["walk"]
         src = {"per-step": "r1_pass_kernel_ncu_summary.json", "grouped": "r2_pass_kernel_ncu_summary.json"}[walk]
+        if world == 1 and replay and (ROOT / "profiles" / "r2_record_kernel_ncu_summary.json").exists():
+            src = "r2_record_kernel_ncu_summary.json"
         prof = json.loads((ROOT / "profiles" / src).read_text())
         ips = float(prof["warp_instructions_per_pixel_step"])
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
@@ -522,6 +594,16 @@ def run_ours(args) -> dict:
             }
     except Exception as exc:  # noqa: BLE001 -- a reporting extra, never allowed to fail the line
         roofline["issue"] = {"error": f"{type(exc).__name__}: {exc}"}
+    if world == 1 and replay:
+        try:
+            src = "r2_replay_kernel_ncu_summary.json"
+            ips = float(json.loads((ROOT / "profiles" / src).read_text())["warp_instructions_per_pixel_step"])
+            mhz = clocks.summary().get("sm_mhz") or clocks.summary().get("sm_max_mhz")
+            ceiling_ms = pixels_local * (TAPS - 1) / 32 * ips / (4 * sms * mhz * 1e6) * 1e3
+            roofline["replay"]["issue"] = {"warp_instructions_per_pixel_step": ips, "source": f"profiles/{src}",
+                                           "ceiling_ms": ceiling_ms, "frac": ceiling_ms / later_ms}
+        except Exception as exc:  # noqa: BLE001
+            roofline["replay"]["issue"] = {"error": f"{type(exc).__name__}: {exc}"}
 
     # ---------------- end to end through the public API, host buffers ---------
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()  # noqa: E731

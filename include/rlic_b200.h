@@ -489,8 +489,10 @@ int rlic_b200_equalize_histogram_f64(const double *image, int64_t ny, int64_t nx
  * the loads of a pass -- per step one field record and one texture value at the walker's
  * cell -- and the tap FMA, and nothing else; the walkers climb a staircase (+1 column, +1
  * row, ...) forward and descend it backward, so neighbouring threads touch neighbouring cells
- * as walkers on a smooth field do.  `dependent` != 0 makes each address wait for the record
- * loaded before it, as in the real walk.  Buffers: a padded texture, a packed field and a
+ * as walkers on a smooth field do.  `dependent` = 1 makes each address wait for the record
+ * loaded before it, as in the real walk; `dependent` = 2 performs the loads of a REPLAYED pass
+ * instead (one texture value per step, no field record: the ceiling of the replay kernel).
+ * Buffers: a padded texture, a packed field and a
  * padded output of the whole ny x nx image (closed walls), as the slab entry points above
  * produce them.  The caller times the launch; d_padded_out is NOT a convolution result.
  */

@@ -1697,7 +1697,10 @@ RLIC_DEFINE_EQUALIZE(double, f64)
         TapSet<T> taps;                                                                          \
         CUDA_TRY(taps.prepare(kernel, klen, s));                                                 \
         const Field<T> *field = reinterpret_cast<const Field<T> *>(d_field);                     \
-        if (dependent)                                                                           \
+        if (dependent == 2)   /* the replay's loads: one texture value per step, no field */     \
+            rlic::gather_ceiling_kernel<T, false, false><<<g.tiles_per_field, 256, 0, s>>>(      \
+                d_padded_texture, field, d_padded_out, g, taps.param, (int)klen);                \
+        else if (dependent)                                                                      \
             rlic::gather_ceiling_kernel<T, true><<<g.tiles_per_field, 256, 0, s>>>(              \
                 d_padded_texture, field, d_padded_out, g, taps.param, (int)klen);                \
         else                                                                                     \

@@ -328,7 +328,7 @@ void run_type(const char *tname, int n, int L, const char *only)
         CK(cudaMemset(ref, 0, cells * sizeof(T)));
         for (int r = 0; r < reps + 1; ++r) {
             CK(cudaEventRecord(e0));
-            k<<<g.tiles_per_field, rlic::kThreads>>>(ptex, field, ref, g, taps, L);
+            k<<<g.tiles_per_field, rlic::kThreads>>>(ptex, field, ref, g, taps, L, rlic::PathPlanes{});
             CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
             float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); if (r) best = fminf(best, ms);
         }
@@ -347,7 +347,7 @@ void run_type(const char *tname, int n, int L, const char *only)
         CK(cudaMemset(out, 0, cells * sizeof(T))); \
         for (int r = 0; r < reps + 1; ++r) { \
             CK(cudaEventRecord(e0)); \
-            k<<<gc.tiles_per_field, TW * TH>>>(ptex, field, out, gc, taps, L); \
+            k<<<gc.tiles_per_field, TW * TH>>>(ptex, field, out, gc, taps, L, rlic::PathPlanes{}); \
             CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); \
             float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); if (r) best = fminf(best, ms); \
         } \
@@ -363,7 +363,7 @@ void run_type(const char *tname, int n, int L, const char *only)
         float best = 1e9; \
         for (int r = 0; r < reps + 1; ++r) { \
             CK(cudaEventRecord(e0)); \
-            k<<<g.tiles_per_field, TW * TH>>>(ptex, field, out, g, taps, L); \
+            k<<<g.tiles_per_field, TW * TH>>>(ptex, field, out, g, taps, L, rlic::PathPlanes{}); \
             CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); \
             float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); if (r) best = fminf(best, ms); \
         } \
@@ -437,13 +437,13 @@ void run_type(const char *tname, int n, int L, const char *only)
         auto kref = rlic::lic_pass_kernel<T, POL, PT, int>; \
         auto k = rlic::lic_pass_kernel<T, POL, PT, int, 16, 16, UNROLL, MINB, FLAVOR, ADMIT, true, WALK>; \
         CK(cudaMemset(ref, 0, cells * sizeof(T))); \
-        kref<<<g.tiles_per_field, 256>>>(ptex, field, ref, g, taps, L); \
+        kref<<<g.tiles_per_field, 256>>>(ptex, field, ref, g, taps, L, rlic::PathPlanes{}); \
         CK(cudaMemcpy(h_ref.data(), ref, cells * sizeof(T), cudaMemcpyDeviceToHost)); \
         float best = 1e9; \
         CK(cudaMemset(out, 0, cells * sizeof(T))); \
         for (int r = 0; r < reps + 1; ++r) { \
             CK(cudaEventRecord(e0)); \
-            k<<<g.tiles_per_field, 256>>>(ptex, field, out, g, taps, L); \
+            k<<<g.tiles_per_field, 256>>>(ptex, field, out, g, taps, L, rlic::PathPlanes{}); \
             CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); \
             float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); if (r) best = fminf(best, ms); \
         } \
@@ -514,7 +514,7 @@ void run_type(const char *tname, int n, int L, const char *only)
         }
         // the later CAND()s compare with the velocity result of the shipped kernel
         auto kref = rlic::lic_pass_kernel<T, false, PT, int>;
-        kref<<<g.tiles_per_field, 256>>>(ptex, field, ref, g, taps, L);
+        kref<<<g.tiles_per_field, 256>>>(ptex, field, ref, g, taps, L, rlic::PathPlanes{});
         CK(cudaMemcpy(h_ref.data(), ref, cells * sizeof(T), cudaMemcpyDeviceToHost));
     }
     // lab20: TMA-staged texture window (f32, this image only: closed walls, 65 taps -> H = 32)
