@@ -130,8 +130,8 @@ void rlic_b200_get_effective_options(int *arithmetic, int *schedule, int *walk);
  * every iteration (lib.rs:432-440), so every pass of a call walks the same paths.
  *   RLIC_B200_PATHS_REPLAY     (default) the first pass of a call with iterations >= 2 records,
  *                              per pixel and step, which way its walker went (bit planes in
- *                              device memory, 4 bytes per pixel, plane and 32 steps: 32 bytes
- *                              per pixel for 65 taps); the other passes replay the record:
+ *                              device memory, 16 bytes per pixel and 32 steps: 32 bytes per
+ *                              pixel for 65 taps); the other passes replay the record:
  *                              per step a move, the texture gather and the reference's fused
  *                              multiply-add with that step's tap, in the reference's order --
  *                              the same bits for about a fifth of the instructions.
@@ -167,6 +167,12 @@ void rlic_b200_debug_force_wide_index(int on);
  * one-thread-per-pixel kernel instead of the two-warps-per-pixel one that halves their latency
  * (lic_pass_pair_kernel, lic_walk.cuh).  Same bits either way; default 1. */
 void rlic_b200_debug_small_image_kernel(int on);
+
+/* Testing / measurement hook: 0 keeps replayed passes (RLIC_B200_PATHS_REPLAY) on the kernel that
+ * gathers the texture through L1; 1 (default) lets kernels of up to 65 taps use the one that
+ * stages each tile's texture window in shared memory.  Same bits either way.  Also settable
+ * with the environment variable RLIC_B200_REPLAY_STAGING=0 (read by the Python binding). */
+void rlic_b200_debug_replay_staging(int on);
 
 /* Testing hook (host code only, no GPU needed): what the padded layout puts in
  * cell `cell` of the buffer of the slab {row0, nrows, halo_lo, halo_hi} of an
@@ -558,6 +564,8 @@ int rlic_b200_pass_slab_peer_f64(const double *d_texture, const double *d_field,
  *                                                         rows it computes into d_paths
  *                                  RLIC_B200_PASS_REPLAY  the rows are computed from the record
  *                                                         (d_field is not read, may be NULL)
+ *                      d_paths must be 16-byte aligned (cudaMalloc and every framework
+ *                      allocator are).
  *                      The record belongs to (field, uv_mode, boundaries, kernel length, slab):
  *                      replaying it with anything else is the caller's error.  Default
  *                      arithmetic and the grouped walk only (EINVAL otherwise).

@@ -134,6 +134,13 @@ def _load() -> ctypes.CDLL:
         getattr(cdll, f"rlic_b200_{name}").restype = _int
     cdll.rlic_b200_path_record_bytes.argtypes = [_i64, _i64, _i64]
     cdll.rlic_b200_path_record_bytes.restype = _i64
+    cdll.rlic_b200_debug_replay_staging.argtypes = [_int]
+    cdll.rlic_b200_debug_replay_staging.restype = None
+    staging = os.environ.get("RLIC_B200_REPLAY_STAGING")
+    if staging:
+        if staging not in ("0", "1"):
+            raise ImportError(f"RLIC_B200_REPLAY_STAGING={staging!r}: expected 0 or 1")
+        cdll.rlic_b200_debug_replay_staging(int(staging))
     paths = os.environ.get("RLIC_B200_PATHS")
     if paths:
         if paths not in PATHS:

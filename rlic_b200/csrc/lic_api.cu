@@ -33,6 +33,7 @@ thread_local int tls_device = 0;
 std::atomic<int64_t> g_launches{0};
 std::atomic<int> g_force_wide{0};   // testing hook: use 64-bit element indices for any size
 std::atomic<int> g_small_images{1}; // testing hook: 0 keeps small passes on the one-thread-per-pixel kernel
+std::atomic<int> g_replay_staging{1}; // testing hook: 0 keeps replayed passes on the kernel that gathers through L1
 // The three choices a call can make (include/rlic_b200.h): which reference build to reproduce,
 // which formulation of the pass kernels, how the host path orders its launches.  Each has a
 // process-wide DEFAULT (the atomics: set once at start-up, e.g. from the environment) and a
@@ -335,8 +336,8 @@ template <typename T> struct PeerTarget {
 enum class Paths { none, record, replay };
 struct PathUse {
     Paths mode = Paths::none;
-    unsigned *rec = nullptr;       // planes * plane_cells words
-    long long plane_cells = 0;     // cells of the whole padded buffer (every field)
+    uint4 *rec = nullptr;          // groups * group_cells entries (one per pixel and group of 32 steps)
+    long long group_cells = 0;     // cells of the whole padded buffer (every field)
 };
 
 // words of the record of one padded buffer of `cells` cells, for a kernel of `klen` taps
@@ -361,7 +362,7 @@ cudaError_t launch_one(const T *tex, const Field<T> *field, T *out, const PassGe
     using Tn = rlic::Tune<T, POL>;
     const rlic::PathPlanes none{nullptr, 0, 0};
     if (paths.mode == Paths::record) {   // grouped walk, default arithmetic (checked by the caller)
-        const rlic::PathPlanes planes{paths.rec, paths.plane_cells, rlic::path_groups_fwd(ntaps)};
+        const rlic::PathPlanes planes{paths.rec, paths.group_cells, rlic::path_groups_fwd(ntaps)};
         if (peer.out)
             rlic::lic_pass_peer_kernel<T, POL, Taps, Idx, rlic::kTileW, rlic::kTileH, Tn::walk_unroll,
                                        record_min_blocks<T, POL>(), Tn::walk_flavor, Tn::walk_admit, true, Tn::walk, true>
@@ -445,22 +446,48 @@ bool paths_are_replayed(int64_t iterations)
            effective_arithmetic() == RLIC_B200_ARITH_FMA_BRANCHLESS && effective_walk() == RLIC_B200_WALK_GROUPED;
 }
 
-// One pass by replay of the recorded paths (lic_replay_kernel); g carries the launch's rows and tiles.
+// One pass by replay of the recorded paths (lic_replay_kernel); g carries the launch's rows.
+// The grid is (tile column, tile row, field).
 template <typename T, typename Idx>
-cudaError_t launch_replay(const T *tex, T *out, const PassGeom &g, const TapSet<T> &taps, unsigned blocks,
+cudaError_t launch_replay(const T *tex, T *out, const PassGeom &g, int64_t nfields, const TapSet<T> &taps,
                           const PeerTarget<T> &peer, const PathUse &paths, cudaStream_t stream)
 {
     using ST = rlic::StepTaps<T, rlic::kStepTapsPerHalf<T>>;
     using GT = rlic::GlobalStepTaps<T>;
     const int groups = std::max(rlic::path_groups_fwd(taps.ntaps), rlic::path_groups_bwd(taps.ntaps));
+    // kernels of up to 65 taps whose window fits: the texture window of each tile staged in
+    // shared memory (lic_replay_staged_kernel)
+    if (taps.in_param && groups <= 1 && sizeof(Idx) == 4 && g_replay_staging.load(std::memory_order_relaxed) != 0 &&
+        rlic::staged_window_bytes(taps.ntaps, sizeof(T)) <= rlic::kStagedMaxBytes) {
+        const dim3 sgrid((unsigned)((g.nx + rlic::kStagedTW - 1) / rlic::kStagedTW),
+                         (unsigned)((g.out_rows + rlic::kStagedTH - 1) / rlic::kStagedTH), (unsigned)nfields);
+        if (sgrid.y > 65535u || sgrid.z > 65535u)
+            return cudaErrorInvalidConfiguration;
+        const size_t smem = (size_t)rlic::staged_window_bytes(taps.ntaps, sizeof(T));
+        if (peer.out)
+            rlic::lic_replay_staged_kernel<T, ST, int, true, rlic::kStagedTW, rlic::kStagedTH, rlic::kStagedPad,
+                                           rlic::kStagedMinBlocks>
+                <<<sgrid, rlic::kStagedTW * rlic::kStagedTH, smem, stream>>>(
+                    tex, paths.rec, out, g, taps.steps, taps.ntaps, paths.group_cells, peer.out, peer.delta);
+        else
+            rlic::lic_replay_staged_kernel<T, ST, int, false, rlic::kStagedTW, rlic::kStagedTH, rlic::kStagedPad,
+                                           rlic::kStagedMinBlocks>
+                <<<sgrid, rlic::kStagedTW * rlic::kStagedTH, smem, stream>>>(
+                    tex, paths.rec, out, g, taps.steps, taps.ntaps, paths.group_cells, nullptr, 0);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        return cudaGetLastError();
+    }
+    const dim3 grid((unsigned)g.tiles_x, (unsigned)((g.out_rows + rlic::kTileH - 1) / rlic::kTileH), (unsigned)nfields);
+    if (grid.y > 65535u || grid.z > 65535u)
+        return cudaErrorInvalidConfiguration;
 #define RLIC_REPLAY(TAPS, TAPV, GROUPS)                                                                    \
     do {                                                                                                   \
         if (peer.out)                                                                                      \
-            rlic::lic_replay_kernel<T, TAPS, Idx, GROUPS, true><<<blocks, rlic::kThreads, 0, stream>>>(    \
-                tex, paths.rec, out, g, TAPV, taps.ntaps, paths.plane_cells, peer.out, peer.delta);        \
+            rlic::lic_replay_kernel<T, TAPS, Idx, GROUPS, true><<<grid, rlic::kThreads, 0, stream>>>(      \
+                tex, paths.rec, out, g, TAPV, taps.ntaps, paths.group_cells, peer.out, peer.delta);        \
         else                                                                                               \
-            rlic::lic_replay_kernel<T, TAPS, Idx, GROUPS, false><<<blocks, rlic::kThreads, 0, stream>>>(   \
-                tex, paths.rec, out, g, TAPV, taps.ntaps, paths.plane_cells, nullptr, 0);                  \
+            rlic::lic_replay_kernel<T, TAPS, Idx, GROUPS, false><<<grid, rlic::kThreads, 0, stream>>>(     \
+                tex, paths.rec, out, g, TAPV, taps.ntaps, paths.group_cells, nullptr, 0);                  \
     } while (0)
     if (!taps.in_param) {
         const GT gt{static_cast<const T *>(taps.global.p), taps.ntaps / 2};
@@ -521,8 +548,8 @@ int launch_pass(const T *tex, const Field<T> *field, T *out, PassGeom g, int64_t
 
     cudaError_t e;
     if (paths.mode == Paths::replay) {
-        e = wide ? launch_replay<T, long long>(tex, out, g, taps, (unsigned)blocks, peer, paths, stream)
-                 : launch_replay<T, int>(tex, out, g, taps, (unsigned)blocks, peer, paths, stream);
+        e = wide ? launch_replay<T, long long>(tex, out, g, nfields, taps, peer, paths, stream)
+                 : launch_replay<T, int>(tex, out, g, nfields, taps, peer, paths, stream);
         CUDA_TRY(e);
         return RLIC_B200_OK;
     }
@@ -599,20 +626,20 @@ bool path_record_fits(size_t bytes)
 // The record of a call: allocated when its passes replay, and how pass `p` (1-based) uses it.
 struct CallPaths {
     DeviceBuf buf;
-    long long plane_cells = 0;
+    long long group_cells = 0;
     bool on = false;
     cudaError_t prepare(int64_t iterations, int64_t cells, int64_t klen, cudaStream_t stream)
     {
         const size_t bytes = path_record_words(cells, klen) * sizeof(unsigned);
         on = paths_are_replayed(iterations) && bytes > 0 && path_record_fits(bytes);
-        plane_cells = cells;
+        group_cells = cells;
         return on ? buf.alloc(bytes, stream) : cudaSuccess;
     }
     PathUse use(int64_t pass) const
     {
         if (!on)
             return PathUse{};
-        return PathUse{pass == 1 ? Paths::record : Paths::replay, static_cast<unsigned *>(buf.p), plane_cells};
+        return PathUse{pass == 1 ? Paths::record : Paths::replay, static_cast<uint4 *>(buf.p), group_cells};
     }
 };
 
@@ -649,7 +676,10 @@ int convolve_host(const T *tex, const T *u, const T *v, int64_t nfields, int64_t
     const int64_t reach = klen / 2;
     int64_t nbands = 1;
     if (nfields == 1) {
-        nbands = std::min<int64_t>(8, (int64_t)(count >> 21));           // >= 2 Mpix per band
+        // >= 1 Mpix per band, at most 16: with replayed passes the compute is no longer than the
+        // uploads, and what an upload-bound call waits for at the end is the skew of the wavefront
+        // (the last pass of band b runs `iterations` bands behind the uploads), i.e. band size
+        nbands = std::min<int64_t>(16, (int64_t)(count >> 20));
         nbands = std::min<int64_t>(nbands, ny / std::max<int64_t>(2 * reach, 64));
         nbands = std::max<int64_t>(nbands, 1);
     }
@@ -1077,8 +1107,8 @@ int pass_slab(const T *d_tex, const T *d_field, T *d_out, int64_t ny, int64_t nx
     peer.delta = (long long)peer_row_delta * g.pitch;
     PathUse paths;
     if (paths_mode != RLIC_B200_PASS_WALK)
-        paths = PathUse{paths_mode == RLIC_B200_PASS_RECORD ? Paths::record : Paths::replay, d_paths,
-                        (long long)g.field_stride};
+        paths = PathUse{paths_mode == RLIC_B200_PASS_RECORD ? Paths::record : Paths::replay,
+                        reinterpret_cast<uint4 *>(d_paths), (long long)g.field_stride};
     return launch_pass<T>(d_tex, reinterpret_cast<const Field<T> *>(d_field), d_out, g, 1,
                           sl.halo_lo + sub0, subn, uv_mode, taps, s, peer, nullptr, nullptr, paths);
 }
@@ -1422,6 +1452,8 @@ void rlic_b200_result_free(void *block)
 void rlic_b200_debug_force_wide_index(int on) { g_force_wide.store(on ? 1 : 0); }
 
 void rlic_b200_debug_small_image_kernel(int on) { g_small_images.store(on ? 1 : 0); }
+
+void rlic_b200_debug_replay_staging(int on) { g_replay_staging.store(on ? 1 : 0); }
 
 int rlic_b200_set_device(int device)
 {

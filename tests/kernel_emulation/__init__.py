@@ -173,11 +173,16 @@ class SlabOps:
         sfx, real = _kind(self._np(src).dtype)
         g = self._geom(plan, walls, taps.size)
         rec = self._np(paths).view(np.uint32)
-        rc = getattr(lib(), f"emu_pass_paths_{sfx}")(
-            _ptr(self._np(src), real), _ptr(self._np(field), real), _ptr(self._np(dst), real), _ptr(g, _i64), 1,
-            plan.halo_lo + a, b - a, mode, _ptr(taps, real), taps.size, 0, int(paths_mode),
-            rec.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)),
-            None if peer is None else _ptr(self._np(peer), real), peer_row_delta)
+        # a replayed pass: the staged kernel where the library would use it (rc 2: not eligible)
+        modes = (3, 2) if int(paths_mode) == 2 and getattr(self, "staging", True) else (int(paths_mode),)
+        for m in modes:
+            rc = getattr(lib(), f"emu_pass_paths_{sfx}")(
+                _ptr(self._np(src), real), _ptr(self._np(field), real), _ptr(self._np(dst), real), _ptr(g, _i64), 1,
+                plan.halo_lo + a, b - a, mode, _ptr(taps, real), taps.size, 0, m,
+                rec.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)),
+                None if peer is None else _ptr(self._np(peer), real), peer_row_delta)
+            if rc != 2:
+                break
         assert rc == 0
 
 
@@ -237,7 +242,9 @@ class Buffers:
 
     def run_pass_paths(self, src, dst, taps, uv_mode, mode, rec, rows=None, wide=False, peer=None,
                        peer_row_delta=0):
-        """One pass that records (mode 1: the tuned grouped walk) or replays (mode 2) the paths."""
+        """One pass that records (mode 1: the tuned grouped walk) or replays the paths (mode 2: gathers
+        through L1; mode 3: the texture window staged in shared memory -- returns False when the
+        library would not use that kernel for this case)."""
         first, count = rows or (self.slab[2], self.slab[1])
         taps = np.ascontiguousarray(taps, dtype=self.dtype)
         rc = getattr(lib(), f"emu_pass_paths_{self.sfx}")(
@@ -245,7 +252,8 @@ class Buffers:
             self._g, self.nfields, first, count, _core.mode_code(uv_mode), _ptr(taps, self.real), taps.size,
             int(wide), int(mode), rec.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)),
             None if peer is None else _ptr(peer, self.real), peer_row_delta)
-        assert rc == 0, "no such paths mode"
+        assert rc in (0, 2), "no such paths mode"
+        return rc == 0
 
 
 def convolve(texture, u, v, *, kernel, uv_mode="velocity", boundaries=(("closed", "closed"),) * 2,
@@ -260,8 +268,12 @@ def convolve(texture, u, v, *, kernel, uv_mode="velocity", boundaries=(("closed"
     src = 0
     rec = b.path_record(len(kernel)) if paths else None
     for it in range(iterations):
-        if paths:
-            b.run_pass_paths(src, 1 - src, kernel, uv_mode, 1 if it == 0 else 2, rec, wide=wide)
+        if paths and it == 0:
+            b.run_pass_paths(src, 1 - src, kernel, uv_mode, 1, rec, wide=wide)
+        elif paths:
+            # paths="staged": the shared-memory kernel where the library would launch it
+            if not (paths == "staged" and b.run_pass_paths(src, 1 - src, kernel, uv_mode, 3, rec, wide=wide)):
+                b.run_pass_paths(src, 1 - src, kernel, uv_mode, 2, rec, wide=wide)
         else:
             b.run_pass(src, 1 - src, kernel, uv_mode, wide=wide, flavor=flavor, admit=admit,
                        branchless=branchless, walk=walk)

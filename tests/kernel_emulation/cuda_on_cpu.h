@@ -27,6 +27,8 @@
 #define __grid_constant__
 
 struct float4 { float x, y, z, w; };
+struct uint4 { unsigned x, y, z, w; };
+static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return {x, y, z, w}; }
 struct double2 { double x, y; };
 static inline float4 make_float4(float x, float y, float z, float w) { return {x, y, z, w}; }
 static inline double2 make_double2(double x, double y) { return {x, y}; }
@@ -75,6 +77,15 @@ namespace emulated {
 struct StepCounts { unsigned long long step, declined, wall, generic; };
 extern thread_local StepCounts step_counts;
 #define RLIC_EMU_EVENT(which) (++emulated::step_counts.which)
+
+// A CTA's shared memory and its barrier, for the one kernel that has them (the staged replay): the
+// emulation runs the threads of a block one after another, twice -- a first sweep in which
+// every thread stops at the barrier (the window is then complete), a second in which the
+// threads carry on past it.  emulate.cpp drives the sweeps.
+extern thread_local bool past_barrier;
+extern thread_local unsigned char shared_bytes[256 * 1024];
+template <typename T> static inline T *shared_window() { return reinterpret_cast<T *>(shared_bytes); }
+static inline bool barrier_then_compute() { return past_barrier; }
 
 static inline float rcp_approx(float b) { return (float)(1.0 / (double)b); }
 static inline double rcp_approx(double b) { return __hiloint2double(__double2hiint(1.0 / b), 0); }

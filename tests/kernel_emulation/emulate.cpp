@@ -23,6 +23,8 @@
 #ifdef EMU_UNIT_F32
 thread_local Dim3 threadIdx, blockIdx, blockDim, gridDim;
 thread_local emulated::StepCounts emulated::step_counts;
+thread_local bool emulated::past_barrier;
+alignas(16) thread_local unsigned char emulated::shared_bytes[256 * 1024];
 #endif
 
 namespace {
@@ -82,6 +84,36 @@ template <typename Body> void launch(unsigned blocks, unsigned threads, Body bod
         g_counts[1] += emulated::step_counts.declined;
         g_counts[2] += emulated::step_counts.wall;
         g_counts[3] += emulated::step_counts.generic;
+    };
+    std::vector<std::thread> pool;
+    for (unsigned w = 1; w < workers; ++w) pool.emplace_back(run);
+    run();
+    for (auto &th : pool) th.join();
+}
+
+// The same for a three-dimensional grid (the replay kernels: tile column, tile row, field).
+// sweeps = 2: a kernel with one barrier (see cuda_on_cpu.h: past_barrier).
+template <typename Body> void launch3(unsigned gx, unsigned gy, unsigned gz, unsigned threads, Body body,
+                                      int sweeps = 1)
+{
+    const unsigned blocks = gx * gy * gz;
+    const unsigned workers = std::max(1u, std::min(blocks, std::thread::hardware_concurrency()));
+    std::atomic<unsigned> next{0};
+    auto run = [&] {
+        gridDim = {gx, gy, gz};
+        blockDim = {threads, 1, 1};
+        for (unsigned b = next.fetch_add(1); b < blocks; b = next.fetch_add(1)) {
+            blockIdx = {b % gx, (b / gx) % gy, b / (gx * gy)};
+            if (sweeps > 1)   // a fresh CTA's shared memory holds nothing useful: NaN patterns, so that a
+                std::memset(emulated::shared_bytes, 0xFF, sizeof emulated::shared_bytes);   // read of an unfilled cell shows
+            for (int sweep = 0; sweep < sweeps; ++sweep) {
+                emulated::past_barrier = sweep == sweeps - 1;
+                for (unsigned t = 0; t < threads; ++t) {
+                    threadIdx = {t, 0, 0};
+                    body();
+                }
+            }
+        }
     };
     std::vector<std::thread> pool;
     for (unsigned w = 1; w < workers; ++w) pool.emplace_back(run);
@@ -292,7 +324,7 @@ void run_record(const T *tex, const T *field, T *out, const PassGeom &g, const T
 {
     using Tn = rlic::Tune<T, POL>;
     auto *f = reinterpret_cast<const rlic::PackedField<T> *>(field);
-    const rlic::PathPlanes planes{rec, plane_cells, rlic::path_groups_fwd(ntaps)};
+    const rlic::PathPlanes planes{reinterpret_cast<uint4 *>(rec), plane_cells, rlic::path_groups_fwd(ntaps)};
     constexpr int kFlavor = Tn::walk_flavor == 4 ? 2 : Tn::walk_flavor;
     if (peer_out)
         launch(blocks, rlic::kThreads, [&] {
@@ -308,17 +340,19 @@ void run_record(const T *tex, const T *field, T *out, const PassGeom &g, const T
 }
 
 template <typename T, typename Taps, typename Idx, int GROUPS>
-void run_replay(const T *tex, T *out, const PassGeom &g, const Taps &taps, int ntaps, unsigned blocks,
-                const unsigned *rec, long long plane_cells, T *peer_out, long long peer_delta)
+void run_replay(const T *tex, T *out, const PassGeom &g, const Taps &taps, int ntaps, unsigned nfields,
+                const unsigned *rec, long long group_cells, T *peer_out, long long peer_delta)
 {
+    const auto *entries = reinterpret_cast<const uint4 *>(rec);
+    const unsigned gy = (unsigned)((g.out_rows + rlic::kTileH - 1) / rlic::kTileH);
     if (peer_out)
-        launch(blocks, rlic::kThreads, [&] {
-            rlic::lic_replay_kernel<T, Taps, Idx, GROUPS, true>(tex, rec, out, g, taps, ntaps, plane_cells, peer_out,
+        launch3((unsigned)g.tiles_x, gy, nfields, rlic::kThreads, [&] {
+            rlic::lic_replay_kernel<T, Taps, Idx, GROUPS, true>(tex, entries, out, g, taps, ntaps, group_cells, peer_out,
                                                                 peer_delta);
         });
     else
-        launch(blocks, rlic::kThreads, [&] {
-            rlic::lic_replay_kernel<T, Taps, Idx, GROUPS, false>(tex, rec, out, g, taps, ntaps, plane_cells, nullptr, 0);
+        launch3((unsigned)g.tiles_x, gy, nfields, rlic::kThreads, [&] {
+            rlic::lic_replay_kernel<T, Taps, Idx, GROUPS, false>(tex, entries, out, g, taps, ntaps, group_cells, nullptr, 0);
         });
 }
 
@@ -360,7 +394,7 @@ int pass_paths(const T *tex, const T *field, T *out, const int64_t *geom, int64_
 #undef EMU_RECORD
         return 0;
     }
-    if (mode != 2) return 1;
+    if (mode != 2 && mode != 3) return 1;
     // the taps in walking order, as TapSet::prepare() lays them out
     ST st;
     std::memset(&st, 0, sizeof st);
@@ -372,10 +406,31 @@ int pass_paths(const T *tex, const T *field, T *out, const int64_t *geom, int64_
     }
     const GST gst{host_taps, (int)kmid};
     const int groups = std::max(rlic::path_groups_fwd(klen), rlic::path_groups_bwd(klen));
+    if (mode == 3) {
+        // lic_replay_staged_kernel, under the conditions launch_replay() uses it
+        if (!in_param || groups > 1 || wide || rlic::staged_window_bytes(klen, sizeof(T)) > rlic::kStagedMaxBytes)
+            return 2;
+        const auto *entries = reinterpret_cast<const uint4 *>(rec);
+        const unsigned gx = (unsigned)((g.nx + rlic::kStagedTW - 1) / rlic::kStagedTW);
+        const unsigned gy = (unsigned)((g.out_rows + rlic::kStagedTH - 1) / rlic::kStagedTH);
+        if (peer_out)
+            launch3(gx, gy, (unsigned)nfields, rlic::kStagedTW * rlic::kStagedTH, [&] {
+                rlic::lic_replay_staged_kernel<T, ST, int, true, rlic::kStagedTW, rlic::kStagedTH, rlic::kStagedPad,
+                                               rlic::kStagedMinBlocks>(tex, entries, out, g, st, ntaps, plane_cells,
+                                                                       peer_out, delta);
+            }, 2);
+        else
+            launch3(gx, gy, (unsigned)nfields, rlic::kStagedTW * rlic::kStagedTH, [&] {
+                rlic::lic_replay_staged_kernel<T, ST, int, false, rlic::kStagedTW, rlic::kStagedTH, rlic::kStagedPad,
+                                               rlic::kStagedMinBlocks>(tex, entries, out, g, st, ntaps, plane_cells,
+                                                                       nullptr, 0);
+            }, 2);
+        return 0;
+    }
 #define EMU_REPLAY(TAPS, TAPV, GROUPS)                                                                               \
     do {                                                                                                              \
-        if (wide) run_replay<T, TAPS, long long, GROUPS>(tex, out, g, TAPV, ntaps, blocks, rec, plane_cells, peer_out, delta); \
-        else run_replay<T, TAPS, int, GROUPS>(tex, out, g, TAPV, ntaps, blocks, rec, plane_cells, peer_out, delta);   \
+        if (wide) run_replay<T, TAPS, long long, GROUPS>(tex, out, g, TAPV, ntaps, (unsigned)nfields, rec, plane_cells, peer_out, delta); \
+        else run_replay<T, TAPS, int, GROUPS>(tex, out, g, TAPV, ntaps, (unsigned)nfields, rec, plane_cells, peer_out, delta);   \
     } while (0)
     if (!in_param) EMU_REPLAY(GST, gst, 0);
     else if (groups <= 1) EMU_REPLAY(ST, st, 1);

@@ -28,14 +28,17 @@ from test_kernel_emulation import WALLS, fuzz_case, random_case
 
 
 def emulated(tex, u, v, kernel, mode="velocity", walls="closed", iterations=2, **how):
-    """record + replay through the emulated kernels, checked against the oracle"""
+    """record + replay through the emulated kernels -- both replay kernels: the one that gathers
+    through L1 and, where the library would launch it, the one with the texture window staged in
+    shared memory -- checked against the oracle"""
     bnd = WALLS[walls]
-    got = ke.convolve(tex, u, v, kernel=kernel, uv_mode=mode, boundaries=bnd, iterations=iterations, paths=True,
-                      **how)
     want = oracle.convolve(np.ascontiguousarray(tex), np.ascontiguousarray(u), np.ascontiguousarray(v),
                            kernel=kernel, uv_mode=mode, boundaries=bnd, iterations=iterations, variant=3)
-    assert got.dtype == tex.dtype and got.shape == tex.shape
-    assert_array_equal(got, want)
+    for paths in (True, "staged"):
+        got = ke.convolve(tex, u, v, kernel=kernel, uv_mode=mode, boundaries=bnd, iterations=iterations, paths=paths,
+                          **how)
+        assert got.dtype == tex.dtype and got.shape == tex.shape
+        assert_array_equal(got, want)
     return got
 
 
@@ -149,8 +152,8 @@ def test_replay_of_a_batch_of_fields():
         b.pad_texture(tex, 0)
         rec = b.path_record(klen)
         src = 0
-        for it in range(3):
-            b.run_pass_paths(src, 1 - src, k, "velocity", 1 if it == 0 else 2, rec)
+        for it, how in enumerate((1, 2, 3)):                 # record, replay through L1, staged replay
+            assert b.run_pass_paths(src, 1 - src, k, "velocity", how, rec)
             src = 1 - src
         got = b.unpad_texture(src)
         for f in range(nf):
@@ -170,7 +173,8 @@ def test_record_in_bands_replay_in_other_bands():
         b.run_pass_paths(0, 1, k, "velocity", 1, rec, rows=rows)
     for rows in ((0, 7), (7, 40), (47, 3)):
         b.run_pass_paths(1, 0, k, "velocity", 2, rec, rows=rows)
-    b.run_pass_paths(0, 1, k, "velocity", 2, rec)
+    for rows in ((0, 21), (21, 5), (26, 24)):                # the staged kernel, tiles cut by the row ranges
+        assert b.run_pass_paths(0, 1, k, "velocity", 3, rec, rows=rows)
     want = oracle.convolve(tex, u, v, kernel=k, boundaries=WALLS["closed"], iterations=3)
     assert_array_equal(b.unpad_texture(1), want)
 
@@ -191,14 +195,14 @@ def test_the_record_does_not_depend_on_the_texture():
 
 
 def test_record_size_and_layout():
-    # four planes of 4 bytes per cell and group of 32 steps, forward groups then backward groups
+    # 16 bytes (four planes) per cell and group of 32 steps, forward groups then backward groups
     cells = _core.padded_cells(10, 20)
-    assert _core.path_record_bytes(10, 20, 65) == 2 * 4 * 4 * cells          # 32 + 32 steps
-    assert _core.path_record_bytes(10, 20, 64) == 2 * 4 * 4 * cells          # 31 + 32
-    assert _core.path_record_bytes(10, 20, 66) == 3 * 4 * 4 * cells          # 32 + 33
+    assert _core.path_record_bytes(10, 20, 65) == 2 * 16 * cells          # 32 + 32 steps
+    assert _core.path_record_bytes(10, 20, 64) == 2 * 16 * cells          # 31 + 32
+    assert _core.path_record_bytes(10, 20, 66) == 3 * 16 * cells          # 32 + 33
     assert _core.path_record_bytes(10, 20, 1) == 0
-    assert _core.path_record_bytes(10, 20, 2) == 1 * 4 * 4 * cells           # 0 + 1
-    assert _core.path_record_bytes(10, 20, 129) == 4 * 4 * 4 * cells
+    assert _core.path_record_bytes(10, 20, 2) == 1 * 16 * cells           # 0 + 1
+    assert _core.path_record_bytes(10, 20, 129) == 4 * 16 * cells
     # a uniform +x field, closed walls: every step of the forward half moves along x upwards
     tex = np.random.default_rng(1).random((6, 80))
     b = ke.Buffers(np.float64, 6, 80, _core.wall_codes(WALLS["closed"]), 9)
@@ -206,11 +210,17 @@ def test_record_size_and_layout():
     b.pad_texture(tex, 0)
     rec = b.path_record(9)
     b.run_pass_paths(0, 1, np.ones(9), "velocity", 1, rec)
-    planes = rec.reshape(2, 4, -1)                                            # (group, plane, cell)
+    entries = rec.reshape(2, -1, 4)                                           # (group, cell, plane)
     pitch = 82
     cell = pitch + 2 * pitch + 40                                             # pixel (2, 40): far from the walls
-    assert planes[0, 0, cell] == 0 and planes[0, 1, cell] == 0 and planes[0, 2, cell] == 0       # forward: +x
-    assert planes[1, 0, cell] == 0 and planes[1, 1, cell] == 0xF0000000 and planes[1, 2, cell] == 0   # backward: -x x 4
+    axis, sign, rare, extra = (int(x) for x in entries[0, cell])              # forward: +x, +x, +x, +x
+    assert (axis, sign, rare, extra) == (0, 0, 0, 0)
+    axis, sign, rare, extra = (int(x) for x in entries[1, cell])              # backward: -x four times
+    assert (axis, sign, rare, extra) == (0, 0xF0000000, 0, 0)
+    # pixel (2, 79) at the closed right wall: every forward step crosses the wall again (RARE from
+    # the second step on: the step that finds the walker on the wall cell)
+    axis, sign, rare, extra = (int(x) for x in entries[0, pitch + 2 * pitch + 79])
+    assert (axis, sign, rare, extra) == (0, 0, 0x70000000, 0)
 
 
 def test_options_surface():

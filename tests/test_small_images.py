@@ -73,11 +73,19 @@ def test_device_entry_writes_the_dense_result_from_the_last_pass():
                                threads=oracle.max_threads())
         out, n = launches(lambda: convolve_device(d[0], field=field, kernel=k, boundaries="periodic", iterations=its))
         assert_array_equal(out.cpu().numpy(), want)
-        assert n == 1 + its                                  # pad, passes
+        # pad, passes; a call that replays (iterations >= 2) records with the one-thread-per-pixel
+        # kernel, replays, and un-pads
+        assert n == (1 + its if its == 1 else 2 + its)
+        with rlic.options(paths="recompute"):
+            out1, n1 = launches(lambda: convolve_device(d[0], field=field, kernel=k, boundaries="periodic",
+                                                         iterations=its))
+        assert_array_equal(out1.cpu().numpy(), want)
+        assert n1 == 1 + its                                 # pad, passes: the last one writes the dense result
         _core.lib.rlic_b200_debug_small_image_kernel(0)
         try:
-            out2, n2 = launches(lambda: convolve_device(d[0], field=field, kernel=k, boundaries="periodic",
-                                                        iterations=its))
+            with rlic.options(paths="recompute"):
+                out2, n2 = launches(lambda: convolve_device(d[0], field=field, kernel=k, boundaries="periodic",
+                                                            iterations=its))
         finally:
             _core.lib.rlic_b200_debug_small_image_kernel(1)
         assert_array_equal(out2.cpu().numpy(), want)

@@ -17,8 +17,9 @@ step 120 lab_f32 tools/replay_lab 4096 65
 step 120 lab_c5 tools/replay_lab 4096 33 g1
 step 700 pytest_gpu python -m pytest tests -q -m gpu -rxXs
 step 240 bench_recompute env RLIC_B200_PATHS=recompute python bench.py --steps 20 --warmup 5 --no-cpu-baseline
+step 240 bench_unstaged env RLIC_B200_REPLAY_STAGING=0 python bench.py --steps 20 --warmup 5 --no-cpu-baseline
 step 300 configs python tools/bench_configs.py --configs c1,c2,c3,c4
-step 300 c5 python tools/bench_c5_batch.py --fields 512
+step 300 c5 python tools/bench_c5_batch.py --fields 512 --skip-pageable
 step 300 ncu_launches ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv \
     --log-file "$OUT/launches.csv" python bench.py --steps 2 --warmup 1 --no-cpu-baseline
 step 300 ncu_record ncu --set full --clock-control none --import-source on -k regex:lic_pass_kernel -s 2 -c 1 \

@@ -51,7 +51,7 @@ void run_type(const char *tname, int n, int L, const char *only)
     const int groups = rlic::path_groups_fwd(L) + rlic::path_groups_bwd(L);
     const size_t rec_words = (size_t)groups * rlic::kPlanesPerGroup * cells;
 
-    T *tex, *u, *v, *ptex, *ptex2, *ref, *ref2, *out; PackedField<T> *field; unsigned *rec;
+    T *tex, *u, *v, *ptex, *ptex2, *ref, *ref2, *out; PackedField<T> *field; uint4 *rec;
     CK(cudaMalloc(&tex, count * sizeof(T))); CK(cudaMalloc(&u, count * sizeof(T)));
     CK(cudaMalloc(&v, count * sizeof(T)));
     CK(cudaMalloc(&ptex, cells * sizeof(T))); CK(cudaMalloc(&ptex2, cells * sizeof(T)));
@@ -150,7 +150,8 @@ void run_type(const char *tname, int n, int L, const char *only)
         gc.tiles_per_field = gc.tiles_x * ((n + TH - 1) / TH); \
         float best; \
         CK(cudaMemset(out, 0, cells * sizeof(T))); \
-        TIME((k<<<gc.tiles_per_field, TW * TH>>>(ptex2, rec, out, gc, steps, L, (long long)cells, nullptr, 0)), best); \
+        const dim3 grid((unsigned)gc.tiles_x, (unsigned)((n + TH - 1) / TH), 1); \
+        TIME((k<<<grid, TW * TH>>>(ptex2, rec, out, gc, steps, L, (long long)cells, nullptr, 0)), best); \
         CK(cudaMemcpy(h_out.data(), out, cells * sizeof(T), cudaMemcpyDeviceToHost)); \
         bool same = memcmp(h_out.data(), h_ref2.data(), cells * sizeof(T)) == 0; \
         cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, k)); \
@@ -179,6 +180,42 @@ void run_type(const char *tname, int n, int L, const char *only)
     REPLAY("replay g2 32x8 b6", 2, 32, 8, 6);
     REPLAY("replay g0 16x16 b8 (loop)", 0, 16, 16, 8);
     REPLAY("replay g0 16x16 b6 (loop)", 0, 16, 16, 6);
+    // the texture window of each tile staged in shared memory (lic_replay_staged_kernel): a warp is
+    // one row of 32 pixels; TH rows per CTA, PAD extra words per window row (bank spread)
+#define STAGED(NAME, TH, PAD, MINB) do { \
+        if (only && !strstr(NAME, only)) break; \
+        if (rlic::path_groups_fwd(L) > 1 || rlic::path_groups_bwd(L) > 1) break; \
+        const int hh = L / 2; \
+        const size_t smem = (size_t)(32 + 2 * hh + PAD) * (TH + 2 * hh) * sizeof(T); \
+        if (smem > 200 * 1024) break; \
+        auto k = rlic::lic_replay_staged_kernel<T, ST, int, false, 32, TH, PAD, MINB>; \
+        CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        PassGeom gc = g; \
+        const dim3 grid((unsigned)((n + 31) / 32), (unsigned)((n + TH - 1) / TH), 1); \
+        float best; \
+        CK(cudaMemset(out, 0, cells * sizeof(T))); \
+        TIME((k<<<grid, 32 * TH, smem>>>(ptex2, rec, out, gc, steps, L, (long long)cells, nullptr, 0)), best); \
+        CK(cudaMemcpy(h_out.data(), out, cells * sizeof(T), cudaMemcpyDeviceToHost)); \
+        bool same = memcmp(h_out.data(), h_ref2.data(), cells * sizeof(T)) == 0; \
+        cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, k)); \
+        results.push_back({NAME, best, same, fa.numRegs}); \
+    } while (0)
+    STAGED("staged 32x32 pad0 b2", 32, 0, 2);
+    STAGED("staged 32x32 pad4 b2", 32, 4, 2);
+    STAGED("staged 32x32 pad8 b2", 32, 8, 2);
+    STAGED("staged 32x32 pad16 b2", 32, 16, 2);
+    STAGED("staged 32x32 pad1 b2", 32, 1, 2);
+    STAGED("staged 32x16 pad0 b4", 16, 0, 4);
+    STAGED("staged 32x16 pad4 b4", 16, 4, 4);
+    STAGED("staged 32x16 pad8 b4", 16, 8, 4);
+    STAGED("staged 32x16 pad16 b4", 16, 16, 4);
+    STAGED("staged 32x16 pad1 b4", 16, 1, 4);
+    STAGED("staged 32x16 pad8 b3", 16, 8, 3);
+    STAGED("staged 32x16 pad8 b2", 16, 8, 2);
+    STAGED("staged 32x8 pad8 b8", 8, 8, 8);
+    STAGED("staged 32x8 pad8 b6", 8, 8, 6);
+    STAGED("staged 32x8 pad0 b8", 8, 0, 8);
+    STAGED("staged 32x24 pad8 b2", 24, 8, 2);
     if (!only || strstr("ceiling", only)) {
         auto k = rlic::gather_ceiling_kernel<T, false, false>;
         float best;
