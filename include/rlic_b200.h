@@ -529,6 +529,7 @@ int rlic_b200_measure_gather_ceiling_f64(const double *d_padded_texture, const d
  *   peer_signal      after everything enqueued so far on `stream`: raise the 32-bit counter
  *                    `d_flag` (normally in a neighbour's memory) to `value`, with
  *                    system-scope fences around the store
+ *   peer_signal2 / peer_wait4   the same for two / four counters with one launch
  *   peer_wait        hold `stream` until the counter `d_flag` (in local memory) has reached
  *                    `value` (signed distance, so counters may wrap); after `timeout_ms`
  *                    the wait gives up and sets *d_timed_out (device memory, may be NULL)
@@ -601,6 +602,14 @@ int rlic_b200_peer_free(void *ptr);
 int rlic_b200_peer_signal(uint32_t *d_flag, uint32_t value, void *stream);
 int rlic_b200_peer_wait(const uint32_t *d_flag, uint32_t value, int64_t timeout_ms, int *d_timed_out,
                         void *stream);
+/* The same for several counters with one launch each (a replayed pass lasts a few hundred
+ * microseconds; the one-thread launches count): signal2 raises up to two counters to `value`,
+ * wait4 holds the stream until each of up to four counters has reached its own value.  Null
+ * flags are skipped (at least one must be given). */
+int rlic_b200_peer_signal2(uint32_t *d_flag_a, uint32_t *d_flag_b, uint32_t value, void *stream);
+int rlic_b200_peer_wait4(const uint32_t *d_flag0, uint32_t value0, const uint32_t *d_flag1, uint32_t value1,
+                         const uint32_t *d_flag2, uint32_t value2, const uint32_t *d_flag3, uint32_t value3,
+                         int64_t timeout_ms, int *d_timed_out, void *stream);
 
 /*
  * BATCH of independent fields on the host (BASELINE config 5): `nfields`

@@ -116,7 +116,9 @@ def _load() -> ctypes.CDLL:
     cdll.rlic_b200_peer_free.argtypes = [_vp]
     cdll.rlic_b200_peer_signal.argtypes = [_vp, ctypes.c_uint32, _vp]
     cdll.rlic_b200_peer_wait.argtypes = [_vp, ctypes.c_uint32, _i64, _vp, _vp]
-    for name in ("alloc", "open", "close", "free", "signal", "wait"):
+    cdll.rlic_b200_peer_signal2.argtypes = [_vp, _vp, ctypes.c_uint32, _vp]
+    cdll.rlic_b200_peer_wait4.argtypes = [_vp, ctypes.c_uint32] * 4 + [_i64, _vp, _vp]
+    for name in ("alloc", "open", "close", "free", "signal", "wait", "signal2", "wait4"):
         getattr(cdll, f"rlic_b200_peer_{name}").restype = _int
     cdll.rlic_b200_set_thread_options.argtypes = [_int, _int, _int]
     cdll.rlic_b200_set_thread_options.restype = _int

@@ -67,7 +67,7 @@ void prefault_for_write(void *ptr, size_t bytes)
 // cudaMemcpyAsync from pageable memory is staged by the driver through one
 // bounce buffer on the calling thread (~10-12 GB/s measured here).  Pinned
 // sources go straight to the copy engine.  For pageable sources we do the
-// staging ourselves: a few worker threads memcpy 4 MiB chunks into a small pool
+// staging ourselves: a few worker threads memcpy 1 MiB chunks into a small pool
 // of pinned buffers and enqueue each chunk's DMA as soon as it is filled, so
 // the memcpy of one chunk overlaps the DMA of the others.
 class Workers {
@@ -104,8 +104,10 @@ private:
         std::lock_guard<std::mutex> lk(mu_);
         if (!threads_.empty())
             return;
+        // the caller takes part too: up to eight threads copy (one thread moves ~10 GB/s, the host
+        // link takes ~55)
         unsigned hw = std::thread::hardware_concurrency();
-        unsigned count = std::min(3u, hw > 2 ? hw / 2 - 1 : 1u);
+        unsigned count = std::min(7u, hw > 2 ? hw / 2 - 1 : 1u);
         for (unsigned t = 0; t < count; ++t)
             threads_.emplace_back([this] { loop(); }).detach();
     }
@@ -147,8 +149,8 @@ Workers &workers()
 
 class PinnedPool {
 public:
-    static constexpr size_t kChunk = (size_t)4 << 20;
-    static constexpr int kSlots = 12;
+    static constexpr size_t kChunk = (size_t)1 << 20;   // small enough that one band of one array (4 MiB at
+    static constexpr int kSlots = 48;                    // 4096^2 / 16 bands) keeps several threads busy
     struct Slot {
         void *host = nullptr;
         cudaEvent_t drained = nullptr;   // recorded after the DMA that reads this slot

@@ -13,6 +13,7 @@
 #include <nvtx3/nvToolsExt.h>   // header-only: ranges show up in Nsight Systems / ncu --nvtx, cost nothing otherwise
 
 #include <atomic>
+#include <chrono>
 #include <climits>
 #include <cstdarg>
 #include <cstdio>
@@ -33,7 +34,7 @@ thread_local int tls_device = 0;
 std::atomic<int64_t> g_launches{0};
 std::atomic<int> g_force_wide{0};   // testing hook: use 64-bit element indices for any size
 std::atomic<int> g_small_images{1}; // testing hook: 0 keeps small passes on the one-thread-per-pixel kernel
-std::atomic<int> g_replay_staging{1}; // testing hook: 0 keeps replayed passes on the kernel that gathers through L1
+std::atomic<int> g_replay_staging{0}; // testing hook: 0 keeps replayed passes on the kernel that gathers through L1
 // The three choices a call can make (include/rlic_b200.h): which reference build to reproduce,
 // which formulation of the pass kernels, how the host path orders its launches.  Each has a
 // process-wide DEFAULT (the atomics: set once at start-up, e.g. from the environment) and a
@@ -643,6 +644,66 @@ struct CallPaths {
     }
 };
 
+// RLIC_B200_TRACE=1: the host entry point reports, on stderr, when (host clock, ms since entry) it
+// finished allocating, enqueueing the uploads and the passes, and returning, and when (device
+// clock, ms since the first upload began) the last upload, the last pass and the last download
+// ended.  A measurement aid (tools/e2e_probe.py); costs nothing when off.
+struct HostTrace {
+    bool on = false;
+    double t0 = 0;
+    std::vector<std::pair<const char *, double>> marks;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // begin, uploads, passes, downloads
+    static double now()
+    {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    }
+    HostTrace()
+    {
+        static const bool wanted = getenv("RLIC_B200_TRACE") && atoi(getenv("RLIC_B200_TRACE")) != 0;
+        on = wanted;
+        t0 = on ? now() : 0;
+    }
+    void mark(const char *what)
+    {
+        if (on)
+            marks.push_back({what, now() - t0});
+    }
+    void device(int which, cudaStream_t s)
+    {
+        if (!on)
+            return;
+        if (!ev[which])
+            cudaEventCreate(&ev[which]);
+        cudaEventRecord(ev[which], s);
+    }
+    ~HostTrace()
+    {
+        if (!on)
+            return;
+        mark("return");
+        std::string line = "rlic_b200 trace: host ms";
+        char buf[96];
+        for (auto &m : marks) {
+            snprintf(buf, sizeof buf, " | %s %.3f", m.first, m.second);
+            line += buf;
+        }
+        line += " || device ms since first upload";
+        const char *names[4] = {"", "uploads done", "passes done", "downloads done"};
+        for (int k = 1; k < 4; ++k)
+            if (ev[0] && ev[k]) {
+                float ms = 0;
+                if (cudaEventElapsedTime(&ms, ev[0], ev[k]) == cudaSuccess) {
+                    snprintf(buf, sizeof buf, " | %s %.3f", names[k], ms);
+                    line += buf;
+                }
+            }
+        fprintf(stderr, "%s\n", line.c_str());
+        for (cudaEvent_t e : ev)
+            if (e)
+                cudaEventDestroy(e);
+    }
+};
+
 // Host entry: upload -> passes -> download, pipelined over row bands.
 //   stream `io`  : uploads (band by band: u, v -> packed field; texture -> padded
 //                  buffer) and downloads (padded -> dense -> host)
@@ -655,6 +716,7 @@ int convolve_host(const T *tex, const T *u, const T *v, int64_t nfields, int64_t
                   int64_t iterations, T *out, int device, int *texture_has_negative = nullptr)
 {
     Range whole("rlic_b200 convolve (host)");
+    HostTrace trace;
     if (texture_has_negative)
         *texture_has_negative = 0;
     if (int rc = check_common(ny, nx, klen, uv_mode, w))
@@ -717,6 +779,8 @@ int convolve_host(const T *tex, const T *u, const T *v, int64_t nfields, int64_t
     CUDA_TRY(uploaded.make((size_t)nbands));
     CUDA_TRY(done.make((size_t)nbands));
 
+    trace.mark("allocated");
+    trace.device(0, io.s);
     T *const t_tex = static_cast<T *>(d_tex.p);
     T *const t_work = static_cast<T *>(d_work.p);
     T *const s_u = static_cast<T *>(d_su.p);
@@ -750,12 +814,12 @@ int convolve_host(const T *tex, const T *u, const T *v, int64_t nfields, int64_t
         const int64_t rb = band_begin(b), re = band_begin(b + 1);
         const size_t off = (size_t)rb * (size_t)nx * (size_t)nfields;
         const size_t n = (size_t)(re - rb) * (size_t)nx * (size_t)nfields;
-        const HostToDevice uv_jobs[2] = {{s_u + off, u + off, n * sizeof(T)},
-                                         {s_v + off, v + off, n * sizeof(T)}};
-        CUDA_TRY(upload(uv_jobs, 2, io.s));
+        // one sweep for the three arrays: pageable sources are staged by all the helper threads at once
+        const HostToDevice jobs[3] = {{s_u + off, u + off, n * sizeof(T)},
+                                      {s_v + off, v + off, n * sizeof(T)},
+                                      {s_t + off, tex + off, n * sizeof(T)}};
+        CUDA_TRY(upload(jobs, 3, io.s));
         CUDA_TRY(launch_pack<T>(s_u + off, s_v + off, t_field, g, rb, re, nfields, io.s));
-        const HostToDevice tex_job{s_t + off, tex + off, n * sizeof(T)};
-        CUDA_TRY(upload(&tex_job, 1, io.s));
         CUDA_TRY(launch_pad<T>(s_t + off, t_tex, g, rb, re, nfields, flag, io.s));
         CUDA_TRY(cudaEventRecord(uploaded.ev[(size_t)b], io.s));
         return RLIC_B200_OK;
@@ -798,9 +862,13 @@ int convolve_host(const T *tex, const T *u, const T *v, int64_t nfields, int64_t
                     return rc;
             }
         }
+        trace.mark("uploads enqueued");
+        trace.device(1, io.s);
         for (; next < order.size(); ++next)
             if (int rc = band_pass(order[next]))
                 return rc;
+        trace.mark("passes enqueued");
+        trace.device(2, run.s);
         T *const result = bufs[(iterations - 1) & 1];
         if (is_pageable(out))
             prefault_for_write(out, bytes);
@@ -816,11 +884,14 @@ int convolve_host(const T *tex, const T *u, const T *v, int64_t nfields, int64_t
             CUDA_TRY(launch_unpad<T>(result, s_t + off, g, rb, re, 1, back.s));
             CUDA_TRY(cudaMemcpyAsync(out + off, s_t + off, n * sizeof(T), cudaMemcpyDeviceToHost, back.s));
         }
+        trace.mark("downloads enqueued");
+        trace.device(3, back.s);
         CUDA_TRY(cudaStreamSynchronize(back.s));
         if (texture_has_negative)
             CUDA_TRY(cudaMemcpyAsync(texture_has_negative, flag, sizeof(int), cudaMemcpyDeviceToHost, io.s));
         CUDA_TRY(cudaStreamSynchronize(io.s));
         CUDA_TRY(cudaStreamSynchronize(run.s));
+        trace.mark("synchronised");
         return RLIC_B200_OK;
     }
 
@@ -1802,6 +1873,32 @@ int rlic_b200_peer_signal(uint32_t *d_flag, uint32_t value, void *stream)
     if (!d_flag)
         return fail(RLIC_B200_EINVAL, "null flag");
     rlic::peer_signal_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(d_flag, value);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    return RLIC_B200_OK;
+}
+
+int rlic_b200_peer_signal2(uint32_t *d_flag_a, uint32_t *d_flag_b, uint32_t value, void *stream)
+{
+    tls_error.clear();
+    if (!d_flag_a && !d_flag_b)
+        return fail(RLIC_B200_EINVAL, "null flags");
+    rlic::peer_signal2_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(d_flag_a, d_flag_b, value);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    return RLIC_B200_OK;
+}
+
+int rlic_b200_peer_wait4(const uint32_t *d_flag0, uint32_t value0, const uint32_t *d_flag1, uint32_t value1,
+                         const uint32_t *d_flag2, uint32_t value2, const uint32_t *d_flag3, uint32_t value3,
+                         int64_t timeout_ms, int *d_timed_out, void *stream)
+{
+    tls_error.clear();
+    if ((!d_flag0 && !d_flag1 && !d_flag2 && !d_flag3) || timeout_ms <= 0)
+        return fail(RLIC_B200_EINVAL, "bad argument to peer_wait4");
+    const rlic::PeerWaits w{{d_flag0, d_flag1, d_flag2, d_flag3}, {value0, value1, value2, value3}};
+    rlic::peer_wait4_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(
+        w, (long long)timeout_ms * 1000000ll, d_timed_out);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     CUDA_TRY(cudaGetLastError());
     return RLIC_B200_OK;

@@ -225,6 +225,28 @@ class CudaSlabOps:
         _core.check(_core.lib.rlic_b200_peer_wait(flags.data_ptr() + 4 * index, value & 0xFFFFFFFF, timeout_ms,
                                                   flags.data_ptr() + 4 * timed_out_index, self._stream()))
 
+    def signal_many(self, targets, value):
+        """``signal`` for up to two counters -- ``targets``: ``(flags, index)`` pairs -- in one launch."""
+        from rlic_b200 import _core
+
+        ptrs = [f.data_ptr() + 4 * i for f, i in targets]
+        for k in range(0, len(ptrs), 2):
+            pair = ptrs[k:k + 2] + [None] * (2 - len(ptrs[k:k + 2]))
+            _core.check(_core.lib.rlic_b200_peer_signal2(pair[0], pair[1], value & 0xFFFFFFFF, self._stream()))
+
+    def wait_many(self, flags, waits, timeout_ms, timed_out_index):
+        """``wait`` for up to four counters of the local ``flags`` -- ``waits``: ``(index, value)``
+        pairs -- in one launch."""
+        from rlic_b200 import _core
+
+        for k in range(0, len(waits), 4):
+            args = []
+            for index, value in waits[k:k + 4]:
+                args += [flags.data_ptr() + 4 * index, value & 0xFFFFFFFF]
+            args += [None, 0] * (4 - len(waits[k:k + 4]))
+            _core.check(_core.lib.rlic_b200_peer_wait4(*args, timeout_ms, flags.data_ptr() + 4 * timed_out_index,
+                                                       self._stream()))
+
 
 class _DevicePointer:
     """A raw device allocation as a ``__cuda_array_interface__`` producer (zero-copy into torch)."""
@@ -607,18 +629,40 @@ class ShardedConvolver:
         up = px.remote.get(p.up) if p.up is not None else None
         down = px.remote.get(p.down) if p.down is not None else None
 
-        def wait(which_up, which_down, value):
+        def wait(which_up, which_down, value, and_up=None, and_down=None, and_value=0):
+            """hold the stream until my counters `which_up` / `which_down` have reached `value` (and,
+            when given, `and_up` / `and_down` have reached `and_value`): one launch where the ops can"""
+            waits = []
             if up is not None:
-                self.ops.wait(flags, which_up, value, limit, _TIMED_OUT)
+                waits.append((which_up, value))
+                if and_up is not None:
+                    waits.append((and_up, and_value))
             if down is not None:
-                self.ops.wait(flags, which_down, value, limit, _TIMED_OUT)
+                waits.append((which_down, value))
+                if and_down is not None:
+                    waits.append((and_down, and_value))
+            if not waits:
+                return
+            if hasattr(self.ops, "wait_many"):
+                self.ops.wait_many(flags, waits, limit, _TIMED_OUT)
+            else:
+                for index, v in waits:
+                    self.ops.wait(flags, index, v, limit, _TIMED_OUT)
 
         def signal(which_at_up, which_at_down, value):
             # my upper neighbour sees me below it, my lower neighbour sees me above it
+            targets = []
             if up is not None:
-                self.ops.signal(up[1], which_at_up, value)
+                targets.append((up[1], which_at_up))
             if down is not None:
-                self.ops.signal(down[1], which_at_down, value)
+                targets.append((down[1], which_at_down))
+            if not targets:
+                return
+            if hasattr(self.ops, "signal_many"):
+                self.ops.signal_many(targets, value)
+            else:
+                for f, index in targets:
+                    self.ops.signal(f, index, value)
 
         return up, down, wait, signal
 
@@ -663,15 +707,15 @@ class ShardedConvolver:
         self._mark("push initial halos")
         for k in range(1, n + 1):
             src, dst = bufs[(k - 1) % 2], bufs[k % 2]
-            wait(_HALO_FROM_UP, _HALO_FROM_DOWN, c + k)
+            if k == n or k < 2:
+                wait(_HALO_FROM_UP, _HALO_FROM_DOWN, c + k)
+            else:   # the halos of this pass's input, and room for this pass's strips: one launch
+                wait(_HALO_FROM_UP, _HALO_FROM_DOWN, c + k, _FREE_FROM_UP, _FREE_FROM_DOWN, c + k - 1)
             self._mark("wait halo")
             if k == n:
                 rows_runner(k, src, dst, 0, rows)
                 self._mark("last pass")
                 break
-            if k >= 2:
-                wait(_FREE_FROM_UP, _FREE_FROM_DOWN, c + k - 1)
-                self._mark("wait free")
             # the edge strips, stored into the neighbours' halos as they are computed
             if up is not None:
                 self._pass_rows(src, dst, 0, h, k, up[0][k % 2], px.delta_up)

@@ -202,6 +202,15 @@ class HostFlags:
                 return
             time.sleep(0.0005)
 
+    # the one-launch forms (rlic_b200_peer_signal2 / _peer_wait4)
+    def signal_many(self, targets, value):
+        for flags, index in targets:
+            self.signal(flags, index, value)
+
+    def wait_many(self, flags, waits, timeout_ms, timed_out_index):
+        for index, value in waits:
+            self.wait(flags, index, value, timeout_ms, timed_out_index)
+
 
 def _peer_methods(cls):
     """Adds the peer-exchange half of the ops interface to a CPU ops class."""

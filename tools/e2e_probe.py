@@ -26,3 +26,12 @@ bench("public API (pageable in)", lambda: rlic_b200.convolve(tp,up,vp,kernel=k,i
 bench("pinned in/out, 1 iteration", lambda: call(tex,u,v,out_pinned,1))
 bench("np.empty + touch 64MB", lambda: np.empty_like(tex).fill(0))
 bench("validation texture<0 any", lambda: np.any(tex<0))
+
+# RLIC_B200_TRACE=1 python tools/e2e_probe.py: where a call's time goes (lic_api.cu: HostTrace)
+import os
+if os.environ.get("RLIC_B200_TRACE"):
+    print("--- traced calls: pinned in / pinned out, then pageable in / pinned out", file=sys.stderr)
+    for _ in range(3):
+        call(tex, u, v, out_pinned)
+    for _ in range(3):
+        call(tp, up, vp, out_pinned)
