@@ -108,6 +108,8 @@ def _load() -> ctypes.CDLL:
     cdll.rlic_b200_get_schedule.restype = _int
     cdll.rlic_b200_debug_wavefront_order.argtypes = [_i64, _i64, ctypes.POINTER(ctypes.c_int32), _i64]
     cdll.rlic_b200_debug_wavefront_order.restype = _i64
+    cdll.rlic_b200_debug_band_plan.argtypes = [_i64, _i64, _i64, _i64, ctypes.POINTER(_i64), _i64]
+    cdll.rlic_b200_debug_band_plan.restype = _i64
     # peer memory and flags of the fused halo exchange (rlic_b200/sharded.py)
     handle = ctypes.POINTER(ctypes.c_ubyte)
     cdll.rlic_b200_peer_alloc.argtypes = [_i64, ctypes.POINTER(_vp), handle]

@@ -157,7 +157,7 @@ struct DeviceBuf {
 // that on every exit path -- early error returns included -- no kernel is still using a buffer
 // when cudaFreeAsync hands it back on another stream.
 struct StreamDrain {
-    const Stream *streams[3];
+    const Stream *streams[4];
     ~StreamDrain()
     {
         for (const Stream *st : streams)
@@ -609,6 +609,45 @@ std::vector<BandPass> wavefront_order(int64_t nbands, int64_t iterations)
     return order;
 }
 
+// Row bands of a host call over one image: edges[b] .. edges[b + 1] are the rows of band b.
+// The call is a pipeline -- uploads, passes, downloads -- and, since the passes became cheaper
+// than the uploads (recorded paths), what it waits for at the end is the work that cannot start
+// before the last band has arrived: the last pass of a band runs `iterations` bands behind the
+// uploads (wavefront_order).  So the bands are large where the copy engine should stream and
+// SMALL at the end, where their size is the tail: counted from the bottom, iterations + 1 bands
+// of the smallest size, then doubling up to an eighth of the image.  A band is at least two
+// kernel half-widths tall (a pass reaches one band up and down, and overwrites what the
+// previous pass of the neighbouring bands read) and a multiple of the tile height, the top band
+// takes the remainder.
+std::vector<int64_t> band_plan(int64_t ny, int64_t nx, int64_t reach, int64_t iterations)
+{
+    const int64_t tile = rlic::kTileH;
+    auto round_up = [&](int64_t x) { return (x + tile - 1) / tile * tile; };
+    int64_t smallest = round_up(std::max<int64_t>(2 * reach, 64));
+    if (nx > 0)
+        smallest = std::max(smallest, round_up(((int64_t)1 << 18) / nx));      // >= 256 Kpix per band
+    std::vector<int64_t> edges{0, ny};
+    if (ny * nx < ((int64_t)1 << 21) || ny < 3 * smallest)
+        return edges;
+    const int64_t largest = std::max(smallest, round_up(ny / 8));
+    std::vector<int64_t> sizes;                  // from the bottom of the image up
+    int64_t left = ny, size = smallest;
+    int64_t tail = std::min<int64_t>(std::max<int64_t>(iterations, 1) + 1, 6);
+    while (left >= size + smallest && sizes.size() < 40) {
+        sizes.push_back(size);
+        left -= size;
+        if (tail > 1)
+            --tail;
+        else
+            size = std::min(largest, size * 2);
+    }
+    sizes.push_back(left);                       // the top band: whatever remains (>= smallest)
+    edges.assign(1, 0);
+    for (size_t k = sizes.size(); k-- > 0;)
+        edges.push_back(edges.back() + sizes[k]);
+    return edges;
+}
+
 // The record is planes * 4 bytes per cell (32 bytes for a 65-tap kernel): small next to 180 GB,
 // but a caller may have filled the device.  Large records are checked against the free memory;
 // when one does not fit the call simply walks every pass.
@@ -736,31 +775,31 @@ int convolve_host(const T *tex, const T *u, const T *v, int64_t nfields, int64_t
 
     // Row bands (single images only; a batch chunk is pipelined by its caller).
     const int64_t reach = klen / 2;
-    int64_t nbands = 1;
-    if (nfields == 1) {
-        // >= 1 Mpix per band, at most 16: with replayed passes the compute is no longer than the
-        // uploads, and what an upload-bound call waits for at the end is the skew of the wavefront
-        // (the last pass of band b runs `iterations` bands behind the uploads), i.e. band size
-        nbands = std::min<int64_t>(16, (int64_t)(count >> 20));
-        nbands = std::min<int64_t>(nbands, ny / std::max<int64_t>(2 * reach, 64));
-        nbands = std::max<int64_t>(nbands, 1);
-    }
-    int64_t band_rows = (ny + nbands - 1) / nbands;
-    band_rows = (band_rows + rlic::kTileH - 1) / rlic::kTileH * rlic::kTileH;
-    nbands = (ny + band_rows - 1) / band_rows;
+    const std::vector<int64_t> edges =
+        nfields == 1 ? band_plan(ny, nx, reach, iterations) : std::vector<int64_t>{0, ny};
+    const int64_t nbands = (int64_t)edges.size() - 1;
     const bool periodic_y = w.y_left == RLIC_B200_PERIODIC || w.y_right == RLIC_B200_PERIODIC;
-    auto band_begin = [&](int64_t b) { return std::min(ny, b * band_rows); };
+    auto band_begin = [&](int64_t b) { return edges[(size_t)b]; };
+    auto band_of_row = [&](int64_t row) {
+        return (int64_t)(std::upper_bound(edges.begin(), edges.end(), row) - edges.begin()) - 1;
+    };
+    // the last band a pass-1 walker of band b can reach: it must be on the device first
+    auto upload_needed = [&](int64_t b) {
+        return periodic_y ? nbands - 1 : band_of_row(std::min(ny - 1, band_begin(b + 1) - 1 + reach));
+    };
 
     CUDA_TRY(use_device(device));
-    Stream io, run, back;   // `back` is created by the wavefront schedule only
+    Stream io, prep, run, back;   // `back` is created by the wavefront schedule only
     CUDA_TRY(cudaStreamCreateWithFlags(&io.s, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&run.s, cudaStreamNonBlocking));
+    if (nbands > 1)   // the layout conversions of a band run beside the next band's copies
+        CUDA_TRY(cudaStreamCreateWithFlags(&prep.s, cudaStreamNonBlocking));
     // Two padded texture buffers (the uploaded texture's doubles as the second
     // work buffer), the packed field, and dense staging for the three uploads
     // (the texture's staging is reused for the download).
     DeviceBuf d_tex, d_work, d_field, d_su, d_sv, d_st, d_flag;
     CallPaths paths;
-    StreamDrain drain{{&io, &run, &back}};
+    StreamDrain drain{{&io, &run, &back, &prep}};
     CUDA_TRY(d_tex.alloc(padded_bytes, io.s));
     CUDA_TRY(d_work.alloc(padded_bytes, io.s));
     CUDA_TRY(d_field.alloc(4 * padded_bytes, io.s));
@@ -775,9 +814,11 @@ int convolve_host(const T *tex, const T *u, const T *v, int64_t nfields, int64_t
     CUDA_TRY(taps.prepare(kernel, klen, io.s));
     // (allocated on `io`, first used on `run` behind an `uploaded` event recorded later on `io`)
     CUDA_TRY(paths.prepare(iterations, g.field_stride * nfields, klen, io.s));
-    Events uploaded, done;
+    Events uploaded, done, copied;
     CUDA_TRY(uploaded.make((size_t)nbands));
     CUDA_TRY(done.make((size_t)nbands));
+    if (prep.s)
+        CUDA_TRY(copied.make((size_t)nbands));
 
     trace.mark("allocated");
     trace.device(0, io.s);
@@ -795,9 +836,7 @@ int convolve_host(const T *tex, const T *u, const T *v, int64_t nfields, int64_t
 
     auto first_pass_band = [&](int64_t b) -> int {
         // rows this band's walkers can reach must be on the device
-        const int64_t last_row = std::min(ny - 1, band_begin(b + 1) - 1 + reach);
-        const int64_t need = periodic_y ? nbands - 1 : std::min(nbands - 1, last_row / band_rows);
-        CUDA_TRY(cudaStreamWaitEvent(run.s, uploaded.ev[(size_t)need], 0));
+        CUDA_TRY(cudaStreamWaitEvent(run.s, uploaded.ev[(size_t)upload_needed(b)], 0));
         int rc = launch_pass<T>(t_tex, t_field, bufs[0], g, nfields, band_begin(b),
                                 band_begin(b + 1) - band_begin(b), uv_mode, taps, run.s, PeerTarget<T>{},
                                 nullptr, nullptr, paths.use(1));
@@ -819,9 +858,16 @@ int convolve_host(const T *tex, const T *u, const T *v, int64_t nfields, int64_t
                                       {s_v + off, v + off, n * sizeof(T)},
                                       {s_t + off, tex + off, n * sizeof(T)}};
         CUDA_TRY(upload(jobs, 3, io.s));
-        CUDA_TRY(launch_pack<T>(s_u + off, s_v + off, t_field, g, rb, re, nfields, io.s));
-        CUDA_TRY(launch_pad<T>(s_t + off, t_tex, g, rb, re, nfields, flag, io.s));
-        CUDA_TRY(cudaEventRecord(uploaded.ev[(size_t)b], io.s));
+        // the conversions: on their own stream when there are bands, so that the copy engine goes
+        // straight on with the next band (the first allocation-ordered use of the buffers is `io`'s)
+        cudaStream_t conv = prep.s ? prep.s : io.s;
+        if (prep.s) {
+            CUDA_TRY(cudaEventRecord(copied.ev[(size_t)b], io.s));
+            CUDA_TRY(cudaStreamWaitEvent(prep.s, copied.ev[(size_t)b], 0));
+        }
+        CUDA_TRY(launch_pack<T>(s_u + off, s_v + off, t_field, g, rb, re, nfields, conv));
+        CUDA_TRY(launch_pad<T>(s_t + off, t_tex, g, rb, re, nfields, flag, conv));
+        CUDA_TRY(cudaEventRecord(uploaded.ev[(size_t)b], conv));
         return RLIC_B200_OK;
     };
 
@@ -832,10 +878,6 @@ int convolve_host(const T *tex, const T *u, const T *v, int64_t nfields, int64_t
     if (effective_schedule() == RLIC_B200_SCHEDULE_WAVEFRONT && !periodic_y &&
         iterations >= 2 && nbands >= 2) {
         const std::vector<BandPass> order = wavefront_order(nbands, iterations);
-        auto upload_needed = [&](int64_t b) {   // last band a pass-1 walker of band b can reach
-            const int64_t last_row = std::min(ny - 1, band_begin(b + 1) - 1 + reach);
-            return std::min(nbands - 1, last_row / band_rows);
-        };
         auto band_pass = [&](const BandPass &bp) -> int {
             const int64_t b = bp.band;
             // pass p reads what pass p-1 wrote (pass 1: the uploaded texture) and writes bufs[(p-1) % 2]
@@ -887,6 +929,8 @@ int convolve_host(const T *tex, const T *u, const T *v, int64_t nfields, int64_t
         trace.mark("downloads enqueued");
         trace.device(3, back.s);
         CUDA_TRY(cudaStreamSynchronize(back.s));
+        if (prep.s)
+            CUDA_TRY(cudaStreamSynchronize(prep.s));   // the sign flag is raised by the padding kernels
         if (texture_has_negative)
             CUDA_TRY(cudaMemcpyAsync(texture_has_negative, flag, sizeof(int), cudaMemcpyDeviceToHost, io.s));
         CUDA_TRY(cudaStreamSynchronize(io.s));
@@ -902,8 +946,7 @@ int convolve_host(const T *tex, const T *u, const T *v, int64_t nfields, int64_t
             return rc;
         // launch every band of pass 1 whose reach is now covered
         while (next_band < nbands && !periodic_y) {
-            const int64_t last_row = std::min(ny - 1, band_begin(next_band + 1) - 1 + reach);
-            if (std::min(nbands - 1, last_row / band_rows) > b)
+            if (upload_needed(next_band) > b)
                 break;
             if (int rc = first_pass_band(next_band))
                 return rc;
@@ -949,6 +992,8 @@ int convolve_host(const T *tex, const T *u, const T *v, int64_t nfields, int64_t
         CUDA_TRY(launch_unpad<T>(result, s_t + off, g, rb, re, nfields, io.s));
         CUDA_TRY(cudaMemcpyAsync(out + off, s_t + off, n * sizeof(T), cudaMemcpyDeviceToHost, io.s));
     }
+    if (prep.s)
+        CUDA_TRY(cudaStreamSynchronize(prep.s));       // the sign flag is raised by the padding kernels
     if (texture_has_negative)
         CUDA_TRY(cudaMemcpyAsync(texture_has_negative, flag, sizeof(int), cudaMemcpyDeviceToHost, io.s));
     CUDA_TRY(cudaStreamSynchronize(io.s));
@@ -1313,7 +1358,7 @@ int equalize_host(const T *image, int64_t ny, int64_t nx, int64_t nbins, T *out,
     Stream st;
     CUDA_TRY(cudaStreamCreateWithFlags(&st.s, cudaStreamNonBlocking));
     DeviceBuf d_in, d_out;
-    StreamDrain drain{{&st, nullptr, nullptr}};
+    StreamDrain drain{{&st, nullptr, nullptr, nullptr}};
     CUDA_TRY(d_in.alloc(bytes, st.s));
     CUDA_TRY(d_out.alloc(bytes, st.s));
     const HostToDevice job{d_in.p, image, bytes};
@@ -1465,6 +1510,17 @@ void rlic_b200_get_effective_options(int *arithmetic, int *schedule, int *walk)
     if (arithmetic) *arithmetic = effective_arithmetic();
     if (schedule) *schedule = effective_schedule();
     if (walk) *walk = effective_walk();
+}
+
+int64_t rlic_b200_debug_band_plan(int64_t ny, int64_t nx, int64_t klen, int64_t iterations, int64_t *edges,
+                                  int64_t capacity)
+{
+    if (ny <= 0 || nx <= 0 || klen <= 0)
+        return 0;
+    const std::vector<int64_t> plan = band_plan(ny, nx, klen / 2, iterations);
+    for (size_t k = 0; k < plan.size() && (int64_t)k < capacity && edges; ++k)
+        edges[k] = plan[k];
+    return (int64_t)plan.size();
 }
 
 int64_t rlic_b200_debug_wavefront_order(int64_t nbands, int64_t iterations, int32_t *pass_band,

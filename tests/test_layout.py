@@ -111,3 +111,38 @@ def test_bad_requests_are_refused():
     assert f(8, 8, 0, 8, 0, 0, 0, 0, 0, 0, 10**9, out) == _core.EINVAL       # cell outside the buffer
     assert f(8, 8, 4, 8, 0, 0, 0, 0, 0, 0, 0, out) == _core.ESHARD           # rows beyond the image
     assert f(8, 8, 0, 8, 0, 0, 0, 7, 0, 0, 0, out) == _core.EINVAL           # unknown boundary code
+
+
+def test_band_plan_of_the_host_path():
+    """The row bands of a host call (rlic_b200_debug_band_plan): they tile the image, every band
+    is at least two kernel half-widths tall (a pass reaches one band up and down) and at least
+    64 rows, inner edges sit on tile rows counted from the bottom, the bands at the end -- whose
+    size is what an upload-bound call waits for after its last upload -- are the smallest, and
+    small or narrow images are not cut at all."""
+    import ctypes
+
+    import numpy as np
+
+    from rlic_b200 import _core
+
+    def plan(ny, nx, klen, iterations):
+        e = np.zeros(64, dtype=np.int64)
+        n = _core.lib.rlic_b200_debug_band_plan(ny, nx, klen, iterations, e.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), 64)
+        assert 2 <= n <= 64
+        return e[:n]
+
+    for ny, nx, klen, its in ((4096, 4096, 65, 5), (4096, 4096, 65, 1), (16384, 16384, 65, 20), (2048, 2048, 129, 1),
+                              (1000, 3000, 65, 3), (4100, 4096, 65, 5), (3000, 5000, 257, 4), (46341, 46341, 65, 2)):
+        e = plan(ny, nx, klen, its)
+        sizes = np.diff(e)
+        assert e[0] == 0 and e[-1] == ny and (sizes > 0).all()
+        if len(sizes) > 1:
+            assert sizes.min() >= max(2 * (klen // 2), 64)
+            assert ((ny - e[1:-1]) % 16 == 0).all()
+            assert sizes[-1] == sizes.min()
+            tail = min(its + 1, 6)
+            assert (sizes[-tail:] == sizes[-1]).all() or len(sizes) <= tail
+            assert (np.diff(sizes[1:]) <= 0).all()          # never growing towards the end (the top band takes the remainder)
+    assert len(plan(256, 256, 65, 2)) == 2                   # too small to pipeline
+    assert len(plan(100, 100000, 9, 3)) == 2                 # too few rows
+    assert _core.lib.rlic_b200_debug_band_plan(0, 10, 5, 1, None, 0) == 0
