@@ -89,8 +89,40 @@ int fail(int code, const char *fmt, ...)
 // Stream and stream-ordered allocations that clean up on every exit path.
 struct Stream {
     cudaStream_t s = nullptr;
-    ~Stream() { if (s) cudaStreamDestroy(s); }
+    bool borrowed = false;   // from the calling thread's cache (host_stream): not destroyed here
+    ~Stream() { if (s && !borrowed) cudaStreamDestroy(s); }
 };
+
+// The streams of the host entry points, kept per calling thread and device: creating and
+// destroying four streams costs a small image's call several tens of microseconds each way, and
+// a thread runs one host call at a time (concurrent calls come from different threads and so
+// have their own).  `role` 0..3: copies, conversions, passes, downloads.
+cudaError_t host_stream(int device, int role, Stream &out)
+{
+    struct Cache {
+        std::vector<cudaStream_t> streams;   // [device * 4 + role]
+        ~Cache()
+        {
+            for (cudaStream_t st : streams)
+                if (st)
+                    cudaStreamDestroy(st);   // (fails harmlessly once the runtime is gone)
+        }
+    };
+    thread_local Cache cache;
+    const size_t slot = (size_t)device * 4 + (size_t)role;
+    if (slot >= cache.streams.size())
+        cache.streams.resize(slot + 1, nullptr);
+    if (!cache.streams[slot]) {
+        cudaError_t e = cudaStreamCreateWithFlags(&cache.streams[slot], cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            cache.streams[slot] = nullptr;
+            return e;
+        }
+    }
+    out.s = cache.streams[slot];
+    out.borrowed = true;
+    return cudaSuccess;
+}
 // The library's scratch comes from PRIVATE stream-ordered pools, one per device, never from the
 // device's default pool: the device entry points run next to a host framework's own allocator
 // (torch), and a process-wide release threshold on the shared default pool would keep our
@@ -590,19 +622,25 @@ struct Events {
 // Order in which the (pass, band) launches of the wavefront schedule are issued on the one
 // compute stream.  Pass p of band b reads pass p-1 of bands b-1, b, b+1 (a band is at
 // least two kernel half-widths tall) and overwrites what pass p-1 of those same bands
-// read (two ping-pong buffers), so it may run once those three are done: launches are
-// grouped in slots b + 2 (p - 1), a slot's members are independent of each other, and
-// within a slot the pass-1 launch -- the only one that waits for an upload -- goes last.
+// read (two ping-pong buffers), so it may run once those three are done.  On an in-order
+// stream the tightest order that guarantees it is the diagonal one: slots b + (p - 1), and within
+// a slot ascending passes -- (1, s), (2, s - 1), (3, s - 2), ...: each launch finds the last of
+// its three predecessors, pass p-1 of band b+1, right in front of it.  The last pass of band b
+// therefore runs `iterations - 1` bands behind pass 1, which in turn needs the upload of band
+// b + 1: once the last band has arrived, about iterations^2 / 2 band-passes remain, all on the
+// small bands at the end of the image (band_plan).  (Round 1 used slots b + 2 (p - 1), twice
+// the skew, for the sake of independent launches within a slot -- which a single stream cannot
+// exploit.)
 struct BandPass { int pass, band; };   // pass is 1-based
 
 std::vector<BandPass> wavefront_order(int64_t nbands, int64_t iterations)
 {
     std::vector<BandPass> order;
     order.reserve((size_t)(nbands * iterations));
-    const int64_t slots = (nbands - 1) + 2 * (iterations - 1) + 1;
+    const int64_t slots = (nbands - 1) + (iterations - 1) + 1;
     for (int64_t slot = 0; slot < slots; ++slot)
-        for (int64_t p = iterations; p >= 1; --p) {
-            const int64_t b = slot - 2 * (p - 1);
+        for (int64_t p = 1; p <= iterations; ++p) {
+            const int64_t b = slot - (p - 1);
             if (b >= 0 && b < nbands)
                 order.push_back({(int)p, (int)b});
         }
@@ -790,10 +828,10 @@ int convolve_host(const T *tex, const T *u, const T *v, int64_t nfields, int64_t
 
     CUDA_TRY(use_device(device));
     Stream io, prep, run, back;   // `back` is created by the wavefront schedule only
-    CUDA_TRY(cudaStreamCreateWithFlags(&io.s, cudaStreamNonBlocking));
-    CUDA_TRY(cudaStreamCreateWithFlags(&run.s, cudaStreamNonBlocking));
+    CUDA_TRY(host_stream(device, 0, io));
+    CUDA_TRY(host_stream(device, 2, run));
     if (nbands > 1)   // the layout conversions of a band run beside the next band's copies
-        CUDA_TRY(cudaStreamCreateWithFlags(&prep.s, cudaStreamNonBlocking));
+        CUDA_TRY(host_stream(device, 1, prep));
     // Two padded texture buffers (the uploaded texture's doubles as the second
     // work buffer), the packed field, and dense staging for the three uploads
     // (the texture's staging is reused for the download).
@@ -915,7 +953,7 @@ int convolve_host(const T *tex, const T *u, const T *v, int64_t nfields, int64_t
         if (is_pageable(out))
             prefault_for_write(out, bytes);
         // results leave on their own stream: the bus is full duplex, and `io` may still be uploading
-        CUDA_TRY(cudaStreamCreateWithFlags(&back.s, cudaStreamNonBlocking));
+        CUDA_TRY(host_stream(device, 3, back));
         for (int64_t b = 0; b < nbands; ++b) {
             const int64_t rb = band_begin(b), re = band_begin(b + 1);
             const size_t off = (size_t)rb * (size_t)nx;

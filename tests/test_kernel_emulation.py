@@ -614,11 +614,16 @@ def test_wavefront_order_respects_every_dependency(nbands, iterations):
             for nb in (b - 1, b, b + 1):
                 if 0 <= nb < nbands:
                     assert at[(p - 1, nb)] < k
-    # within a group of mutually independent launches the one that waits for an upload is last
+    # the diagonal order: slots b + (p - 1) in turn, ascending passes within a slot, so that the
+    # last pass of a band runs only `iterations - 1` bands behind the first
+    slots = [b + (p - 1) for p, b in order]
+    assert slots == sorted(slots)
     for k in range(1, len(order)):
         (p0, b0), (p1, b1) = order[k - 1], order[k]
-        if b0 + 2 * (p0 - 1) == b1 + 2 * (p1 - 1):
-            assert p0 > p1
+        if b0 + (p0 - 1) == b1 + (p1 - 1):
+            assert p0 < p1
+    for b in range(nbands):
+        assert at[(iterations, b)] - at[(1, b)] <= iterations * (iterations - 1) + iterations
 
 
 @pytest.mark.parametrize("dtype,mode,walls,iterations", [
