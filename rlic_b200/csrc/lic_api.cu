@@ -653,10 +653,12 @@ std::vector<BandPass> wavefront_order(int64_t nbands, int64_t iterations)
 // before the last band has arrived: the last pass of a band runs `iterations` bands behind the
 // uploads (wavefront_order).  So the bands are large where the copy engine should stream and
 // SMALL at the end, where their size is the tail: counted from the bottom, iterations + 1 bands
-// of the smallest size, then doubling up to an eighth of the image.  A band is at least two
-// kernel half-widths tall (a pass reaches one band up and down, and overwrites what the
-// previous pass of the neighbouring bands read) and a multiple of the tile height, the top band
-// takes the remainder.
+// of the smallest size, then doubling up to a thirty-second of the image.  (Not larger: the last
+// pass of a band runs `iterations` BANDS behind the uploads, so with bands of an eighth of the
+// image half of the passes were still to run when the last upload ended -- measured, 2.1 ms of
+// a 6.1 ms call.)  A band is at least two kernel half-widths tall (a pass reaches one band up
+// and down, and overwrites what the previous pass of the neighbouring bands read) and a
+// multiple of the tile height, the top band takes the remainder.
 std::vector<int64_t> band_plan(int64_t ny, int64_t nx, int64_t reach, int64_t iterations)
 {
     const int64_t tile = rlic::kTileH;
@@ -667,11 +669,11 @@ std::vector<int64_t> band_plan(int64_t ny, int64_t nx, int64_t reach, int64_t it
     std::vector<int64_t> edges{0, ny};
     if (ny * nx < ((int64_t)1 << 21) || ny < 3 * smallest)
         return edges;
-    const int64_t largest = std::max(smallest, round_up(ny / 8));
+    const int64_t largest = std::max(smallest, round_up(ny / 32));
     std::vector<int64_t> sizes;                  // from the bottom of the image up
     int64_t left = ny, size = smallest;
     int64_t tail = std::min<int64_t>(std::max<int64_t>(iterations, 1) + 1, 6);
-    while (left >= size + smallest && sizes.size() < 40) {
+    while (left >= size + smallest && sizes.size() < 47) {
         sizes.push_back(size);
         left -= size;
         if (tail > 1)
