@@ -156,9 +156,8 @@ int64_t rlic_b200_debug_wavefront_order(int64_t nbands, int64_t iterations, int3
 
 /* Testing hook (host code only): the row bands the host entry points cut a single ny x nx image
  * into for a `klen`-tap kernel and `iterations` passes -- edges[b] .. edges[b + 1] are the rows
- * of band b; bands of about a thirty-second of the image, smaller ones at the end (what an upload-bound call waits for after
- * its last upload is proportional to the size of its last bands).  Returns the number of edges
- * (bands + 1; at most `capacity` are written). */
+ * of band b: about sixteen bands, each at least two kernel half-widths (and 64 rows, 256 Kpix)
+ * tall.  Returns the number of edges (bands + 1; at most `capacity` are written). */
 int64_t rlic_b200_debug_band_plan(int64_t ny, int64_t nx, int64_t klen, int64_t iterations, int64_t *edges,
                                   int64_t capacity);
 

@@ -648,38 +648,35 @@ std::vector<BandPass> wavefront_order(int64_t nbands, int64_t iterations)
 }
 
 // Row bands of a host call over one image: edges[b] .. edges[b + 1] are the rows of band b.
-// The call is a pipeline -- uploads, passes, downloads -- and, since the passes became cheaper
-// than the uploads (recorded paths), what it waits for at the end is the work that cannot start
-// before the last band has arrived: the last pass of a band runs `iterations` bands behind the
-// uploads (wavefront_order).  So the bands are large where the copy engine should stream and
-// SMALL at the end, where their size is the tail: counted from the bottom, iterations + 1 bands
-// of the smallest size, then doubling up to a thirty-second of the image.  (Not larger: the last
-// pass of a band runs `iterations` BANDS behind the uploads, so with bands of an eighth of the
-// image half of the passes were still to run when the last upload ended -- measured, 2.1 ms of
-// a 6.1 ms call.)  A band is at least two kernel half-widths tall (a pass reaches one band up
-// and down, and overwrites what the previous pass of the neighbouring bands read) and a
-// multiple of the tile height, the top band takes the remainder.
+// The call is a pipeline -- uploads, passes, downloads -- and since the passes became cheaper
+// than the uploads (recorded paths) its length is the uploads plus whatever cannot start before
+// the last band has arrived: the last pass of a band runs `iterations` bands behind the uploads
+// (wavefront_order), so small bands would make a short tail -- but a pass over a small band is
+// bound by the latency of one wave of walkers, not by throughput (measured with ncu, 4096
+// columns: replaying 64 rows takes 19 us, 256 rows 39 us, 512 rows 66 us; walking them 40 /
+// 116 / 218 us), so small bands make the passes themselves slow.  Sixteen bands is where the
+// two meet for the headline image (a model fed with those launch times and the copy rate puts
+// 16 x 256 rows at 5.4 ms, 8 x 512 at 5.9, 35 bands of 64-128 rows at 6.2; the last was also
+// measured: 6.6).  A band is at least two kernel half-widths tall (a pass reaches one band up
+// and down, and overwrites what the previous pass of the neighbouring bands read), at least 64
+// rows and 256 Kpix, and a multiple of the tile height; the top band takes the remainder.
 std::vector<int64_t> band_plan(int64_t ny, int64_t nx, int64_t reach, int64_t iterations)
 {
+    (void)iterations;
     const int64_t tile = rlic::kTileH;
     auto round_up = [&](int64_t x) { return (x + tile - 1) / tile * tile; };
     int64_t smallest = round_up(std::max<int64_t>(2 * reach, 64));
     if (nx > 0)
         smallest = std::max(smallest, round_up(((int64_t)1 << 18) / nx));      // >= 256 Kpix per band
     std::vector<int64_t> edges{0, ny};
-    if (ny * nx < ((int64_t)1 << 21) || ny < 3 * smallest)
+    if (ny * nx < ((int64_t)1 << 21) || ny < 2 * smallest)
         return edges;
-    const int64_t largest = std::max(smallest, round_up(ny / 32));
+    const int64_t size = std::max(smallest, round_up(ny / 16));
     std::vector<int64_t> sizes;                  // from the bottom of the image up
-    int64_t left = ny, size = smallest;
-    int64_t tail = std::min<int64_t>(std::max<int64_t>(iterations, 1) + 1, 6);
+    int64_t left = ny;
     while (left >= size + smallest && sizes.size() < 47) {
         sizes.push_back(size);
         left -= size;
-        if (tail > 1)
-            --tail;
-        else
-            size = std::min(largest, size * 2);
     }
     sizes.push_back(left);                       // the top band: whatever remains (>= smallest)
     edges.assign(1, 0);
