@@ -497,8 +497,9 @@ def run_ours(args) -> dict:
     if world == 1 and replay:
         groups = 2 * ((TAPS // 2 + 31) // 32)
         replay_bytes = (TAPS - 1) * 4 + 4 + 4 + 3 * 4 * groups      # gathers + centre + store + three planes per group
-        roofline["kernel"] = ("lic_pass_kernel<float,...,REC> (pass 1: the walk, recording the paths; "
-                              f"{first_ms:.3f} of the {pass_ms / args.steps:.3f} ms the step's passes take)")
+        roofline["kernel"] = ("lic_pass_kernel<float,...,REC> (pass 1: the walk, recording the paths: the longest "
+                              f"launch of the step, {first_ms:.3f} of the {pass_ms / args.steps:.3f} ms its passes take; "
+                              f"the four replay launches take {(ITERATIONS - 1) * later_ms:.3f} ms: roofline.replay)")
         roofline["algorithmic_bytes_per_launch"] = gather_bytes_per_pixel() * pixels_local
         roofline["step_share"] = {"walk_record_ms": first_ms, "replay_ms_each": later_ms,
                                   "replay_launches": ITERATIONS - 1, "passes_ms": pass_ms / args.steps}
@@ -511,6 +512,8 @@ def run_ours(args) -> dict:
                     f"x 4 = {replay_bytes} (the replay reads no field); nominal like the fraction above: the gathers "
                     "are served by L1/L2",
             "vs_walking_pass": first_ms / later_ms,
+            # the same pass in section 8(d)'s accounting of the REFERENCE algorithm (u, v and texture per step)
+            "reference_pass_equivalent_GBps": gather_bytes_per_pixel() * pixels_local / (later_ms * 1e-3) / 1e9,
         }
         try:
             tr = json.loads(tf.read_text())
@@ -725,6 +728,17 @@ def run_ours(args) -> dict:
             line["parity"].update(path_divergence(rlic_b200, h_u, h_v, 0, N_SIDE))
         except Exception as exc:  # noqa: BLE001
             line["parity"] = {"error": f"{type(exc).__name__}: {exc}"}
+        try:
+            # ... and the timed step's own result -- all ITERATIONS passes, i.e. the recorded paths
+            # replayed four times -- on three bands (the top wall, the middle, the bottom wall)
+            bands = [slab_parity_band(0, 1, result[first:first + 64].cpu().numpy(), first)
+                     for first in (0, N_SIDE // 2 - 32, N_SIDE - 64)]
+            line["parity"]["all_passes"] = {
+                "against": f"CPU oracle, all {ITERATIONS} passes (which walks every pass), on three 64-row bands of "
+                           "the device-resident step's result",
+                "bit_equal": all(b["bit_equal"] for b in bands), "bands": bands}
+        except Exception as exc:  # noqa: BLE001
+            line.setdefault("parity", {})["all_passes"] = {"error": f"{type(exc).__name__}: {exc}"}
         cb["single_thread"] = cpu_single_thread(texture, u, v, kernel)
     elif rank == 0:
         line["cpu_baseline"] = None
