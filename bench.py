@@ -107,6 +107,7 @@ class ClockSampler:
         if not inside:   # region shorter than one sampling period: fall back to the whole loaded run
             inside = [l for _, l in self.lines]
             where = "warm-up + timed region"
+        per_gpu: dict[str, list[float]] = {}
         for line in inside:
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 8:
@@ -115,6 +116,7 @@ class ClockSampler:
                 sm.append(float(parts[1]))
                 smax.append(float(parts[2]))
                 power.append(float(parts[3]))
+                per_gpu.setdefault(parts[0], []).append(float(parts[1]))
             except ValueError:
                 continue
             for name, flag in zip(names, parts[4:8]):
@@ -122,9 +124,12 @@ class ClockSampler:
                     reasons.add(name)
         if self.index is None or not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax),
-                "power_w_max": max(power), "reasons": sorted(reasons), "samples": len(sm),
-                "sampled_during": where}
+        out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax),
+               "power_w_max": max(power), "reasons": sorted(reasons), "samples": len(sm),
+               "sampled_during": where}
+        if len(per_gpu) > 1:    # one figure per GPU of the job: a slow one must not hide in the median
+            out["sm_mhz_per_gpu"] = {k: statistics.median(v) for k, v in sorted(per_gpu.items())}
+        return out
 
 
 def make_slab(rank: int, world: int):
@@ -458,8 +463,14 @@ def run_ours(args) -> dict:
     pass_ms = sum(a.elapsed_time(b) for a, b, _ in ev)   # the 5 pass launches of every step
     first_ms = sum(a.elapsed_time(m) for a, _, m in ev) / args.steps      # world == 1: the first pass alone
     later_ms = sum(m.elapsed_time(b) for _, b, m in ev) / args.steps / max(ITERATIONS - 1, 1)   # each of the others
+    per_rank_ms = None
     if dist is not None:
         t = torch.tensor([total_ms, pass_ms], device=dev, dtype=torch.float64)
+        # every rank's own device time per step travels with the line: `value` is their maximum,
+        # and a spread between ranks (or between runs) can be attributed to a GPU
+        mine = [torch.zeros(1, device=dev, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(mine, t[:1] / args.steps)
+        per_rank_ms = [float(x.item()) for x in mine]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, pass_ms = t.tolist()
         n_l = torch.tensor([launches], device=dev, dtype=torch.int64)
@@ -717,6 +728,8 @@ def run_ours(args) -> dict:
         "pixel_steps_per_s": value * 1e6 * (TAPS - 1),
         "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
     }
+    if per_rank_ms is not None:
+        line["ms_per_step_per_rank"] = per_rank_ms
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cb = cpu_baseline(None)
         pass1 = cb.pop("_pass1")

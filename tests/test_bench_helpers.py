@@ -85,3 +85,32 @@ def test_slab_parity_band_checks_slab_edges_against_a_whole_image_run(monkeypatc
     wrong[3, 7] = np.nextafter(wrong[3, 7], np.float32(9))
     got = bench.slab_parity_band(1, world, wrong, 0)
     assert not got["bit_equal"] and got["mismatches"] == 1
+
+
+def test_clock_sampler_summary_keeps_the_timed_region_and_every_gpu_of_the_job():
+    """One nvidia-smi poller watches all GPUs of a job: the summary is the median over the samples
+    that arrived inside the timed region, throttle reasons are collected, and with several GPUs
+    each one's own median is listed (a slow GPU must not hide in the job's median)."""
+    s = bench.ClockSampler("0,1")
+    s.t0, s.t1 = 10.0, 11.0
+    ok = "Not Active, Not Active, Not Active, Not Active"
+    s.lines = [
+        (9.0, f"0, 1000, 1965, 150.0, {ok}"),                       # warm-up: ignored
+        (10.1, f"0, 1965, 1965, 300.5, {ok}"),
+        (10.1, f"1, 1500, 1965, 280.0, Not Active, Not Active, Not Active, Active"),
+        (10.6, f"0, 1965, 1965, 301.0, {ok}"),
+        (10.6, f"1, 1510, 1965, 281.0, {ok}"),
+        (10.7, "garbage"),
+        (12.0, f"0, 500, 1965, 90.0, {ok}"),                        # after the region: ignored
+    ]
+    got = s.summary()
+    assert got["samples"] == 4 and got["sampled_during"] == "timed region"
+    assert got["sm_max_mhz"] == 1965.0 and got["power_w_max"] == 301.0
+    assert got["reasons"] == ["sw_power_cap"]
+    assert got["sm_mhz_per_gpu"] == {"0": 1965.0, "1": 1505.0}
+    json.dumps(got)
+    one = bench.ClockSampler("0")
+    one.t0, one.t1 = 10.0, 11.0
+    one.lines = [(10.2, f"0, 1965, 1965, 300.0, {ok}")]
+    assert "sm_mhz_per_gpu" not in one.summary() and one.summary()["sm_mhz"] == 1965.0
+    assert bench.ClockSampler(None).summary()["samples"] == 0
