@@ -17,9 +17,11 @@ buffers need), and the interiors are computed while those copies are in flight. 
 per-pixel arithmetic is the single-GPU kernel's in global row numbers, so the result is
 bit-identical to an unsharded run.
 
-Written after round 1's GPU time was spent: verified on the CPU through the emulated
-kernels (``tests/test_multi_device.py``), not yet run on GPUs.  The compute steps are
-injectable (``ops``) for that purpose; there is no CPU compute path in this package.
+Verified on the CPU through the emulated kernels and on B200s against ``convolve``
+(``tests/test_multi_device.py``; a box with fewer GPUs than slabs lists a device several
+times); a convenience, not benchmarked -- every pass walks (no recorded paths), and end to end
+it is bound by one process's uploads.  The compute steps are injectable (``ops``) for the CPU
+tests; there is no CPU compute path in this package.
 """
 
 from __future__ import annotations

@@ -18,9 +18,9 @@ with its two wall cells is the contiguous cell range
 The per-pixel arithmetic is the single-GPU kernel's, in global row numbers, so
 the gathered result is bit-identical to an unsharded run.
 
-``exchange="peer"`` (opt-in; written after round 1's GPU time was spent, so the NCCL
-exchange stays the default until it has run on hardware) fuses the per-iteration
-texture exchange into the passes over the edge strips: the pass kernel stores every
+``exchange="peer"`` (what ``bench.py --gpus N`` and ``tools/bench_c4_scaling.py`` use; measured
+on 2, 4 and 8 B200s: DESIGN.md section 7) fuses the per-iteration texture exchange into the
+passes over the edge strips: the pass kernel stores every
 row it computes there into the neighbour's halo as well, through that neighbour's
 buffer mapped into this process (CUDA IPC; the stores travel over NVLink while the
 strip is still being computed), and two pairs of counters per neighbour -- raised by

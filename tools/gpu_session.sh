@@ -7,7 +7,7 @@
 #   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/gpu_session.sh'
 #
 # Steps (each independent; a failure is logged and the script goes on):
-#   1  the -m gpu suite (includes the first_gpu_run tests: XPASS = good)
+#   1  the -m gpu suite
 #   2  smoke() of __graft_entry__
 #   3  bench.py as the driver runs it, then with the grouped walk, the wavefront schedule and
 #      the fma-only arithmetic (the JSON line's e2e.walk / e2e.schedule / e2e.arithmetic say
