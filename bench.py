@@ -396,7 +396,7 @@ def run_ours(args) -> dict:
         record = (torch.empty(_core.path_record_bytes(N_SIDE, N_SIDE, TAPS) // 4, dtype=torch.int32, device=dev)
                   if replay else None)
 
-        def step(events=None):
+        def step(events=None, replay=replay):
             st = int(torch.cuda.current_stream().cuda_stream)
             _core.check(lib.rlic_b200_slab_pack_field_f32(d_u.data_ptr(), d_v.data_ptr(), *slab, *closed,
                                                           field.data_ptr(), st))
@@ -461,6 +461,34 @@ def run_ours(args) -> dict:
         launches = _core.launch_count() - launches0
     total_ms = t_begin.elapsed_time(t_end)
     pass_ms = sum(a.elapsed_time(b) for a, b, _ in ev)   # the 5 pass launches of every step
+    every_pass_walks = None
+    if world == 1 and replay:
+        # The same step with every pass WALKING its streamlines, as the reference does in every
+        # iteration (RLIC_B200_PATHS=recompute), timed the same way right after the timed region:
+        # the line then says how much of `value` is the recorded paths and how much the walk kernel.
+        try:
+            expected = result.clone()
+            for _ in range(3):
+                step(replay=False)
+            w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            w0.record()
+            for _ in range(args.steps):
+                walked = step(replay=False)
+            w1.record()
+            w1.synchronize()
+            walk_ms = w0.elapsed_time(w1) / args.steps
+            every_pass_walks = {
+                "value": pixels_local * ITERATIONS / (walk_ms * 1e-3) / 1e6, "unit": METRIC, "ms_per_step": walk_ms,
+                "steps": args.steps, "result_bit_equal_to_the_timed_step": bool(torch.equal(walked, expected)),
+                "note": "the same step with the record/replay switched off (five launches of the walking "
+                        "lic_pass_kernel), device-resident, CUDA events; not the headline, for comparison",
+            }
+        except Exception as exc:  # noqa: BLE001 -- a reporting extra
+            every_pass_walks = {"error": f"{type(exc).__name__}: {exc}"}
+        else:
+            result.copy_(expected)       # `result` is the timed step's own output for everything below
+            del expected
     first_ms = sum(a.elapsed_time(m) for a, _, m in ev) / args.steps      # world == 1: the first pass alone
     later_ms = sum(m.elapsed_time(b) for _, b, m in ev) / args.steps / max(ITERATIONS - 1, 1)   # each of the others
     per_rank_ms = None
@@ -730,6 +758,8 @@ def run_ours(args) -> dict:
     }
     if per_rank_ms is not None:
         line["ms_per_step_per_rank"] = per_rank_ms
+    if every_pass_walks is not None:
+        line["every_pass_walks"] = every_pass_walks
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cb = cpu_baseline(None)
         pass1 = cb.pop("_pass1")
