@@ -836,6 +836,7 @@ int convolve_host(const T *tex, const T *u, const T *v, int64_t nfields, int64_t
     // (the texture's staging is reused for the download).
     DeviceBuf d_tex, d_work, d_field, d_su, d_sv, d_st, d_flag;
     CallPaths paths;
+    TapSet<T> taps;                // (owns a device copy of kernels beyond the parameter block)
     StreamDrain drain{{&io, &run, &back, &prep}};
     CUDA_TRY(d_tex.alloc(padded_bytes, io.s));
     CUDA_TRY(d_work.alloc(padded_bytes, io.s));
@@ -847,7 +848,6 @@ int convolve_host(const T *tex, const T *u, const T *v, int64_t nfields, int64_t
         CUDA_TRY(d_flag.alloc(sizeof(int), io.s));
         CUDA_TRY(cudaMemsetAsync(d_flag.p, 0, sizeof(int), io.s));
     }
-    TapSet<T> taps;
     CUDA_TRY(taps.prepare(kernel, klen, io.s));
     // (allocated on `io`, first used on `run` behind an `uploaded` event recorded later on `io`)
     CUDA_TRY(paths.prepare(iterations, g.field_stride * nfields, klen, io.s));

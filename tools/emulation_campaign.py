@@ -5,6 +5,7 @@ limits 2^-40 / 2^40 and their neighbours, denormals, the largest finite values, 
 arithmetic builds and both index widths.  Bitwise comparison, NaN payloads included.
 
     python tools/emulation_campaign.py <first seed> <seconds> [walk]
+    python tools/emulation_campaign.py <first seed> <seconds> replay    (recorded paths: record + replay kernels)
 
 `walk` (default 0) selects the formulation of the pass kernels: 0 per-step, 1 the grouped walk
 as the library dispatches it (rlic::Tune), "mix" picks per case among the per-step walk, the
@@ -48,6 +49,12 @@ while time.time()-t0<budget:
         pick=int(rng.integers(4))
         if pick==1: how=dict(walk=1)
         elif pick>=2: how=dict(walk=[1,9][int(rng.integers(2))],flavor=int(rng.integers(4)),admit=int(rng.integers(4)))
+    elif walk_arg=="replay":
+        # recorded paths: pass 1 records, the others replay (what the library does for iterations >= 2);
+        # kernels of up to 140 taps (one to three groups of 32 steps per half), either replay kernel
+        its=int(rng.integers(2,5)); klen=int(rng.integers(1,141))
+        k=(rng.random(klen)-0.3).astype(dtype)
+        how=dict(paths=[True,"staged"][int(rng.integers(2))])
     elif walk_arg!="0": how=dict(walk=int(walk_arg))
     if how: branchless=True                      # the grouped walk exists for the default arithmetic
     if "flavor" in how: wide=False; klen=min(klen,60)   # explicit formulations: 32-bit indices only
