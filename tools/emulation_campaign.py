@@ -14,6 +14,8 @@ tuned grouped walk and explicit (flavor, walk) pairs of the grouped walk.
 Round 1: seeds 100000..233822 (133 823 cases, 300 s on 8 cores): 0 mismatches.
 Round 1, `mix` (grouped-walk formulations included): seeds 300000..464805 (164 806 cases, 600 s), 500000..534981
 (34 982, after the alignment-compare change) and 600000..1408645 (808 646 cases, 1800 s): 0 mismatches.
+Round 2, `replay` (recorded paths: the recording walk + either replay kernel, 2-4 iterations, kernels of 1-140 taps):
+seeds 2000000..2227474 (227 475 cases, 900 s): 0 mismatches.
 """
 import sys, time
 from pathlib import Path
