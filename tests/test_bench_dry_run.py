@@ -221,3 +221,24 @@ def test_single_gpu_arm_with_every_pass_walking(cpu_stand_ins, monkeypatch):
     assert "every_pass_walks" not in line and "replay" not in line["roofline"]
     assert line["cpu_baseline"] is None and "parity" not in line
     assert line["e2e"]["paths"] == "recompute"
+
+
+def test_reference_arm_line(monkeypatch):
+    """--impl reference: whole 5-pass steps of the CPU path on the host cores, the contract's keys
+    plus `impl`, and an `e2e` that repeats the line's own value with no copies."""
+    monkeypatch.setattr(bench, "N_SIDE", SIDE)
+    monkeypatch.delenv("RANK", raising=False)
+    args = argparse.Namespace(gpus=1, steps=3, warmup=1, impl="reference", no_cpu_baseline=False)
+    line = json.loads(json.dumps(bench.run_reference(args)))
+    assert line["impl"] == "reference" and line["metric"] == line["unit"] == "Mpix/s" and line["n_gpus"] == 1
+    assert line["steps"] == 3 and line["warmup"] == 1 and line["higher_is_better"] is True and line["gpu_launches"] == 0
+    assert line["config"] == json.loads(json.dumps(bench.workload_config(1)))          # the GPU arm's config
+    assert line["e2e"] == {"value": line["value"], "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] == oracle.max_threads() and cb["value"] == line["value"]
+    assert "whole convolve calls" in cb["sample"] and cb["steps_timed"] == 3
+    assert abs(line["ms_per_step"] * 1e-3 * line["value"] * 1e6 - bench.ITERATIONS * SIDE * SIDE) < 1
+    assert line["single_thread"]["value"] > 0
+    # the other ranks of a torchrun launch do nothing
+    monkeypatch.setenv("RANK", "1")
+    assert bench.run_reference(args) == {}
