@@ -242,3 +242,105 @@ def test_reference_arm_line(monkeypatch):
     # the other ranks of a torchrun launch do nothing
     monkeypatch.setenv("RANK", "1")
     assert bench.run_reference(args) == {}
+
+
+# ---------------------------------------------------------------------------------------------
+# The multi-GPU arm (bench.py --gpus N under torchrun), two ranks over gloo: the sharded driver
+# is the real one, with the kernel source compiled for the CPU as its compute steps and named
+# shared memory for the peer mappings (the stand-ins tests/test_sharded_gloo.py uses).
+def _multi_rank_worker(rank, world, port, exchange, queue):
+    import os
+    import traceback
+
+    try:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), LOCAL_RANK=str(rank),
+                          WORLD_SIZE=str(world), RLIC_B200_EXCHANGE=exchange)
+        import torch.distributed as dist
+
+        import rlic_b200.sharded as sharded
+        import test_sharded_gloo as stand_ins
+
+        bench.N_SIDE = 256                                    # slabs of four kernel half-widths and more
+        cpu = torch.device("cpu")
+        torch.device = lambda *a, **k: cpu
+        torch.Tensor.pin_memory = lambda self: self
+        cuda = torch.cuda
+        cuda.is_available = lambda: True
+        cuda.set_device = lambda d: None
+        cuda.current_device = lambda: 0
+        cuda.synchronize = lambda *a: None
+        cuda.Event, cuda.Stream = _Event, _Stream
+        cuda.current_stream = lambda *a: _Stream()
+        cuda.stream = lambda s: contextlib.nullcontext()
+        cuda.get_device_properties = lambda d: types.SimpleNamespace(multi_processor_count=148)
+        bench.ClockSampler.summary = lambda self: {"sm_mhz": 1965.0, "sm_max_mhz": 1965.0, "reasons": [], "samples": 1}
+
+        real_init = dist.init_process_group
+        dist.init_process_group = lambda backend, **kw: real_init("gloo", rank=rank, world_size=world)
+
+        class Lib:
+            def __getattr__(self, name, real=_core.lib):
+                return getattr(real, name)
+
+            def rlic_b200_set_device(self, device):
+                return 0
+
+        _core.lib = Lib()
+
+        class Convolver(sharded.ShardedConvolver):
+            def __init__(self, *a, **kw):
+                ops = stand_ins._make_ops("emulated kernels, grouped walk")
+                ops.poison_halos = kw.get("exchange") != "peer"
+                super().__init__(*a, ops=ops,
+                                 peers=stand_ins.SharedMemoryPeers() if kw.get("exchange") == "peer" else None, **kw)
+
+        sharded.ShardedConvolver = Convolver
+        sharded.pinned_empty = lambda shape, dtype: np.empty(shape, dtype=dtype)
+
+        args = argparse.Namespace(gpus=world, steps=2, warmup=1, impl="ours", no_cpu_baseline=True)
+        line = bench.run_ours(args)
+        if rank == 0:
+            queue.put(("ok", json.dumps(line)))
+        else:
+            assert line == {}
+    except Exception:
+        queue.put(("error", f"rank {rank}:\n{traceback.format_exc()}"))
+        raise
+
+
+@pytest.mark.parametrize("exchange", ["peer", "nccl"])
+def test_multi_gpu_arm_builds_its_line_over_gloo(exchange):
+    import socket
+
+    import torch.multiprocessing as mp
+
+    world = 2
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    queue = ctx.Queue()
+    procs = [ctx.Process(target=_multi_rank_worker, args=(r, world, port, exchange, queue)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    try:
+        status, payload = queue.get(timeout=300)
+    finally:
+        for pr in procs:
+            pr.join(timeout=120)
+            if pr.is_alive():
+                pr.terminate()
+    assert status == "ok", payload
+    line = json.loads(payload)
+    assert line["n_gpus"] == 2 and line["scaling"] == "weak" and line["steps"] == 2 and line["value"] > 0
+    assert line["config"]["image"] == [512, 256] and "row slabs over 2 GPUs" in line["config"]["workload"]
+    assert len(line["ms_per_step_per_rank"]) == 2 and max(line["ms_per_step_per_rank"]) <= line["ms_per_step"] * 1.0001
+    assert line["e2e"]["exchange"] == exchange and line["e2e"]["value"] > 0 and "host_link" in line["e2e"]
+    assert line["e2e"]["h2d_bytes_per_step"] == 2 * (3 * 4 * 256 * 256 + 4 * bench.TAPS)
+    assert line["cpu_baseline"] is None and "every_pass_walks" not in line
+    # every rank's first and last 64 rows of the five-pass result, against the oracle
+    parity = line["parity"]
+    assert parity["bit_equal"] is True and len(parity["per_rank"]) == 2
+    assert [b["rows"] for pair in parity["per_rank"] for b in pair] == [[0, 64], [192, 256], [256, 320], [448, 512]]
+    assert all(b["bit_equal"] and b["mismatches"] == 0 for pair in parity["per_rank"] for b in pair)
+    assert "error" not in line["roofline"].get("issue", {})
