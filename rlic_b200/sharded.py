@@ -37,7 +37,7 @@ CUDA IPC entry points of the C ABI.  There is no CPU compute path in this packag
 
 from __future__ import annotations
 
-__all__ = ["SlabPlan", "ShardedConvolver", "CudaSlabOps", "CudaPeerMemory", "pinned_empty"]
+__all__ = ["SlabPlan", "ShardedConvolver", "CudaSlabOps", "CudaPeerMemory", "PeerMemoryUnavailable", "pinned_empty"]
 
 import ctypes
 from dataclasses import dataclass
@@ -297,6 +297,14 @@ def pinned_empty(shape, dtype) -> np.ndarray:
     return t.numpy()
 
 
+class PeerMemoryUnavailable(RuntimeError):
+    """``exchange="peer"`` cannot be set up: some rank could not allocate its shareable buffers or
+    map a neighbour's (no peer access between the GPUs, CUDA IPC not permitted in this
+    container, ...).  Raised on EVERY rank of the group -- the ranks agree on the outcome before
+    anyone proceeds, and whatever was allocated or mapped has been released -- so a caller can
+    catch it and build its convolver with ``exchange="nccl"`` instead, consistently."""
+
+
 # counters in a rank's flag block, raised by its neighbours (int32 each)
 _HALO_FROM_UP, _HALO_FROM_DOWN, _FREE_FROM_UP, _FREE_FROM_DOWN, _TIMED_OUT, _NFLAGS = 0, 1, 2, 3, 4, 8
 
@@ -310,23 +318,51 @@ class _PeerExchange:
         self.plan, self.peers = plan, peers
         itemsize = torch.empty((), dtype=dtype).element_size()
         self._own = []                                   # (ptr, handle) of this rank's allocations
-        for nbytes in (plan.cells * itemsize, plan.cells * itemsize, 4 * _NFLAGS, 4 * plan.cells * itemsize):
-            self._own.append(peers.alloc(nbytes))
-        self.bufs = [peers.view(self._own[i][0], plan.cells, dtype, device) for i in (0, 1)]
-        self.flags = peers.view(self._own[2][0], _NFLAGS, torch.int32, device)
-        self.field = peers.view(self._own[3][0], 4 * plan.cells, dtype, device)   # 4 scalars per cell
-        handles = [None] * plan.world
-        dist.all_gather_object(handles, [h for _, h in self._own], group=group)
         self._opened = {}                                # rank -> [ptr, ...]
         self.remote = {}                                 # rank -> (bufs, flags, that rank's plan, field)
-        for rank in {plan.up, plan.down} - {None}:
-            ptrs = [peers.open(h) for h in handles[rank]]
-            self._opened[rank] = ptrs
-            theirs = SlabPlan(ny=plan.ny, nx=plan.nx, world=plan.world, rank=rank, reach=plan.reach,
-                              periodic_y=plan.periodic_y)
-            self.remote[rank] = ([peers.view(ptrs[i], theirs.cells, dtype, device) for i in (0, 1)],
-                                 peers.view(ptrs[2], _NFLAGS, torch.int32, device), theirs,
-                                 peers.view(ptrs[3], 4 * theirs.cells, dtype, device))
+        self.bufs, self.flags, self.field = [], None, None
+
+        def agree(error, payload=None):
+            """Every rank learns whether every rank got this far (a failure must not leave the
+            others waiting in a collective); returns the payloads, or releases everything and
+            raises PeerMemoryUnavailable on all ranks alike."""
+            said = [None] * plan.world
+            dist.all_gather_object(said, (error, payload), group=group)
+            errors = [e for e, _ in said if e]
+            if errors:
+                try:
+                    self._release(group)
+                except Exception as exc:  # noqa: BLE001 -- every rank must leave with the same exception
+                    errors.append(f"(while releasing on rank {plan.rank}: {type(exc).__name__}: {exc})")
+                raise PeerMemoryUnavailable("; ".join(errors))
+            return [x for _, x in said]
+
+        def describe(exc):
+            return f"rank {plan.rank}: {type(exc).__name__}: {exc}"
+
+        error = None
+        try:
+            for nbytes in (plan.cells * itemsize, plan.cells * itemsize, 4 * _NFLAGS, 4 * plan.cells * itemsize):
+                self._own.append(peers.alloc(nbytes))
+            self.bufs = [peers.view(self._own[i][0], plan.cells, dtype, device) for i in (0, 1)]
+            self.flags = peers.view(self._own[2][0], _NFLAGS, torch.int32, device)
+            self.field = peers.view(self._own[3][0], 4 * plan.cells, dtype, device)   # 4 scalars per cell
+        except Exception as exc:  # noqa: BLE001 -- reported to every rank, then raised on all of them
+            error = describe(exc)
+        handles = agree(error, [h for _, h in self._own])
+        try:
+            for rank in {plan.up, plan.down} - {None}:
+                ptrs = self._opened.setdefault(rank, [])
+                for h in handles[rank]:
+                    ptrs.append(peers.open(h))
+                theirs = SlabPlan(ny=plan.ny, nx=plan.nx, world=plan.world, rank=rank, reach=plan.reach,
+                                  periodic_y=plan.periodic_y)
+                self.remote[rank] = ([peers.view(ptrs[i], theirs.cells, dtype, device) for i in (0, 1)],
+                                     peers.view(ptrs[2], _NFLAGS, torch.int32, device), theirs,
+                                     peers.view(ptrs[3], 4 * theirs.cells, dtype, device))
+        except Exception as exc:  # noqa: BLE001
+            error = describe(exc)
+        agree(error)
         # where my edge strips land: my top rows in the upper neighbour's high halo, my
         # bottom rows in the lower neighbour's low halo (buffer rows, theirs minus mine)
         self.delta_up = self.delta_down = 0
@@ -340,16 +376,30 @@ class _PeerExchange:
 
     def close(self, group) -> None:
         dist.barrier(group=group)                        # nobody still writes into a neighbour
+        self._release(group)
+
+    def _release(self, group) -> None:
+        """Unmap the neighbours' buffers, then -- once every rank has -- free this rank's own
+        (collective; also the way out of a set-up that failed on some rank)."""
+        failed = None
         self.remote = {}
         for ptrs in self._opened.values():
             for ptr in ptrs:
-                self.peers.close(ptr)
+                try:
+                    self.peers.close(ptr)
+                except Exception as exc:  # noqa: BLE001 -- the barrier below must still be reached
+                    failed = failed or exc
         self._opened = {}
         dist.barrier(group=group)                        # every mapping is gone before memory is freed
         self.bufs, self.flags, self.field = [], None, None
         for ptr, _ in self._own:
-            self.peers.free(ptr)
+            try:
+                self.peers.free(ptr)
+            except Exception as exc:  # noqa: BLE001
+                failed = failed or exc
         self._own = []
+        if failed is not None:
+            raise failed
 
 
 class ShardedConvolver:

@@ -485,3 +485,94 @@ def test_slabs_thinner_than_the_kernel_reach_are_refused():
     with pytest.raises(ValueError, match="non-adjacent"):
         SlabPlan(ny=64, nx=8, world=8, rank=0, reach=32, periodic_y=False).validate()
     SlabPlan(ny=64, nx=8, world=2, rank=0, reach=32, periodic_y=False).validate()
+
+
+# ---------------------------------------------------------------------------------------------
+# A peer set-up that fails on ONE rank must end on EVERY rank, with everything released, so that
+# the caller can fall back to the NCCL exchange consistently (PeerMemoryUnavailable).
+class _BrokenPeers(SharedMemoryPeers):
+    """Fails on one rank, in `alloc` (after `fail_after` successful calls) or in `open`."""
+
+    live = 0          # segments this process holds (allocated or mapped)
+
+    def __init__(self, rank, broken_rank, where, fail_after=2):
+        super().__init__()
+        self.broken = rank == broken_rank
+        self.where, self.left = where, fail_after
+
+    def _maybe_fail(self, where):
+        if self.broken and self.where == where:
+            if self.left == 0:
+                raise RuntimeError(f"no peer access ({where})")
+            self.left -= 1
+
+    def alloc(self, nbytes):
+        self._maybe_fail("alloc")
+        return super().alloc(nbytes)
+
+    def open(self, handle):
+        self._maybe_fail("open")
+        return super().open(handle)
+
+
+def _broken_peer_worker(rank, world, port, where, queue):
+    try:
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        import oracle
+        from rlic_b200.sharded import PeerMemoryUnavailable, ShardedConvolver
+
+        ny, nx, klen = 96, 19, 9
+        rng = np.random.default_rng(3)
+        tex = rng.random((ny, nx)).astype(np.float32)
+        u = (rng.random((ny, nx)) - 0.5).astype(np.float32)
+        v = (rng.random((ny, nx)) - 0.5).astype(np.float32)
+        kernel = (rng.random(klen) + 0.1).astype(np.float32)
+        peers = _BrokenPeers(rank, world - 1, where)
+        sc = ShardedConvolver(ny, nx, kernel=kernel, ops=_make_ops("emulated kernels"), exchange="peer", peers=peers)
+        mine = slice(sc.plan.row0, sc.plan.row1)
+        message = None
+        try:
+            sc.set_field(torch.from_numpy(u[mine].copy()), torch.from_numpy(v[mine].copy()))
+        except PeerMemoryUnavailable as exc:
+            message = str(exc)
+        assert message is not None, "the broken set-up went unnoticed on this rank"
+        assert f"rank {world - 1}: RuntimeError: no peer access ({where})" in message
+        assert not peers._segments, "segments left allocated or mapped after the failed set-up"
+        assert sc._peer is None
+        # ... and the fallback every rank takes gives the right answer
+        ops = _make_ops("emulated kernels")
+        ops.poison_halos = True
+        sc = ShardedConvolver(ny, nx, kernel=kernel, ops=ops, exchange="nccl")
+        sc.set_field(torch.from_numpy(u[mine].copy()), torch.from_numpy(v[mine].copy()))
+        got = sc.convolve(torch.from_numpy(tex[mine].copy()), iterations=3).numpy()
+        want = oracle.convolve(tex, u, v, kernel=kernel, iterations=3)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, bool(np.array_equal(got, want[mine])))
+        if rank == 0:
+            queue.put(("ok", gathered))
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:
+        queue.put(("error", f"rank {rank}:\n{traceback.format_exc()}"))
+        raise
+
+
+@pytest.mark.parametrize("world, where", [(2, "alloc"), (3, "open")])
+def test_a_peer_set_up_that_fails_on_one_rank_ends_on_every_rank(world, where):
+    ctx = mp.get_context("spawn")
+    queue = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_broken_peer_worker, args=(r, world, port, where, queue)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    try:
+        status, payload = queue.get(timeout=120)
+    finally:
+        for pr in procs:
+            pr.join(timeout=60)
+            if pr.is_alive():
+                pr.terminate()
+    assert status == "ok", payload
+    assert all(payload), f"ranks with mismatching slabs after the fallback: {payload}"
