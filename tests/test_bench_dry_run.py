@@ -253,6 +253,8 @@ def _multi_rank_worker(rank, world, port, exchange, queue):
     import traceback
 
     try:
+        refused = exchange == "peer refused"                 # a box whose GPUs cannot map each other's memory
+        exchange = "peer" if refused else exchange
         os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), LOCAL_RANK=str(rank),
                           WORLD_SIZE=str(world), RLIC_B200_EXCHANGE=exchange)
         import torch.distributed as dist
@@ -291,8 +293,11 @@ def _multi_rank_worker(rank, world, port, exchange, queue):
             def __init__(self, *a, **kw):
                 ops = stand_ins._make_ops("emulated kernels, grouped walk")
                 ops.poison_halos = kw.get("exchange") != "peer"
-                super().__init__(*a, ops=ops,
-                                 peers=stand_ins.SharedMemoryPeers() if kw.get("exchange") == "peer" else None, **kw)
+                peers = None
+                if kw.get("exchange") == "peer":
+                    peers = (stand_ins._BrokenPeers(rank, world - 1, "open") if refused
+                             else stand_ins.SharedMemoryPeers())
+                super().__init__(*a, ops=ops, peers=peers, **kw)
 
         sharded.ShardedConvolver = Convolver
         sharded.pinned_empty = lambda shape, dtype: np.empty(shape, dtype=dtype)
@@ -308,7 +313,7 @@ def _multi_rank_worker(rank, world, port, exchange, queue):
         raise
 
 
-@pytest.mark.parametrize("exchange", ["peer", "nccl"])
+@pytest.mark.parametrize("exchange", ["peer", "nccl", "peer refused"])
 def test_multi_gpu_arm_builds_its_line_over_gloo(exchange):
     import socket
 
@@ -335,7 +340,12 @@ def test_multi_gpu_arm_builds_its_line_over_gloo(exchange):
     assert line["n_gpus"] == 2 and line["scaling"] == "weak" and line["steps"] == 2 and line["value"] > 0
     assert line["config"]["image"] == [512, 256] and "row slabs over 2 GPUs" in line["config"]["workload"]
     assert len(line["ms_per_step_per_rank"]) == 2 and max(line["ms_per_step_per_rank"]) <= line["ms_per_step"] * 1.0001
-    assert line["e2e"]["exchange"] == exchange and line["e2e"]["value"] > 0 and "host_link" in line["e2e"]
+    if exchange == "peer refused":      # every rank fell back to the NCCL exchange, and the line says why
+        assert line["e2e"]["exchange"] == "nccl"
+        assert line["e2e"]["exchange_fallback"].startswith("peer -> nccl: rank 1: RuntimeError: no peer access")
+    else:
+        assert line["e2e"]["exchange"] == exchange and "exchange_fallback" not in line["e2e"]
+    assert line["e2e"]["value"] > 0 and "host_link" in line["e2e"]
     assert line["e2e"]["h2d_bytes_per_step"] == 2 * (3 * 4 * 256 * 256 + 4 * bench.TAPS)
     assert line["cpu_baseline"] is None and "every_pass_walks" not in line
     # every rank's first and last 64 rows of the five-pass result, against the oracle
