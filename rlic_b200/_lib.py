@@ -59,16 +59,19 @@ def _check_inputs(texture, u, v, kernel, uv_mode, boundaries, iterations, defer_
         add(ValueError(f"Invalid uv_mode {uv_mode!r}. Expected one of {_KNOWN_UV_MODES}"))
 
     named = (("texture", texture), ("u", u), ("v", v), ("kernel", kernel))
-    expectation = (
-        "Expected texture, u, v and kernel with identical dtype, "
-        f"from {_SUPPORTED_DTYPES}. Got "
-        + ", ".join(f"{name}.dtype={arr.dtype!r}" for name, arr in named)
-    )
+
+    def expectation() -> str:      # built only when it is needed: four dtype reprs cost more than the rest
+        return (
+            "Expected texture, u, v and kernel with identical dtype, "
+            f"from {_SUPPORTED_DTYPES}. Got "
+            + ", ".join(f"{name}.dtype={arr.dtype!r}" for name, arr in named)
+        )
+
     seen = {arr.dtype for _, arr in named}
     if rejected := seen.difference(_SUPPORTED_DTYPES):
-        add(TypeError(f"Found unsupported data type(s): {list(rejected)}. {expectation}"))
+        add(TypeError(f"Found unsupported data type(s): {list(rejected)}. {expectation()}"))
     if len(seen) != 1:
-        add(TypeError(f"Data types mismatch. {expectation}"))
+        add(TypeError(f"Data types mismatch. {expectation()}"))
 
     if texture.ndim != 2:
         add(
