@@ -541,6 +541,19 @@ def run_ours(args) -> dict:
         "note": "achieved = (3*(L-1)+2)*4 gather bytes per pixel x pixels per launch / mean launch time",
     }
 
+    if world > 1:
+        # one figure for the whole call here: the strips, the exchange and the interior of a pass
+        # are several launches, so the call's passes are timed together and averaged
+        if getattr(sc, "_call_paths", False):
+            roofline["kernel"] = (f"mean over the {ITERATIONS} passes of a call on this GPU's slab: pass 1 walks and "
+                                  "records (lic_pass_kernel<float,...,REC>), the others replay (lic_replay_kernel), "
+                                  "each as two edge strips + interior with the halo exchange fused into the strips' "
+                                  "stores; the N = 1 line has one roofline object per kernel")
+            roofline["note"] = ("achieved = section 8(d)'s bytes of the REFERENCE pass, (3*(L-1)+2)*4 per pixel, over "
+                                "the mean pass time: a replayed pass moves fewer (the N = 1 line's roofline.replay)")
+        else:
+            roofline["kernel"] = (f"mean over the {ITERATIONS} passes of a call on this GPU's slab "
+                                  "(lic_pass_kernel<float,...>: two edge strips + interior per pass, halo exchange included)")
     if world == 1 and replay:
         groups = 2 * ((TAPS // 2 + 31) // 32)
         replay_bytes = (TAPS - 1) * 4 + 4 + 4 + 3 * 4 * groups      # gathers + centre + store + three planes per group

@@ -354,3 +354,4 @@ def test_multi_gpu_arm_builds_its_line_over_gloo(exchange):
     assert [b["rows"] for pair in parity["per_rank"] for b in pair] == [[0, 64], [192, 256], [256, 320], [448, 512]]
     assert all(b["bit_equal"] and b["mismatches"] == 0 for pair in parity["per_rank"] for b in pair)
     assert "error" not in line["roofline"].get("issue", {})
+    assert "pass 1 walks and records" in line["roofline"]["kernel"] and "replay" not in line["roofline"]
