@@ -4,9 +4,12 @@
     python tools/run_reference_tests.py [--reference /root/reference] [--backend native|oracle|emulation] [pytest args]
 
 The files are read where they lie (nothing of the reference is copied); its conftest.py is not
-loaded (it imports `runtime_introspect`, a reporting-only dependency that is not installed here),
-and tests/test_regressions.py is left out (it needs vectorplot, which is not installable here;
-tests/test_regressions.py of this repository restates it against exact arithmetic).
+loaded (it imports `runtime_introspect`, a reporting-only dependency that is not installed here).
+tests/test_regressions.py compares with vectorplot, which is not installable here: unless the real
+package is importable, a stand-in `vectorplot.lic_internal.line_integral_convolution` is put in its
+place -- the exact rational-arithmetic streamline tracer of tests/regression_cases.py, which sums
+the way vectorplot's loop does -- so that the reference's file still runs as written, at its own
+tolerances (rtol 1.5e-7, atol 1e-6); the output says which of the two was used.
 
 What computes behind `rlic.convolve` (everything in front of it -- signature, validation, error
 messages, boundary handling, dtype dispatch -- is rlic_b200's own Python layer in all cases):
@@ -80,6 +83,27 @@ def main() -> int:
             return compute(c(texture), c(u), c(v), c(kernel), mode, boundaries, int(iterations))
 
         _core.convolve_f32 = _core.convolve_f64 = stand_in
+
+    if args.backend != "native" or _core.device_count() >= 1:
+        files.append("test_regressions.py")
+        try:
+            import vectorplot.lic_internal  # noqa: F401
+            print("test_regressions.py: against the real vectorplot")
+        except ImportError:
+            import types
+
+            import regression_cases
+
+            def line_integral_convolution(u, v, texture, kernel, polarization):
+                return regression_cases.exact_streamline_sum(texture, u, v, kernel,
+                                                             "polarization" if polarization else "velocity")
+
+            package, module = types.ModuleType("vectorplot"), types.ModuleType("vectorplot.lic_internal")
+            module.line_integral_convolution = line_integral_convolution
+            package.lic_internal = module
+            sys.modules["vectorplot"], sys.modules["vectorplot.lic_internal"] = package, module
+            print("test_regressions.py: vectorplot is not installed; the exact-arithmetic tracer of "
+                  "tests/regression_cases.py stands in for its line_integral_convolution")
 
     sys.modules["rlic"] = rlic_b200
     for sub in ("_boundaries", "_lib", "_typing"):
