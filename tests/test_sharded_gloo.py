@@ -295,6 +295,95 @@ def _free_port() -> int:
         return s.getsockname()[1]
 
 
+# ---------------------------------------------------------------------------------------------
+# The ranks of these tests are three long-lived processes: starting a process and importing
+# torch in it takes four to five seconds, and the thirty-odd cases below would spend four minutes
+# doing only that.  Every case still gets a fresh process group (its own port, created and
+# destroyed by the worker function) and fresh ops / peer objects; a case that fails or times out
+# takes the pool down with it, so that the next one starts from new processes.
+def _rank_loop(tasks, results):
+    while True:
+        job = tasks.get()
+        if job is None:
+            return
+        name, args = job
+        rank = args[0]
+        try:
+            globals()[name](*args[:4], results, *args[4:])
+            results.put(("done", rank))
+        except BaseException:                       # the worker has reported it; this process is done for
+            results.put(("died", rank))
+            return
+
+
+class _RankPool:
+    SIZE = 3
+
+    def __init__(self):
+        ctx = mp.get_context("spawn")
+        self.results = ctx.Queue()
+        self.tasks = [ctx.Queue() for _ in range(self.SIZE)]
+        self.procs = [ctx.Process(target=_rank_loop, args=(t, self.results), daemon=True) for t in self.tasks]
+        for pr in self.procs:
+            pr.start()
+
+    def stop(self, kill=False):
+        for t, pr in zip(self.tasks, self.procs):
+            if not kill:
+                t.put(None)
+        for pr in self.procs:
+            if not kill:
+                pr.join(timeout=20)
+            if pr.is_alive():
+                pr.terminate()
+                pr.join(timeout=20)
+
+
+_pool = None
+
+
+def _run_ranks(worker, world, args, timeout):
+    """Runs `worker(rank, world, port, *args[:1], queue, *args[1:])` on `world` ranks of the pool and
+    returns what rank 0 reported: ("ok", payload) or ("error", traceback)."""
+    import queue as queue_errors
+    import time
+
+    global _pool
+    if _pool is None:
+        _pool = _RankPool()
+    pool, port = _pool, _free_port()
+    for r in range(world):
+        pool.tasks[r].put((worker.__name__, (r, world, port, *args)))
+    report, finished, deadline = None, 0, time.monotonic() + timeout
+    try:
+        while finished < world:
+            kind, payload = pool.results.get(timeout=max(0.1, deadline - time.monotonic()))
+            if kind in ("done", "died"):
+                finished += 1
+                if kind == "died":
+                    report = report if report and report[0] == "error" else ("error", f"rank {payload} died")
+            elif kind == "error" or report is None:
+                report = (kind, payload)
+            if report is not None and report[0] == "error":     # the others may be waiting for the failed rank
+                deadline = min(deadline, time.monotonic() + 10)
+    except queue_errors.Empty:
+        if report is None or report[0] != "error":
+            report = ("error", f"timed out after {timeout} s; last report: {report}")
+    if report is None or report[0] != "ok":
+        pool.stop(kill=True)
+        _pool = None
+    return report or ("error", "no rank reported")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _rank_pool_lifetime():
+    yield
+    global _pool
+    if _pool is not None:
+        _pool.stop()
+        _pool = None
+
+
 CASES = {
     "closed-2": (2, (40, 23, 9, "closed", "velocity", 3, np.float64)),
     "periodic-ring-2": (2, (36, 17, 11, "periodic", "velocity", 3, np.float32)),
@@ -307,19 +396,7 @@ CASES = {
 @pytest.mark.parametrize("name", CASES)
 def test_sharded_equals_unsharded(name, ops_kind):
     world, case = CASES[name]
-    ctx = mp.get_context("spawn")
-    queue = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, case, queue, ops_kind)) for r in range(world)]
-    for pr in procs:
-        pr.start()
-    try:
-        status, payload = queue.get(timeout=120)
-    finally:
-        for pr in procs:
-            pr.join(timeout=60)
-            if pr.is_alive():
-                pr.terminate()
+    status, payload = _run_ranks(_worker, world, (case, ops_kind), timeout=120)
     assert status == "ok", payload
     assert all(payload), f"ranks with mismatching slabs: {payload}"
 
@@ -345,20 +422,7 @@ def test_fused_peer_exchange_equals_unsharded(name, ops_kind):
     named shared memory) and the halo / free counters order the passes; two calls in a row,
     so that the counters and the start-of-call handshake are exercised too."""
     world, case = PEER_CASES[name]
-    ctx = mp.get_context("spawn")
-    queue = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, case, queue, ops_kind, "peer", 2))
-             for r in range(world)]
-    for pr in procs:
-        pr.start()
-    try:
-        status, payload = queue.get(timeout=180)
-    finally:
-        for pr in procs:
-            pr.join(timeout=60)
-            if pr.is_alive():
-                pr.terminate()
+    status, payload = _run_ranks(_worker, world, (case, ops_kind, "peer", 2), timeout=180)
     assert status == "ok", payload
     assert all(payload), f"ranks with mismatching slabs: {payload}"
 
@@ -427,19 +491,7 @@ def test_host_slabs_in_host_slabs_out(name, exchange):
     if exchange == "nccl" and name not in ("closed-2", "y-periodic-3"):
         pytest.skip("the unpipelined path is covered by two cases")
     world, case = HOST_CASES[name]
-    ctx = mp.get_context("spawn")
-    queue = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_host_worker, args=(r, world, port, case, queue, exchange)) for r in range(world)]
-    for pr in procs:
-        pr.start()
-    try:
-        status, payload = queue.get(timeout=180)
-    finally:
-        for pr in procs:
-            pr.join(timeout=60)
-            if pr.is_alive():
-                pr.terminate()
+    status, payload = _run_ranks(_host_worker, world, (case, exchange), timeout=180)
     assert status == "ok", payload
     assert all(payload), f"ranks with mismatching slabs: {payload}"
 
@@ -561,18 +613,6 @@ def _broken_peer_worker(rank, world, port, where, queue):
 
 @pytest.mark.parametrize("world, where", [(2, "alloc"), (3, "open")])
 def test_a_peer_set_up_that_fails_on_one_rank_ends_on_every_rank(world, where):
-    ctx = mp.get_context("spawn")
-    queue = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_broken_peer_worker, args=(r, world, port, where, queue)) for r in range(world)]
-    for pr in procs:
-        pr.start()
-    try:
-        status, payload = queue.get(timeout=120)
-    finally:
-        for pr in procs:
-            pr.join(timeout=60)
-            if pr.is_alive():
-                pr.terminate()
+    status, payload = _run_ranks(_broken_peer_worker, world, (where,), timeout=120)
     assert status == "ok", payload
     assert all(payload), f"ranks with mismatching slabs after the fallback: {payload}"
