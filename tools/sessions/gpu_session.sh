@@ -4,7 +4,7 @@
 # gpurun_out/ (merged back by gpurun).  Nothing here changes clocks or kills by pattern.
 #
 #   python __graft_entry__.py && sh tools/build_lab.sh      # here, without a GPU: the built files travel
-#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/gpu_session.sh'
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/sessions/gpu_session.sh'
 #
 # Steps (each independent; a failure is logged and the script goes on):
 #   1  the -m gpu suite
@@ -15,7 +15,7 @@
 #   4  every BASELINE configuration (tools/bench_configs.py), default and wavefront
 #   5  ncu launch list of one bench step, and a full capture of the f64 pass kernel
 set -u
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 OUT=gpurun_out/session
 mkdir -p "$OUT"
 step() {   # step <seconds> <name> <command...>

@@ -2,14 +2,14 @@
 # Two-GPU session (round 2): the multi-GPU paths on real hardware, each step with its own
 # time limit, output under gpurun_out/session2/ (merged back by gpurun).
 #
-#   /usr/local/graft/bin/gpurun --gpus 2 --timeout 900 -- 'bash tools/gpu_session_2gpu.sh'
+#   /usr/local/graft/bin/gpurun --gpus 2 --timeout 900 -- 'bash tools/sessions/gpu_session_2gpu.sh'
 #
 #   1  the two-GPU tests: NCCL halo exchange, fused peer exchange (device and host-slab
 #      pipeline), single-process multi-device slabs, batch over every visible device
 #   2  bench.py --gpus 2 with the NCCL exchange, then with RLIC_B200_EXCHANGE=peer
 #   3  C4 strong scaling on one and two GPUs (tools/bench_c4_scaling.py), both exchanges
 set -u
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 OUT=gpurun_out/session2
 mkdir -p "$OUT"
 step() {   # step <seconds> <name> <command...>

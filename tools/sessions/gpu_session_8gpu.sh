@@ -3,7 +3,7 @@
 # time limit, output under gpurun_out/session8/ (merged back by gpurun).  An 8-GPU call is
 # charged 8x: everything here is sized to finish in about five minutes.
 #
-#   /usr/local/graft/bin/gpurun --gpus 8 --timeout 700 -- 'bash tools/gpu_session_8gpu.sh'
+#   /usr/local/graft/bin/gpurun --gpus 8 --timeout 700 -- 'bash tools/sessions/gpu_session_8gpu.sh'
 #
 #   1  bench.py --gpus 8 three times with the fused peer exchange (spread), once with NCCL,
 #      and --gpus 4 with the peer exchange
@@ -12,7 +12,7 @@
 #   3  C5: 4096 fields over 8 GPUs (tools/bench_c5_batch.py)
 #   4  the multi-GPU tests on this box
 set -u
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 OUT=gpurun_out/session8
 mkdir -p "$OUT"
 step() {   # step <seconds> <name> <command...>

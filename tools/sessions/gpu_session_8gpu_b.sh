@@ -3,7 +3,7 @@
 # time-out check, one clock sampler per job), the NCCL exchange beside it, the per-rank phase
 # table, and the host-link floor (in the bench lines: e2e.host_link).
 set -u
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 OUT=gpurun_out/session8b
 mkdir -p "$OUT"
 step() { local limit=$1 name=$2; shift 2; echo "=== $name" | tee -a "$OUT/summary.txt"; local t0=$SECONDS

@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 # Diagnostics for the peer exchange at N GPUs (default 4) + the lab's new candidates on GPU 0.
 set -u
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 N=${1:-4}
 OUT=gpurun_out/diag$N
 mkdir -p "$OUT"

@@ -2,7 +2,7 @@
 # One-GPU check of the late additions: the whole GPU suite (histogram equalisation, small-image
 # kernel), the configurations (C1 through the raw ABI too), the launch list of a C1 call.
 set -u
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 OUT=gpurun_out/final1
 mkdir -p "$OUT"
 step() { local limit=$1 name=$2; shift 2; echo "=== $name" | tee -a "$OUT/summary.txt"; local t0=$SECONDS

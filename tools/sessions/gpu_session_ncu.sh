@@ -2,9 +2,9 @@
 # One-GPU session: the whole GPU suite, the bench line, the lab's latest candidates, and the ncu
 # evidence of the kernels that ship (launch list + one full capture each of the f32 velocity,
 # f64 velocity (C1) and f64 polarization (C3) pass kernels).  Output under gpurun_out/ncu/.
-#   /usr/local/graft/bin/gpurun --timeout 1200 -- 'bash tools/gpu_session_ncu.sh'
+#   /usr/local/graft/bin/gpurun --timeout 1200 -- 'bash tools/sessions/gpu_session_ncu.sh'
 set -u
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 OUT=gpurun_out/ncu
 mkdir -p "$OUT"
 step() { local limit=$1 name=$2; shift 2; echo "=== $name" | tee -a "$OUT/summary.txt"; local t0=$SECONDS

@@ -2,9 +2,9 @@
 # One-GPU session for the recorded-path replay (PathPlanes in lic_walk.cuh): the whole GPU suite,
 # the bench line with and without replay, the lab's record / replay variants, every configuration,
 # and the ncu evidence of the two kernels of a step (launch list + one full capture each).
-#   /usr/local/graft/bin/gpurun --timeout 1100 -- 'bash tools/gpu_session_replay.sh'
+#   /usr/local/graft/bin/gpurun --timeout 1100 -- 'bash tools/sessions/gpu_session_replay.sh'
 set -u
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 OUT=gpurun_out/${SESSION_NAME:-replay}
 mkdir -p "$OUT"
 step() { local limit=$1 name=$2; shift 2; echo "=== $name" | tee -a "$OUT/summary.txt"; local t0=$SECONDS

@@ -1,9 +1,9 @@
 #!/usr/bin/env bash
 # One-GPU check after the host-path changes (tapered row bands, conversions beside the copies):
 # the whole GPU suite, the bench line, the host path's trace, every configuration.
-#   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/gpu_session_replay3.sh'
+#   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/sessions/gpu_session_replay3.sh'
 set -u
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 OUT=gpurun_out/${SESSION_NAME:-replay3}
 mkdir -p "$OUT"
 step() { local limit=$1 name=$2; shift 2; echo "=== $name" | tee -a "$OUT/summary.txt"; local t0=$SECONDS

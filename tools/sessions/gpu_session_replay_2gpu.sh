@@ -2,9 +2,9 @@
 # Two-GPU session for the recorded-path replay: the two-GPU tests, bench.py --gpus 2 with both
 # exchanges, the per-rank phase table, C4 strong scaling at 1 and 2 GPUs, plus -- on one GPU of
 # the box -- the bench line, the host path's trace and the ncu capture of the replay kernel.
-#   /usr/local/graft/bin/gpurun --gpus 2 --timeout 900 -- 'bash tools/gpu_session_replay_2gpu.sh'
+#   /usr/local/graft/bin/gpurun --gpus 2 --timeout 900 -- 'bash tools/sessions/gpu_session_replay_2gpu.sh'
 set -u
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 OUT=gpurun_out/${SESSION_NAME:-replay_2gpu}
 mkdir -p "$OUT"
 step() { local limit=$1 name=$2; shift 2; echo "=== $name" | tee -a "$OUT/summary.txt"; local t0=$SECONDS

@@ -1,9 +1,9 @@
 #!/usr/bin/env bash
 # Eight-GPU session for the recorded-path replay: bench.py --gpus 8 as the driver runs it (twice:
 # spread), --gpus 4 and the same box's --gpus 1, C4 strong scaling on 8 GPUs, C5 on 8 GPUs.
-#   /usr/local/graft/bin/gpurun --gpus 8 --timeout 400 -- 'bash tools/gpu_session_replay_8gpu.sh'
+#   /usr/local/graft/bin/gpurun --gpus 8 --timeout 400 -- 'bash tools/sessions/gpu_session_replay_8gpu.sh'
 set -u
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 OUT=gpurun_out/${SESSION_NAME:-replay_8gpu}
 mkdir -p "$OUT"
 step() { local limit=$1 name=$2; shift 2; echo "=== $name" | tee -a "$OUT/summary.txt"; local t0=$SECONDS

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Turns the output of tools/gpu_session.sh / gpu_session_2gpu.sh (gpurun_out/session*/) into
+"""Turns the output of tools/sessions/gpu_session.sh / gpu_session_2gpu.sh (gpurun_out/session*/) into
 the artefacts that get committed under profiles/ and prints the decisions they support.
 
     python tools/summarise_session.py [--round 2] [--session gpurun_out/session]
@@ -51,7 +51,7 @@ def main() -> None:
     args = ap.parse_args()
     src = ROOT / args.session
     if not src.is_dir():
-        raise SystemExit(f"{src} does not exist: run tools/gpu_session.sh through gpurun first")
+        raise SystemExit(f"{src} does not exist: run tools/sessions/gpu_session.sh through gpurun first")
     dst = ROOT / "profiles"
     tag = f"r{args.round}_{src.name}"
 
