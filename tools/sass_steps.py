@@ -64,12 +64,13 @@ def demangle(name: str) -> str:
 
 
 def describe(label: str) -> str:
-    """<T, POL, Taps, Idx, TW, TH, UNROLL, MINB, FLAVOR, ADMIT, BRANCHLESS, WALK> -> short text"""
+    """<T, POL, Taps, Idx, TW, TH, UNROLL, MINB, FLAVOR, ADMIT, BRANCHLESS, WALK, REC> -> short text"""
     args = [a.strip() for a in re.sub(r"ParamTaps<(\w+), (\d+)>", r"ParamTaps", label.strip("<>")).split(",")]
     t, pol = args[0], args[1] == "true"
     unroll, minb, flavor, admit, walk = args[6], args[7], args[8], args[9], args[11]
+    rec = " recording" if len(args) > 12 and args[12] == "true" else ""
     return (f"{'f32' if t == 'float' else 'f64'} {'pol' if pol else 'vel'} unroll {unroll} blocks {minb} "
-            f"flavor {flavor} admit {admit} walk {walk:>2}")
+            f"flavor {flavor} admit {admit} walk {walk:>2}{rec}")
 
 
 def pipe_of(op: str) -> str:
@@ -110,7 +111,9 @@ def main() -> None:
         label = demangle(name)
         if not label.startswith("<"):
             continue
-        steps_per_group = int([a.strip() for a in label.split(",")][-6])   # UNROLL
+        # <T, POL, Taps, Idx, TW, TH, UNROLL, ...>: counted from the front (the list grows at the back)
+        steps_per_group = int([a.strip() for a in re.sub(r"ParamTaps<(\w+), (\d+)>", "ParamTaps",
+                                                          label.strip("<>")).split(",")][6])
         loops = sorted(loops_of(body), key=lambda lh: lh[0] - lh[1])[:2]    # the two main loops
         per_step, fp64, local = [], [], 0
         mix = collections.Counter()

@@ -27,6 +27,15 @@ template <typename T, bool POL, typename PT> const void *tuned_grouped()
     return variant<T, POL, PT, Tn::walk, Tn::walk_flavor>();
 }
 
+// the recording walk as launch_one() instantiates it (lic_api.cu: record_min_blocks)
+template <typename T, bool POL, typename PT> const void *tuned_recording()
+{
+    using Tn = Tune<T, POL>;
+    constexpr int minb = Tn::walk_min_blocks > 6 ? 6 : Tn::walk_min_blocks;
+    return (const void *)&lic_pass_kernel<T, POL, PT, int, kTileW, kTileH, Tn::walk_unroll, minb, Tn::walk_flavor,
+                                          Tn::walk_admit, true, Tn::walk, true>;
+}
+
 #define SWEEP(T, POL, PT, FLAVOR) \
     variant<T, POL, PT, 1, FLAVOR>(), variant<T, POL, PT, 3, FLAVOR>(), variant<T, POL, PT, 5, FLAVOR>(), \
     variant<T, POL, PT, 7, FLAVOR>(), variant<T, POL, PT, 9, FLAVOR>(), variant<T, POL, PT, 11, FLAVOR>()
@@ -42,6 +51,8 @@ const void *table[] = {
     shipped<double, false, PT64>(), shipped<double, true, PT64>(),
     tuned_grouped<float, false, PT32>(), tuned_grouped<float, true, PT32>(),
     tuned_grouped<double, false, PT64>(), tuned_grouped<double, true, PT64>(),
+    tuned_recording<float, false, PT32>(), tuned_recording<float, true, PT32>(),
+    tuned_recording<double, false, PT64>(), tuned_recording<double, true, PT64>(),
     SWEEP(float, false, PT32, 1), SWEEP(float, false, PT32, 2), SWEEP(float, false, PT32, 0),
     SWEEP(float, true, PT32, 0), SWEEP(float, true, PT32, 2),
     SWEEP(double, false, PT64, 0), SWEEP(double, false, PT64, 2),
