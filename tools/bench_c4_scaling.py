@@ -36,7 +36,7 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 
 from rlic_b200 import _core, workloads  # noqa: E402
-from rlic_b200.sharded import ShardedConvolver  # noqa: E402
+from rlic_b200.sharded import PeerMemoryUnavailable, ShardedConvolver  # noqa: E402
 
 
 def image_rows(n: int, r0: int, r1: int):
@@ -93,7 +93,13 @@ def main() -> None:
     r0, r1 = sc.plan.row0, sc.plan.row1
     tex, u, v = image_rows(n, r0, r1)
     d_tex, d_u, d_v = (torch.from_numpy(a).to(dev) for a in (tex, u, v))
-    sc.set_field(d_u, d_v)
+    try:
+        sc.set_field(d_u, d_v)
+    except PeerMemoryUnavailable as exc:      # raised on every rank alike: go on with NCCL messages
+        if rank == 0:
+            print(f"peer exchange unavailable ({exc}); using exchange='nccl'", file=sys.stderr)
+        sc = ShardedConvolver(n, n, kernel=kernel, boundaries="closed", exchange="nccl")
+        sc.set_field(d_u, d_v)
     del d_u, d_v
 
     out = sc.convolve(d_tex, iterations=args.iterations)   # warm-up
