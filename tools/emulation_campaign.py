@@ -6,6 +6,7 @@ arithmetic builds and both index widths.  Bitwise comparison, NaN payloads inclu
 
     python tools/emulation_campaign.py <first seed> <seconds> [walk]
     python tools/emulation_campaign.py <first seed> <seconds> replay    (recorded paths: record + replay kernels)
+    python tools/emulation_campaign.py <first seed> <seconds> bands     (the same, every pass cut into its own random row bands)
 
 `walk` (default 0) selects the formulation of the pass kernels: 0 per-step, 1 the grouped walk
 as the library dispatches it (rlic::Tune), "mix" picks per case among the per-step walk, the
@@ -15,7 +16,10 @@ Round 1: seeds 100000..233822 (133 823 cases, 300 s on 8 cores): 0 mismatches.
 Round 1, `mix` (grouped-walk formulations included): seeds 300000..464805 (164 806 cases, 600 s), 500000..534981
 (34 982, after the alignment-compare change) and 600000..1408645 (808 646 cases, 1800 s): 0 mismatches.
 Round 2, `replay` (recorded paths: the recording walk + either replay kernel, 2-4 iterations, kernels of 1-140 taps):
-seeds 2000000..2227474 (227 475 cases, 900 s): 0 mismatches.
+seeds 2000000..2227474 (227 475 cases, 900 s) and 3000000..3282116 (282 117 cases, 1500 s): 0 mismatches.
+Round 2, `bands` (the same with every pass cut into its own random row bands, as the host path and the slab drivers
+launch them): seeds 5100000..5255462 (155 463 cases, 800 s): 0 mismatches.
+Round 2, `mix` on the kernels as they ship at the end of the round: seeds 4000000..4258330 (258 331 cases, 800 s): 0 mismatches.
 """
 import sys, time
 from pathlib import Path
@@ -57,10 +61,34 @@ while time.time()-t0<budget:
         its=int(rng.integers(2,5)); klen=int(rng.integers(1,141))
         k=(rng.random(klen)-0.3).astype(dtype)
         how=dict(paths=[True,"staged"][int(rng.integers(2))])
-    elif walk_arg!="0": how=dict(walk=int(walk_arg))
+    elif walk_arg not in ("0","bands"): how=dict(walk=int(walk_arg))
     if how: branchless=True                      # the grouped walk exists for the default arithmetic
     if "flavor" in how: wide=False; klen=min(klen,60)   # explicit formulations: 32-bit indices only
     k=k[:klen]
+    if walk_arg=="bands":
+        # the host path and the slab drivers: every pass in its own random row bands (the record is written
+        # by one set of launches and read by others), replays by either kernel
+        from rlic_b200 import _core
+        its=int(rng.integers(2,5)); klen=int(rng.integers(1,100)); k=(rng.random(klen)-0.3).astype(dtype)
+        def bands():
+            cuts=sorted(set(int(c) for c in rng.integers(1,max(ny,2),size=int(rng.integers(0,4))) if 0<c<ny))
+            edges=[0,*cuts,ny]; return [(a,b-a) for a,b in zip(edges,edges[1:])]
+        with np.errstate(all="ignore"):
+            b=ke.Buffers(dtype,ny,nx,_core.wall_codes(walls),klen); b.pack_field(u,v); b.pad_texture(tex,0)
+            rec=b.path_record(klen); src=0
+            for it in range(its):
+                for rows in bands():
+                    if it==0: b.run_pass_paths(src,1-src,k,mode,1,rec,rows=rows,wide=wide)
+                    elif not (rng.integers(2) and b.run_pass_paths(src,1-src,k,mode,3,rec,rows=rows,wide=wide)):
+                        b.run_pass_paths(src,1-src,k,mode,2,rec,rows=rows,wide=wide)
+                src=1-src
+            got=b.unpad_texture(src)
+            want=oracle.convolve(tex,u,v,kernel=k,uv_mode=mode,boundaries=walls,iterations=its,variant=3)
+        n+=1
+        if not np.array_equal(got.view(np.uint8),want.view(np.uint8)):
+            bad+=1; print("MISMATCH seed",seed-1,dtype.__name__,(ny,nx),klen,mode,walls,its,"bands",flush=True)
+            if bad>10: break
+        continue
     with np.errstate(all="ignore"):
         got=ke.convolve(tex,u,v,kernel=k,uv_mode=mode,boundaries=walls,iterations=its,branchless=branchless,wide=wide,**how)
         want=oracle.convolve(tex,u,v,kernel=k,uv_mode=mode,boundaries=walls,iterations=its,variant=3 if branchless else 1)
