@@ -499,7 +499,7 @@ def run_ours(args) -> dict:
             del expected
     first_ms = sum(a.elapsed_time(m) for a, _, m in ev) / args.steps      # world == 1: the first pass alone
     later_ms = sum(m.elapsed_time(b) for _, b, m in ev) / args.steps / max(ITERATIONS - 1, 1)   # each of the others
-    per_rank_ms = None
+    per_rank_ms = solo_per_rank_ms = None
     if dist is not None:
         t = torch.tensor([total_ms, pass_ms], device=dev, dtype=torch.float64)
         # every rank's own device time per step travels with the line: `value` is their maximum,
@@ -512,6 +512,29 @@ def run_ours(args) -> dict:
         n_l = torch.tensor([launches], device=dev, dtype=torch.int64)
         dist.all_reduce(n_l)
         launches = int(n_l.item())
+        # The ranks of a sharded call advance in lock step (each pass waits for the neighbours'
+        # halos), so their times per step above agree whichever GPU sets the pace.  What tells a
+        # slow GPU apart is its speed ALONE: one walking pass over its own slab, no exchange, a
+        # few repetitions, every rank at once after the barrier that ended the timed region.
+        solo_ms = -1.0
+        try:
+            pads = sc._peer.bufs if sc._peer is not None else sc._work[1:3]
+            run_solo = lambda: sc.ops.pass_rows(pads[0], sc.field, pads[1], sc.plan, 0, sc.plan.nrows,  # noqa: E731
+                                                sc.taps, sc.mode, sc.walls)
+            run_solo()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for _ in range(3):
+                run_solo()
+            s1.record()
+            s1.synchronize()
+            solo_ms = s0.elapsed_time(s1) / 3
+        except Exception:  # noqa: BLE001 -- a diagnostic; the gather below must still be entered by every rank
+            solo_ms = -1.0
+        mine = [torch.zeros(1, device=dev, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(mine, torch.tensor([solo_ms], device=dev, dtype=torch.float64))
+        solo_per_rank_ms = [float(x.item()) for x in mine]
+        barrier()
     ms_per_step = total_ms / args.steps
     pixels_all = pixels_local * world
     value = pixels_all * ITERATIONS / (ms_per_step * 1e-3) / 1e6
@@ -786,6 +809,7 @@ def run_ours(args) -> dict:
     }
     if per_rank_ms is not None:
         line["ms_per_step_per_rank"] = per_rank_ms
+        line["solo_walking_pass_ms_per_rank"] = solo_per_rank_ms
     if every_pass_walks is not None:
         line["every_pass_walks"] = every_pass_walks
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -340,6 +340,7 @@ def test_multi_gpu_arm_builds_its_line_over_gloo(exchange):
     assert line["n_gpus"] == 2 and line["scaling"] == "weak" and line["steps"] == 2 and line["value"] > 0
     assert line["config"]["image"] == [512, 256] and "row slabs over 2 GPUs" in line["config"]["workload"]
     assert len(line["ms_per_step_per_rank"]) == 2 and max(line["ms_per_step_per_rank"]) <= line["ms_per_step"] * 1.0001
+    assert len(line["solo_walking_pass_ms_per_rank"]) == 2 and min(line["solo_walking_pass_ms_per_rank"]) > 0
     if exchange == "peer refused":      # every rank fell back to the NCCL exchange, and the line says why
         assert line["e2e"]["exchange"] == "nccl"
         assert line["e2e"]["exchange_fallback"].startswith("peer -> nccl: rank 1: RuntimeError: no peer access")
